@@ -1,0 +1,229 @@
+// ab_elemwise.cuh — hand-written kernel skeleton for one fused
+// Elemwise{Composite} node (reference: aesara/tensor/elemwise.py:835-1168 and
+// the loop generators of aesara/tensor/elemwise_cgen.py:228-462).
+//
+// The Python code generator (aesara_b200/codegen/elemwise.py) emits, in front
+// of this file:
+//     #define AB_NIN / AB_NOUT / AB_VEC
+//     #define AB_INPUTS(X)   X(0, float) X(1, float) ...        (k, element type)
+//     #define AB_OUTPUTS(X)  X(0, float) ...
+//     __device__ void ab_body(<in types...>, <out types&...>)   the scalar DAG
+//     #define AB_CALL_BODY(IN, OUT) ab_body(IN(0), IN(1), ..., OUT(0), ...)
+//
+// Three kernels per module, each in a vectorised and a scalar flavour:
+//   ab_ew_flat*  every operand is a contiguous run or a broadcast scalar
+//                (element stride 1 or 0) — the 128-bit streaming path;
+//   ab_ew_rows*  2-D [rows, cols] with inner stride 1/0 and arbitrary row
+//                stride (bias broadcast [1,H]+[B,H], column-slice views);
+//   ab_ew_nd     anything else: DimShuffle / broadcast / negative strides
+//                folded into index arithmetic (up to AB_MAX_DIMS merged dims).
+// HBM-bound by construction: each operand element is read/written once.
+#pragma once
+
+#define AB_NOPS (AB_NIN + AB_NOUT)
+
+struct AbEwParams {
+  long long n;                  // number of output elements
+  int ndim;                     // merged dims (ab_ew_nd), 1 (flat) or 2 (rows)
+  int pad_;
+  long long shape[AB_MAX_DIMS];
+  void* ptr[AB_NOPS];           // inputs, then outputs
+  long long stride[AB_NOPS][AB_MAX_DIMS];  // element strides, 0 = broadcast
+};
+
+#define AB_THREADS 256
+
+// ------------------------------------------------------------------ flat ------
+template <int VEC, int UNROLL>
+__device__ __forceinline__ void ab_ew_flat_impl(const AbEwParams& p) {
+  const long long nvec = p.n / VEC;
+  const long long gstride = (long long)gridDim.x * AB_THREADS;
+  long long v0 = (long long)blockIdx.x * AB_THREADS + threadIdx.x;
+
+#define AB_DECL_IN(k, T)                                         \
+  const T* ip##k = reinterpret_cast<const T*>(p.ptr[k]); \
+  const bool bc##k = (p.stride[k][0] == 0);                      \
+  T sc##k = T();                                                 \
+  if (bc##k) sc##k = ip##k[0];
+  AB_INPUTS(AB_DECL_IN)
+#undef AB_DECL_IN
+#define AB_DECL_OUT(k, T) T* op##k = reinterpret_cast<T*>(p.ptr[AB_NIN + k]);
+  AB_OUTPUTS(AB_DECL_OUT)
+#undef AB_DECL_OUT
+
+  for (; v0 < nvec; v0 += gstride * UNROLL) {
+#define AB_LD(k, T)                                               \
+  ab_pack<T, VEC> in##k[UNROLL];                                  \
+  _Pragma("unroll") for (int u = 0; u < UNROLL; ++u) {            \
+    const long long v = v0 + u * gstride;                         \
+    if (bc##k) {                                                  \
+      _Pragma("unroll") for (int e = 0; e < VEC; ++e) in##k[u].v[e] = sc##k; \
+    } else if (v < nvec) {                                        \
+      ab_load_pack<T, VEC>(in##k[u], ip##k + v * VEC);            \
+    }                                                             \
+  }
+    AB_INPUTS(AB_LD)
+#undef AB_LD
+#define AB_DO(k, T) ab_pack<T, VEC> out##k[UNROLL];
+    AB_OUTPUTS(AB_DO)
+#undef AB_DO
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (v0 + u * gstride < nvec) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+#define AB_IN_E(k) in##k[u].v[e]
+#define AB_OUT_E(k) out##k[u].v[e]
+          AB_CALL_BODY(AB_IN_E, AB_OUT_E);
+#undef AB_IN_E
+#undef AB_OUT_E
+        }
+      }
+    }
+#define AB_ST(k, T)                                               \
+  _Pragma("unroll") for (int u = 0; u < UNROLL; ++u) {            \
+    const long long v = v0 + u * gstride;                         \
+    if (v < nvec) ab_store_pack<T, VEC>(op##k + v * VEC, out##k[u]); \
+  }
+    AB_OUTPUTS(AB_ST)
+#undef AB_ST
+  }
+
+  // tail (n % VEC elements) by the first threads of block 0
+  if (VEC > 1 && blockIdx.x == 0) {
+    const long long t = nvec * VEC + threadIdx.x;
+    if (t < p.n) {
+#define AB_TIN(k, T) const T tin##k = bc##k ? sc##k : ip##k[t];
+      AB_INPUTS(AB_TIN)
+#undef AB_TIN
+#define AB_TOUT(k, T) T tout##k;
+      AB_OUTPUTS(AB_TOUT)
+#undef AB_TOUT
+#define AB_IN_E(k) tin##k
+#define AB_OUT_E(k) tout##k
+      AB_CALL_BODY(AB_IN_E, AB_OUT_E);
+#undef AB_IN_E
+#undef AB_OUT_E
+#define AB_TST(k, T) op##k[t] = tout##k;
+      AB_OUTPUTS(AB_TST)
+#undef AB_TST
+    }
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(AB_THREADS)
+ab_ew_flat_vec(const __grid_constant__ AbEwParams p) {
+  ab_ew_flat_impl<AB_VEC, AB_UNROLL>(p);
+}
+extern "C" __global__ void __launch_bounds__(AB_THREADS)
+ab_ew_flat(const __grid_constant__ AbEwParams p) {
+  ab_ew_flat_impl<1, 4>(p);
+}
+
+// ------------------------------------------------------------------ rows ------
+// shape = [rows, cols]; stride[k][1] in {0,1}; stride[k][0] arbitrary.
+// grid.x covers column vectors, grid.y strides over rows.
+template <int VEC, int UNROLL>
+__device__ __forceinline__ void ab_ew_rows_impl(const AbEwParams& p) {
+  const long long rows = p.shape[0];
+  const long long cvec = p.shape[1] / VEC;  // launcher guarantees divisibility
+  const long long cv = (long long)blockIdx.x * AB_THREADS + threadIdx.x;
+  if (cv >= cvec) return;
+#define AB_DECL_IN(k, T)                                               \
+  const T* ip##k = reinterpret_cast<const T*>(p.ptr[k]) + \
+                                (p.stride[k][1] ? cv * VEC : 0);      \
+  const long long rs##k = p.stride[k][0];                              \
+  const bool bc##k = (p.stride[k][1] == 0);
+  AB_INPUTS(AB_DECL_IN)
+#undef AB_DECL_IN
+#define AB_DECL_OUT(k, T)                                              \
+  T* op##k = reinterpret_cast<T*>(p.ptr[AB_NIN + k]) + cv * VEC;       \
+  const long long ors##k = p.stride[AB_NIN + k][0];
+  AB_OUTPUTS(AB_DECL_OUT)
+#undef AB_DECL_OUT
+
+  const long long rstep = gridDim.y;
+  for (long long r0 = blockIdx.y; r0 < rows; r0 += rstep * UNROLL) {
+#define AB_LD(k, T)                                               \
+  ab_pack<T, VEC> in##k[UNROLL];                                  \
+  _Pragma("unroll") for (int u = 0; u < UNROLL; ++u) {            \
+    const long long r = r0 + u * rstep;                           \
+    if (r < rows) {                                               \
+      if (bc##k) {                                                \
+        const T s = ip##k[r * rs##k];                             \
+        _Pragma("unroll") for (int e = 0; e < VEC; ++e) in##k[u].v[e] = s; \
+      } else {                                                    \
+        ab_load_pack<T, VEC>(in##k[u], ip##k + r * rs##k);        \
+      }                                                           \
+    }                                                             \
+  }
+    AB_INPUTS(AB_LD)
+#undef AB_LD
+#define AB_DO(k, T) ab_pack<T, VEC> out##k[UNROLL];
+    AB_OUTPUTS(AB_DO)
+#undef AB_DO
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (r0 + u * rstep < rows) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+#define AB_IN_E(k) in##k[u].v[e]
+#define AB_OUT_E(k) out##k[u].v[e]
+          AB_CALL_BODY(AB_IN_E, AB_OUT_E);
+#undef AB_IN_E
+#undef AB_OUT_E
+        }
+      }
+    }
+#define AB_ST(k, T)                                               \
+  _Pragma("unroll") for (int u = 0; u < UNROLL; ++u) {            \
+    const long long r = r0 + u * rstep;                           \
+    if (r < rows) ab_store_pack<T, VEC>(op##k + r * ors##k, out##k[u]); \
+  }
+    AB_OUTPUTS(AB_ST)
+#undef AB_ST
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(AB_THREADS)
+ab_ew_rows_vec(const __grid_constant__ AbEwParams p) {
+  ab_ew_rows_impl<AB_VEC, AB_UNROLL>(p);
+}
+extern "C" __global__ void __launch_bounds__(AB_THREADS)
+ab_ew_rows(const __grid_constant__ AbEwParams p) {
+  ab_ew_rows_impl<1, 4>(p);
+}
+
+// -------------------------------------------------------------------- nd ------
+extern "C" __global__ void __launch_bounds__(AB_THREADS)
+ab_ew_nd(const __grid_constant__ AbEwParams p) {
+  const long long gstride = (long long)gridDim.x * AB_THREADS;
+  for (long long i = (long long)blockIdx.x * AB_THREADS + threadIdx.x; i < p.n; i += gstride) {
+    long long off[AB_NOPS];
+#pragma unroll
+    for (int k = 0; k < AB_NOPS; ++k) off[k] = 0;
+    long long rem = i;
+    for (int d = p.ndim - 1; d >= 0; --d) {
+      const long long sz = p.shape[d];
+      const long long q = rem / sz;
+      const long long idx = rem - q * sz;
+      rem = q;
+#pragma unroll
+      for (int k = 0; k < AB_NOPS; ++k) off[k] += idx * p.stride[k][d];
+    }
+#define AB_NIN_LD(k, T) const T nin##k = reinterpret_cast<const T*>(p.ptr[k])[off[k]];
+    AB_INPUTS(AB_NIN_LD)
+#undef AB_NIN_LD
+#define AB_NOUT_D(k, T) T nout##k;
+    AB_OUTPUTS(AB_NOUT_D)
+#undef AB_NOUT_D
+#define AB_IN_E(k) nin##k
+#define AB_OUT_E(k) nout##k
+    AB_CALL_BODY(AB_IN_E, AB_OUT_E);
+#undef AB_IN_E
+#undef AB_OUT_E
+#define AB_NOUT_ST(k, T) reinterpret_cast<T*>(p.ptr[AB_NIN + k])[off[AB_NIN + k]] = nout##k;
+    AB_OUTPUTS(AB_NOUT_ST)
+#undef AB_NOUT_ST
+  }
+}

@@ -59,11 +59,11 @@ class Var:
         if self.name:
             d["name"] = self.name
         if self.const is not None:
-            a = np.ascontiguousarray(self.const)
+            a = np.asarray(self.const)
             d["const"] = {
                 "dtype": a.dtype.name,
                 "shape": list(a.shape),
-                "b64": base64.b64encode(a.tobytes()).decode("ascii"),
+                "b64": base64.b64encode(a.tobytes(order="C")).decode("ascii"),
             }
         if self.const_other is not None:
             d["const_other"] = self.const_other

@@ -1,0 +1,207 @@
+"""Device-resident n-d arrays for the B200 runtime.
+
+A :class:`DeviceArray` is (owner, pointer, dtype, shape, element strides) —
+the device analogue of the NumPy arrays that live in the reference's storage
+cells (``aesara/link/basic.py:39`` ``Container``).  Views (``DimShuffle``,
+``Subtensor``, ``Reshape``) share the owner, exactly like the reference's
+``view_map`` ops share NumPy bases.  PyTorch provides the allocator, the
+streams and the host<->device copies (plumbing only — no torch op computes).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+_TORCH_BYTES = torch.uint8
+
+
+def current_device():
+    return torch.cuda.current_device()
+
+
+def stream_handle():
+    """Raw ``cudaStream_t`` of torch's current stream (int)."""
+    return torch.cuda.current_stream().cuda_stream
+
+
+def c_strides(shape):
+    st, acc = [], 1
+    for n in reversed(shape):
+        st.append(acc)
+        acc *= max(int(n), 1)
+    return tuple(reversed(st))
+
+
+def f_strides(shape):
+    st, acc = [], 1
+    for n in shape:
+        st.append(acc)
+        acc *= max(int(n), 1)
+    return tuple(st)
+
+
+class DeviceArray:
+    """A strided view of device memory.  Strides are in elements."""
+
+    __slots__ = ("owner", "ptr", "dtype", "shape", "strides", "itemsize", "__weakref__")
+
+    def __init__(self, owner, ptr, dtype, shape, strides):
+        self.owner = owner  # torch uint8 tensor (or any object keeping memory alive)
+        self.ptr = int(ptr)
+        self.dtype = np.dtype(dtype)
+        self.itemsize = self.dtype.itemsize
+        self.shape = tuple(int(s) for s in shape)
+        self.strides = tuple(int(s) for s in strides)
+
+    # -- construction -------------------------------------------------------
+    @staticmethod
+    def empty(shape, dtype, order="C", device=None):
+        dtype = np.dtype(dtype)
+        shape = tuple(int(s) for s in shape)
+        n = 1
+        for s in shape:
+            if s < 0:
+                raise ValueError("negative dimensions are not allowed")
+            n *= s
+        dev = torch.device("cuda", current_device() if device is None else device)
+        buf = torch.empty(max(n * dtype.itemsize, 1), dtype=_TORCH_BYTES, device=dev)
+        st = c_strides(shape) if order == "C" else f_strides(shape)
+        return DeviceArray(buf, buf.data_ptr(), dtype, shape, st)
+
+    @staticmethod
+    def from_numpy(a, device=None, pinned_ok=True):
+        a = np.asarray(a)
+        src = np.ascontiguousarray(a)
+        out = DeviceArray.empty(src.shape, src.dtype, device=device)
+        if src.size:
+            hb = torch.from_numpy(src.reshape(-1).view(np.uint8))
+            out.owner[: hb.numel()].copy_(hb, non_blocking=hb.is_pinned())
+        return out
+
+    @staticmethod
+    def from_torch(t):
+        """Wrap a (dense) torch CUDA tensor without copying."""
+        dt = {
+            torch.float32: "float32", torch.float64: "float64", torch.int64: "int64",
+            torch.int32: "int32", torch.int16: "int16", torch.int8: "int8",
+            torch.uint8: "uint8", torch.bool: "bool",
+        }[t.dtype]
+        return DeviceArray(t, t.data_ptr(), dt, tuple(t.shape), tuple(t.stride()))
+
+    # -- properties -----------------------------------------------------------
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+    @property
+    def nbytes(self):
+        return self.size * self.itemsize
+
+    def is_c_contiguous(self):
+        acc = 1
+        for n, s in zip(reversed(self.shape), reversed(self.strides)):
+            if n == 1:
+                continue
+            if s != acc:
+                return False
+            acc *= n
+        return True
+
+    def is_f_contiguous(self):
+        acc = 1
+        for n, s in zip(self.shape, self.strides):
+            if n == 1:
+                continue
+            if s != acc:
+                return False
+            acc *= n
+        return True
+
+    # -- views ----------------------------------------------------------------
+    def view(self, shape, strides, offset_elems=0):
+        return DeviceArray(self.owner, self.ptr + offset_elems * self.itemsize, self.dtype,
+                           shape, strides)
+
+    def dimshuffle(self, new_order):
+        """``aesara/tensor/elemwise.py:222-239``: transpose + insert/drop size-1 dims."""
+        kept = [o for o in new_order if o != "x"]
+        for d in range(self.ndim):
+            if d not in kept and self.shape[d] != 1:
+                raise ValueError("DimShuffle: cannot drop a non-broadcastable dimension")
+        shape = [1 if o == "x" else self.shape[o] for o in new_order]
+        strides = [0 if o == "x" else self.strides[o] for o in new_order]
+        return self.view(shape, strides)
+
+    def index(self, idx):
+        """Basic NumPy indexing (ints and slices) -> view."""
+        idx = tuple(idx) + (slice(None),) * (self.ndim - len(idx))
+        if len(idx) > self.ndim:
+            raise IndexError("too many indices for array")
+        off, shape, strides = 0, [], []
+        for d, (i, n, s) in enumerate(zip(idx, self.shape, self.strides)):
+            if isinstance(i, slice):
+                start, stop, step = i.indices(n)
+                ln = len(range(start, stop, step))
+                off += start * s if ln > 0 else 0
+                shape.append(ln)
+                strides.append(s * step)
+            else:
+                i = int(i)
+                if i < -n or i >= n:
+                    raise IndexError(f"index {i} is out of bounds for axis {d} with size {n}")
+                if i < 0:
+                    i += n
+                off += i * s
+        return self.view(shape, strides, off)
+
+    def reshape_view(self, shape):
+        """Reshape without copying; only valid for C-contiguous arrays."""
+        shape = [int(s) for s in shape]
+        if -1 in shape:
+            known = 1
+            for s in shape:
+                if s != -1:
+                    known *= s
+            shape[shape.index(-1)] = self.size // max(known, 1)
+        n = 1
+        for s in shape:
+            n *= s
+        if n != self.size:
+            raise ValueError(f"cannot reshape array of size {self.size} into shape {tuple(shape)}")
+        if not self.is_c_contiguous():
+            raise ValueError("reshape_view needs a C-contiguous array")
+        return self.view(shape, c_strides(shape))
+
+    # -- host transfer ----------------------------------------------------------
+    def to_numpy(self):
+        from .kernels import contiguous_copy
+
+        src = self if self.is_c_contiguous() else contiguous_copy(self)
+        out = np.empty(src.shape, dtype=src.dtype)
+        if src.size:
+            base_off = src.ptr - src.owner.data_ptr()
+            if isinstance(src.owner, torch.Tensor) and src.owner.dtype == _TORCH_BYTES:
+                t = src.owner[base_off : base_off + src.nbytes]
+            else:  # a wrapped typed torch tensor
+                t = src.owner.contiguous().view(-1).view(_TORCH_BYTES)[base_off : base_off + src.nbytes]
+            host = t.cpu().numpy()
+            out.reshape(-1).view(np.uint8)[:] = host
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.to_numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def item(self):
+        return self.to_numpy().reshape(()).item() if self.size == 1 else self.to_numpy().item()
+
+    def __repr__(self):
+        return f"DeviceArray(shape={self.shape}, dtype={self.dtype.name}, strides={self.strides})"

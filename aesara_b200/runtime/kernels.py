@@ -1,0 +1,262 @@
+"""Launch wrappers: IR-level operations -> C-ABI calls on DeviceArrays."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ..codegen.careduce import careduce_source
+from ..codegen.elemwise import elemwise_source
+from ..ir import DTYPE_CODE
+from . import lib as _lib
+from .device import DeviceArray, c_strides, f_strides, stream_handle
+
+
+class ElemwiseKernel:
+    """One fused ``Elemwise{Composite}`` module (compiled on first use)."""
+
+    _by_key = {}
+
+    def __init__(self, expr):
+        self.expr = expr
+        self.src, self.meta = elemwise_source(expr)
+        self.n_in = self.meta["n_in"]
+        self.n_out = self.meta["n_out"]
+        self.out_dtypes = [np.dtype(d) for d in expr["out_dtypes"]]
+        self.in_dtypes = [np.dtype(d) for d in expr["inputs"]]
+        self._handle = None
+        nops = self.n_in + self.n_out
+        self._itemsizes = (C.c_int32 * nops)(*self.meta["itemsizes"])
+        self._ptrs = (C.c_void_p * nops)()
+
+    @classmethod
+    def get(cls, expr):
+        import json
+
+        key = json.dumps(expr, sort_keys=True, default=str)
+        k = cls._by_key.get(key)
+        if k is None:
+            k = cls._by_key[key] = cls(expr)
+        return k
+
+    def compile(self):
+        """NVRTC-compile (disk cached); does not need a GPU."""
+        return _lib.compile_cubin(self.src, "ew")
+
+    def handle(self):
+        if self._handle is None:
+            self._handle = _lib.load_module(self.src, "ew")
+        return self._handle
+
+    def launch(self, shape, ins, outs):
+        """ins/outs: DeviceArrays already broadcast-compatible with ``shape``
+        (inputs may have size-1 dims where ``shape`` is larger)."""
+        nd = len(shape)
+        nops = self.n_in + self.n_out
+        shp = (C.c_int64 * max(nd, 1))(*shape)
+        strides = (C.c_int64 * max(nops * nd, 1))()
+        k = 0
+        for a in ins:
+            self._ptrs[k] = a.ptr
+            for d in range(nd):
+                strides[k * nd + d] = 0 if a.shape[d] == 1 else a.strides[d]
+            k += 1
+        for a in outs:
+            self._ptrs[k] = a.ptr
+            for d in range(nd):
+                strides[k * nd + d] = a.strides[d]
+            k += 1
+        lib = _lib.load()
+        _lib.check(lib.ab_elemwise_launch(self.handle(), self.n_in, self.n_out, nd, shp,
+                                          self._ptrs, strides, self._itemsizes,
+                                          self.meta["vec"], self.meta["unroll"],
+                                          stream_handle()))
+
+
+def broadcast_shape(arrays, what="Elemwise"):
+    """Run-time broadcast rule of ``elemwise_cgen.py:72-125``."""
+    nd = arrays[0].ndim
+    out = []
+    for d in range(nd):
+        n = 1
+        for a in arrays:
+            s = a.shape[d]
+            if s != 1:
+                if n != 1 and s != n:
+                    raise ValueError(
+                        f"Input dimension mismatch. (input[?].shape[{d}] = {s}, "
+                        f"expected {n}) in {what}"
+                    )
+                n = s
+        # a zero-size input makes the output zero-size
+        if any(a.shape[d] == 0 for a in arrays):
+            n = 0
+        out.append(n)
+    return tuple(out)
+
+
+def elemwise_out_order(ins, shape):
+    """Output layout rule of ``aesara/tensor/elemwise.py:912-925``: Fortran
+    order iff every non-scalar input is F- but not C-contiguous."""
+    big = [a for a in ins if a.size > 1 and a.ndim > 1]
+    if big and all(a.is_f_contiguous() and not a.is_c_contiguous() for a in big) and all(
+        a.shape == tuple(shape) for a in big
+    ):
+        return "F"
+    return "C"
+
+
+_IDENTITY = {}
+
+
+def _identity_kernel(dtype):
+    dt = np.dtype(dtype).name
+    k = _IDENTITY.get(dt)
+    if k is None:
+        expr = {"inputs": [dt], "out_dtypes": [dt], "outputs": ["t0"], "name": f"copy_{dt}",
+                "stmts": [{"op": "identity", "args": ["i0"], "dtype": dt, "in_dtypes": [dt]}]}
+        k = _IDENTITY[dt] = ElemwiseKernel.get(expr)
+    return k
+
+
+def copy_into(dst: DeviceArray, src: DeviceArray):
+    """dst[...] = src with NumPy broadcasting of src (strided copy kernel)."""
+    if dst.size == 0:
+        return
+    if src.ndim < dst.ndim:
+        src = src.view((1,) * (dst.ndim - src.ndim) + src.shape,
+                       (0,) * (dst.ndim - src.ndim) + src.strides)
+    if src.ndim != dst.ndim:
+        raise ValueError("copy_into: source has more dimensions than destination")
+    for d in range(dst.ndim):
+        if src.shape[d] not in (1, dst.shape[d]):
+            raise ValueError(f"could not broadcast input array from shape {src.shape} into shape {dst.shape}")
+    if src.dtype != dst.dtype:
+        k = _cast_kernel(src.dtype, dst.dtype)
+    else:
+        k = _identity_kernel(dst.dtype)
+    k.launch(dst.shape, [src], [dst])
+
+
+_CAST = {}
+
+
+def _cast_kernel(src_dt, dst_dt):
+    s, d = np.dtype(src_dt).name, np.dtype(dst_dt).name
+    k = _CAST.get((s, d))
+    if k is None:
+        expr = {"inputs": [s], "out_dtypes": [d], "outputs": ["t0"], "name": f"cast_{s}_{d}",
+                "stmts": [{"op": "cast", "args": ["i0"], "dtype": d, "in_dtypes": [s]}]}
+        k = _CAST[(s, d)] = ElemwiseKernel.get(expr)
+    return k
+
+
+def contiguous_copy(a: DeviceArray, order="C") -> DeviceArray:
+    out = DeviceArray.empty(a.shape, a.dtype, order=order)
+    copy_into(out, a)
+    return out
+
+
+def add_into(dst: DeviceArray, src: DeviceArray):
+    """dst[...] += src (IncSubtensor without set_instead_of_inc)."""
+    dt = dst.dtype.name
+    expr = {"inputs": [dt, src.dtype.name], "out_dtypes": [dt], "outputs": ["t0"],
+            "name": f"inc_{dt}",
+            "stmts": [{"op": "add", "args": ["i0", "i1"], "dtype": dt,
+                       "in_dtypes": [dt, src.dtype.name]}]}
+    if src.ndim < dst.ndim:
+        src = src.view((1,) * (dst.ndim - src.ndim) + src.shape,
+                       (0,) * (dst.ndim - src.ndim) + src.strides)
+    ElemwiseKernel.get(expr).launch(dst.shape, [dst, src], [dst])
+
+
+class CAReduceKernel:
+    _by_key = {}
+
+    def __init__(self, scalar_op, in_dtype, acc_dtype, out_dtype):
+        self.src, self.meta = careduce_source(scalar_op, in_dtype, acc_dtype, out_dtype)
+        self.out_dtype = np.dtype(out_dtype)
+        self._handle = None
+
+    @classmethod
+    def get(cls, scalar_op, in_dtype, acc_dtype, out_dtype):
+        key = (scalar_op, str(in_dtype), str(acc_dtype), str(out_dtype))
+        k = cls._by_key.get(key)
+        if k is None:
+            k = cls._by_key[key] = cls(*key)
+        return k
+
+    def compile(self):
+        return _lib.compile_cubin(self.src, "red")
+
+    def handle(self):
+        if self._handle is None:
+            self._handle = _lib.load_module(self.src, "red")
+        return self._handle
+
+    def launch(self, x: DeviceArray, axis):
+        nd = x.ndim
+        mask = [1 if d in axis else 0 for d in range(nd)]
+        out_shape = tuple(n for d, n in enumerate(x.shape) if not mask[d])
+        out = DeviceArray.empty(out_shape, self.out_dtype)
+        if out.size == 0:
+            return out
+        lib = _lib.load()
+        shp = (C.c_int64 * max(nd, 1))(*x.shape)
+        st = (C.c_int64 * max(nd, 1))(*x.strides)
+        msk = (C.c_int32 * max(nd, 1))(*mask)
+        ws_bytes = C.c_size_t()
+        _lib.check(lib.ab_careduce_workspace_bytes(nd, shp, msk, self.meta["acc_itemsize"],
+                                                   C.byref(ws_bytes)))
+        ws = torch.empty(max(ws_bytes.value, 1), dtype=torch.uint8, device=x.owner.device)
+        _lib.check(lib.ab_careduce_launch(self.handle(), nd, shp, st, msk, x.ptr, out.ptr,
+                                          ws.data_ptr(), ws_bytes.value,
+                                          self.meta["in_itemsize"], self.meta["acc_itemsize"],
+                                          self.meta["out_itemsize"], stream_handle()))
+        return out
+
+
+def _blas_code(dtype):
+    dt = np.dtype(dtype).name
+    if dt not in ("float32", "float64"):
+        raise TypeError(f"BLAS ops accept float32/float64 only, got {dt} (aesara/tensor/blas.py:613-629)")
+    return DTYPE_CODE[dt]
+
+
+def gemv(y: DeviceArray, alpha, A: DeviceArray, x: DeviceArray, beta):
+    """In place: y <- beta*y + alpha*A@x."""
+    lib = _lib.load()
+    m, n = A.shape
+    code = _blas_code(y.dtype)
+    ws_bytes = C.c_size_t()
+    _lib.check(lib.ab_gemv_workspace_bytes(code, m, n, A.strides[0], A.strides[1], C.byref(ws_bytes)))
+    ws = torch.empty(max(ws_bytes.value, 1), dtype=torch.uint8, device=A.owner.device)
+    _lib.check(lib.ab_gemv(code, m, n, float(alpha), A.ptr, A.strides[0], A.strides[1], x.ptr,
+                           x.strides[0], float(beta), y.ptr, y.strides[0], ws.data_ptr(),
+                           ws_bytes.value, stream_handle()))
+
+
+def ger(A: DeviceArray, alpha, x: DeviceArray, y: DeviceArray):
+    """In place: A <- A + alpha * outer(x, y)."""
+    lib = _lib.load()
+    m, n = A.shape
+    _lib.check(lib.ab_ger(_blas_code(A.dtype), m, n, float(alpha), x.ptr, x.strides[0], y.ptr,
+                          y.strides[0], A.ptr, A.strides[0], A.strides[1], stream_handle()))
+
+
+def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision=0):
+    """In place: C <- beta*C + alpha*A@B."""
+    lib = _lib.load()
+    m, k = A.shape
+    k2, n = B.shape
+    code = _blas_code(C_.dtype)
+    ws_bytes = C.c_size_t()
+    _lib.check(lib.ab_gemm_workspace_bytes(code, precision, m, n, k, A.strides[0], A.strides[1],
+                                           B.strides[0], B.strides[1], C.byref(ws_bytes)))
+    ws = torch.empty(max(ws_bytes.value, 1), dtype=torch.uint8, device=A.owner.device)
+    _lib.check(lib.ab_gemm(code, precision, m, n, k, float(alpha), A.ptr, A.strides[0],
+                           A.strides[1], B.ptr, B.strides[0], B.strides[1], float(beta), C_.ptr,
+                           C_.strides[0], C_.strides[1], ws.data_ptr(), ws_bytes.value,
+                           stream_handle()))

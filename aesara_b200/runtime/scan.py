@@ -1,0 +1,140 @@
+"""``Scan`` on device: the general step loop.
+
+Reference: ``aesara/scan/op.py:1673-2160`` (``Scan.perform``; Cython twin
+``scan_perform.pyx:76-602``).  The recurrent outputs are circular buffers of
+``store_steps`` rows living in device memory; each step gathers the tap rows
+as *views*, runs the lowered inner program (itself a ``ProgramExecutor`` —
+``Scan.make_thunk`` compiles its inner graph with the same linker,
+``op.py:1431-1459``) and writes the results into the row at ``pos``.  No data
+leaves the device between steps; the only host work per step is launching.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import kernels as K
+from .device import DeviceArray
+
+
+class ScanRunner:
+    def __init__(self, node, parent):
+        from .vm import ProgramExecutor
+
+        self.node = node
+        self.parent = parent
+        p = node.params
+        self.info = info = p["info"]
+        self.inner = ProgramExecutor(p["inner"], precision=parent.precision, host_outputs=False)
+        self.destroy = {int(k) for k in p.get("destroy_map", {})}
+        self.mm_in = info["mit_mot_in_slices"]
+        self.mm_out = info["mit_mot_out_slices"]
+        self.tap_array = self.mm_in + info["mit_sot_in_slices"] + info["sit_sot_in_slices"]
+        self.n_mit_mot = len(self.mm_in)
+        self.n_outs = len(self.tap_array)
+        self.n_nit_sot = info["n_nit_sot"]
+        self.n_shared = info["n_shared_outs"]
+        self.n_seqs = info["n_seqs"]
+        self.mintaps = [min(t) for t in self.tap_array] + [0] * self.n_nit_sot
+
+    def run(self, args):
+        info = self.info
+        ex = self.parent
+        prog = ex.program
+        node = self.node
+        n_steps = int(np.asarray(args[0].to_numpy() if isinstance(args[0], DeviceArray) else args[0]).item())
+        if n_steps < 0:
+            raise IndexError(f"Scan was asked to run for negative number of step {n_steps}")
+        n_seqs, n_outs, n_nit, n_sh = self.n_seqs, self.n_outs, self.n_nit_sot, self.n_shared
+
+        def dev(v, k):
+            if isinstance(v, DeviceArray):
+                return v
+            return ex.dev(v, dtype=prog.vars[node.inputs[k]].dtype)
+
+        seqs = [dev(a, 1 + k) for k, a in enumerate(args[1 : 1 + n_seqs])]
+        for idx, s in enumerate(seqs):
+            if s.shape[0] < n_steps:
+                raise ValueError(
+                    f"Sequence {idx} has shape {s.shape} but the Scan's required number of steps is {n_steps}"
+                )
+        o0 = 1 + n_seqs
+        states = [dev(a, o0 + k) for k, a in enumerate(args[o0 : o0 + n_outs])]
+        shared_vals = list(args[o0 + n_outs : o0 + n_outs + n_sh])
+        nit_len = [int(np.asarray(a.to_numpy() if isinstance(a, DeviceArray) else a).item())
+                   for a in args[o0 + n_outs + n_sh : o0 + n_outs + n_sh + n_nit]]
+        non_seqs = list(args[o0 + n_outs + n_sh + n_nit :])
+
+        store_steps = [s.shape[0] for s in states] + nit_len
+        bufs = []
+        for idx, s in enumerate(states):
+            if idx in self.destroy and isinstance(args[o0 + idx], DeviceArray):
+                bufs.append(s)
+            else:
+                bufs.append(K.contiguous_copy(s))
+        nit_bufs = [None] * n_nit
+        out_vars = [prog.vars[v] for v in node.outputs]
+        if n_steps == 0:
+            return bufs + [
+                DeviceArray.empty((0,) * out_vars[n_outs + j].ndim, out_vars[n_outs + j].dtype)
+                for j in range(n_nit)
+            ] + shared_vals
+
+        pos = [(-self.mintaps[idx]) % store_steps[idx] for idx in range(n_outs + n_nit)]
+        i, cond = 0, True
+        while i < n_steps and cond:
+            inner_in = [s.index((i,)) for s in seqs]
+            for idx, taps in enumerate(self.tap_array):
+                for t in taps:
+                    inner_in.append(bufs[idx].index(((pos[idx] + t) % store_steps[idx],)))
+            inner_in += shared_vals
+            inner_in += non_seqs
+            inner_out = self.inner(*inner_in)
+            k = 0
+            for g in range(self.n_mit_mot):
+                for out_slice in self.mm_out[g]:
+                    K.copy_into(bufs[g].index((out_slice + pos[g],)), _d(inner_out[k]))
+                    k += 1
+            for j in range(self.n_mit_mot, n_outs):
+                K.copy_into(bufs[j].index((pos[j],)), _d(inner_out[k]))
+                k += 1
+            for j in range(n_nit):
+                val = _d(inner_out[k])
+                if i == 0:
+                    nit_bufs[j] = DeviceArray.empty((store_steps[n_outs + j],) + val.shape,
+                                                    out_vars[n_outs + j].dtype)
+                K.copy_into(nit_bufs[j].index((pos[n_outs + j],)), val)
+                k += 1
+            for j in range(n_sh):
+                shared_vals[j] = inner_out[k]
+                k += 1
+            if info["as_while"]:
+                c = inner_out[k]
+                cond = not bool(c.item() if isinstance(c, DeviceArray) else np.asarray(c).item())
+            pos = [(p + 1) % s for p, s in zip(pos, store_steps)]
+            i += 1
+
+        allb = bufs + nit_bufs
+        for idx in range(self.n_mit_mot, n_outs + n_nit):
+            st = store_steps[idx]
+            b = allb[idx]
+            if st < i - self.mintaps[idx] and pos[idx] < st and pos[idx] != 0:
+                # un-rotate the circular buffer (op.py:2105-2134)
+                pdx = pos[idx]
+                tmp = K.contiguous_copy(b)
+                K.copy_into(b.index((slice(0, st - pdx),)), tmp.index((slice(pdx, st),)))
+                K.copy_into(b.index((slice(st - pdx, st),)), tmp.index((slice(0, pdx),)))
+            elif st > i - self.mintaps[idx]:
+                tail = b.index((slice(i - self.mintaps[idx], st),))
+                if tail.size:
+                    zero = DeviceArray.from_numpy(np.zeros((1,) * b.ndim, dtype=b.dtype))
+                    K.copy_into(tail, zero)
+                if i < n_steps:
+                    allb[idx] = b.index((slice(0, st - (n_steps - i)),))
+        return allb + shared_vals
+
+
+def _d(v):
+    if isinstance(v, DeviceArray):
+        return v
+    return DeviceArray.from_numpy(np.asarray(v))

@@ -1,0 +1,573 @@
+"""Program executor: the device-side analogue of the reference's VM.
+
+What ``CLazyLinker_call`` does for the C-linker (``lazylinker_c.c:752-890``;
+Python twin ``aesara/link/vm.py:338-421`` ``Loop``) — walk the nodes in order,
+run each thunk, drop intermediates after their last use, report the failing
+node — is done here over a lowered :class:`~aesara_b200.ir.Program`.  Tensor
+work is launched asynchronously on the current CUDA stream through the C ABI;
+int64 shape arithmetic is evaluated on the host *before* the
+launches that depend on it, without device synchronisation.
+
+There is no CPU fallback for tensor work: a node kind without a device
+implementation raises ``NotImplementedError`` at construction time.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..ir import Node, Program
+from . import host_eval
+from . import kernels as K
+from .device import DeviceArray
+
+_EXEC = {}
+
+
+def _op(name):
+    def deco(fn):
+        _EXEC[name] = fn
+        return fn
+
+    return deco
+
+
+class NodeError(RuntimeError):
+    """Raised with the position of the failing node (``vm.position_of_error``)."""
+
+    def __init__(self, position, node, exc):
+        super().__init__(f"{type(exc).__name__}: {exc}\nwhile running node {position}: {node.label or node.op}")
+        self.position = position
+        self.node = node
+        self.original = exc
+
+
+def is_host(v):
+    return not isinstance(v, DeviceArray)
+
+
+class ProgramExecutor:
+    def __init__(self, program: Program, precision: int = 0, host_outputs: bool = True,
+                 time_nodes: bool = False):
+        self.program = program
+        self.precision = precision
+        self.host_outputs = host_outputs
+        self.time_nodes = time_nodes
+        self.position_of_error = -1
+        self._const_host = {}
+        self._const_dev = {}
+        self._staged = {}
+        for vid, v in enumerate(program.vars):
+            if v.const is not None:
+                self._const_host[vid] = v.const if v.kind == "tensor" else v.const.dtype.type(v.const.item())
+            elif v.const_other is not None:
+                c = v.const_other
+                self._const_host[vid] = None if "none" in c else slice(*c["slice"])
+        missing = sorted({n.op for n in program.nodes if n.op not in _EXEC})
+        if missing:
+            raise NotImplementedError(
+                "B200 runtime has no implementation for node kind(s): " + ", ".join(missing)
+            )
+        self._steps = [_EXEC[n.op] for n in program.nodes]
+        # per-node private state (kernels, nested executors)
+        self._state = [dict() for _ in program.nodes]
+        # liveness: drop a value right after its last consumer (allow_gc semantics,
+        # aesara/link/vm.py:666-683)
+        last = {}
+        for i, n in enumerate(program.nodes):
+            for v in n.inputs:
+                last[v] = i
+        keep = set(program.outputs) | set(program.inputs)
+        self._free_after = [[] for _ in program.nodes]
+        for v, i in last.items():
+            if v not in keep and v not in self._const_host:
+                self._free_after[i].append(v)
+        self.node_events = None
+        self.prepare()
+
+    # ------------------------------------------------------------------
+    def prepare(self):
+        """Build (and NVRTC-compile, no GPU needed) the statically known kernels."""
+        for i, n in enumerate(self.program.nodes):
+            st = self._state[i]
+            if n.op == "Elemwise":
+                st["kernel"] = K.ElemwiseKernel.get(n.params["expr"])
+                st["host_ok"] = host_eval.supports(n.params["expr"])
+            elif n.op == "CAReduce":
+                p = n.params
+                st["kernel"] = K.CAReduceKernel.get(p["scalar_op"], p["in_dtype"],
+                                                    p["acc_dtype"], p["out_dtype"])
+            elif n.op == "Scan":
+                from .scan import ScanRunner
+
+                st["runner"] = ScanRunner(n, self)
+
+    def compile_all(self):
+        """Force JIT compilation of every module (used by build()/tests on CPU)."""
+        n = 0
+        for st in self._state:
+            k = st.get("kernel")
+            if k is not None:
+                k.compile()
+                n += 1
+            r = st.get("runner")
+            if r is not None:
+                n += r.inner.compile_all()
+        return n
+
+    # ------------------------------------------------------------------
+    def dev(self, v, key=None, dtype=None):
+        """Device view of a value.  Host values are uploaded; uploads of
+        unchanged values (constants, shape-derived scalars) are reused."""
+        if isinstance(v, DeviceArray):
+            return v
+        a = np.asarray(v) if dtype is None else np.asarray(v, dtype=dtype)
+        if key is None:
+            return DeviceArray.from_numpy(a)
+        ent = self._staged.get(key)
+        sig = (a.dtype.str, a.shape, a.tobytes())
+        if ent is not None and ent[0] == sig:
+            return ent[1]
+        d = DeviceArray.from_numpy(a)
+        self._staged[key] = (sig, d)
+        return d
+
+    def const_dev(self, vid):
+        d = self._const_dev.get(vid)
+        if d is None:
+            d = self._const_dev[vid] = DeviceArray.from_numpy(self._const_host[vid])
+        return d
+
+    # ------------------------------------------------------------------
+    def __call__(self, *inputs):
+        prog = self.program
+        if len(inputs) != len(prog.inputs):
+            raise TypeError(f"expected {len(prog.inputs)} inputs, got {len(inputs)}")
+        env = dict(self._const_host)
+        for vid, val in zip(prog.inputs, inputs):
+            var = prog.vars[vid]
+            if isinstance(val, DeviceArray):
+                if var.kind != "tensor":
+                    raise TypeError("device arrays can only feed tensor inputs")
+                if val.dtype.name != var.dtype or val.ndim != var.ndim:
+                    raise TypeError(
+                        f"input {var.name or vid}: expected {var.dtype} with {var.ndim} dims, "
+                        f"got {val.dtype.name} with {val.ndim}"
+                    )
+            elif var.kind == "tensor":
+                val = np.asarray(val)
+                if val.dtype.name != var.dtype:
+                    val = val.astype(var.dtype)
+                if val.ndim != var.ndim:
+                    raise TypeError(
+                        f"input {var.name or vid}: wrong number of dimensions: expected "
+                        f"{var.ndim}, got {val.ndim} with shape {val.shape}"
+                    )
+                if val.size > host_eval.MAX_HOST_ELEMS:
+                    val = DeviceArray.from_numpy(val)
+            elif var.kind == "scalar":
+                val = np.dtype(var.dtype).type(val)
+            env[vid] = val
+        events = [] if self.time_nodes else None
+        nodes = prog.nodes
+        for i, step in enumerate(self._steps):
+            node = nodes[i]
+            if events is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            try:
+                outs = step(self, i, node, [env[v] for v in node.inputs])
+            except NodeError:
+                raise
+            except Exception as exc:
+                self.position_of_error = i
+                raise NodeError(i, node, exc) from exc
+            if events is not None:
+                e1.record()
+                events.append((i, e0, e1))
+            if len(node.outputs) == 1:
+                env[node.outputs[0]] = outs
+            else:
+                for vid, o in zip(node.outputs, outs):
+                    env[vid] = o
+            for v in self._free_after[i]:
+                env.pop(v, None)
+        self.node_events = events
+        outs = [env[v] for v in prog.outputs]
+        if self.host_outputs:
+            outs = [o.to_numpy() if isinstance(o, DeviceArray) else np.asarray(o) for o in outs]
+        return outs
+
+    def node_times_ms(self):
+        """Per-node device time of the last call (needs ``time_nodes=True``)."""
+        if not self.node_events:
+            return []
+        torch.cuda.synchronize()
+        return [(i, self.program.nodes[i].op, e0.elapsed_time(e1)) for i, e0, e1 in self.node_events]
+
+
+# ---------------------------------------------------------------------------
+# node implementations
+# ---------------------------------------------------------------------------
+def _as_dev_inputs(ex, i, node, args):
+    out = []
+    for k, (vid, a) in enumerate(zip(node.inputs, args)):
+        if isinstance(a, DeviceArray):
+            out.append(a)
+        elif vid in ex._const_host:
+            out.append(ex.const_dev(vid))
+        else:
+            out.append(ex.dev(a, key=(i, k), dtype=ex.program.vars[vid].dtype))
+    return out
+
+
+@_op("Elemwise")
+def _elemwise(ex, i, node, args):
+    st = ex._state[i]
+    p = node.params
+    n_out = len(node.outputs)
+    if all(is_host(a) for a in args) and st["host_ok"]:
+        hargs = [np.asarray(a) for a in args]
+        shape = np.broadcast_shapes(*[a.shape for a in hargs]) if hargs else ()
+        size = int(np.prod(shape)) if shape else 1
+        if size <= host_eval.MAX_HOST_ELEMS:
+            outs = host_eval.eval_expr(p["expr"], hargs)
+            outs = [np.array(np.broadcast_to(o, shape)) for o in outs]
+            return outs[0] if n_out == 1 else outs
+    ins = _as_dev_inputs(ex, i, node, args)
+    shape = K.broadcast_shape(ins, node.label or "Elemwise")
+    kern = st["kernel"]
+    outs = []
+    inplace = p.get("inplace", {})
+    order = None
+    for k in range(n_out):
+        ip = inplace.get(str(k))
+        dt = kern.out_dtypes[k]
+        if ip is not None and ins[ip].shape == shape and ins[ip].dtype == dt and not is_host(args[ip]):
+            outs.append(ins[ip])
+        else:
+            if order is None:
+                order = K.elemwise_out_order(ins, shape)
+            outs.append(DeviceArray.empty(shape, dt, order=order))
+    if all(n != 0 for n in shape) or not shape:
+        kern.launch(shape, ins, outs)
+    return outs[0] if n_out == 1 else outs
+
+
+@_op("ScalarOp")
+def _scalarop(ex, i, node, args):
+    expr = node.params["expr"]
+    if not host_eval.supports(expr):
+        raise NotImplementedError(f"host scalar expression {expr.get('name')} is not supported")
+    vals = [a.to_numpy() if isinstance(a, DeviceArray) else a for a in args]
+    outs = host_eval.eval_expr(expr, vals)
+    outs = [o.dtype.type(o.item()) for o in outs]
+    return outs[0] if len(node.outputs) == 1 else outs
+
+
+@_op("DimShuffle")
+def _dimshuffle(ex, i, node, args):
+    (x,) = args
+    order = node.params["new_order"]
+    if isinstance(x, DeviceArray):
+        return x.dimshuffle(order)
+    x = np.asarray(x)
+    kept = [o for o in order if o != "x"]
+    drop = [d for d in range(x.ndim) if d not in kept]
+    for d in drop:
+        if x.shape[d] != 1:
+            raise ValueError("DimShuffle: cannot drop a non-broadcastable dimension")
+    y = x.transpose(kept + drop)
+    return y.reshape([1 if o == "x" else x.shape[o] for o in order])
+
+
+_NP_REDUCE = {"add": np.add, "mul": np.multiply, "maximum": np.maximum, "minimum": np.minimum,
+              "and": np.bitwise_and, "or": np.bitwise_or, "xor": np.bitwise_xor}
+
+
+@_op("CAReduce")
+def _careduce(ex, i, node, args):
+    (x,) = args
+    p = node.params
+    axis = tuple(p["axis"])
+    if is_host(x):  # shape arithmetic such as prod(shape)
+        xa = np.asarray(x).astype(p["acc_dtype"])
+        out = _NP_REDUCE[p["scalar_op"]].reduce(xa, axis=axis, dtype=p["acc_dtype"]) if axis else xa
+        return np.asarray(out).astype(p["out_dtype"])
+    if p["scalar_op"] in ("maximum", "minimum") and any(x.shape[a] == 0 for a in axis):
+        raise ValueError("zero-size array to reduction operation with no identity")
+    if not axis:
+        out = DeviceArray.empty(x.shape, p["out_dtype"])
+        K.copy_into(out, x)
+        return out
+    return ex._state[i]["kernel"].launch(x, axis)
+
+
+# -- BLAS family -------------------------------------------------------------------
+def _scalar_value(v):
+    if isinstance(v, DeviceArray):
+        return v.item()  # device-resident alpha/beta: one D2H read
+    return np.asarray(v).item()
+
+
+def _fresh_like(x, shape=None):
+    return DeviceArray.empty(x.shape if shape is None else shape, x.dtype)
+
+
+@_op("Dot22")
+def _dot22(ex, i, node, args):
+    x, y = _as_dev_inputs(ex, i, node, args)
+    if x.shape[1] != y.shape[0]:
+        raise ValueError(f"Shape mismatch: x has {x.shape[1]} cols (and {x.shape[0]} rows) but y has "
+                         f"{y.shape[0]} rows (and {y.shape[1]} cols)")
+    z = DeviceArray.empty((x.shape[0], y.shape[1]), x.dtype)
+    K.gemm(z, 1.0, x, y, 0.0, ex.precision)
+    return z
+
+
+@_op("Dot22Scalar")
+def _dot22scalar(ex, i, node, args):
+    x, y = _as_dev_inputs(ex, i, node, args[:2])
+    a = _scalar_value(args[2])
+    if x.shape[1] != y.shape[0]:
+        raise ValueError("Shape mismatch in Dot22Scalar")
+    z = DeviceArray.empty((x.shape[0], y.shape[1]), x.dtype)
+    K.gemm(z, a, x, y, 0.0, ex.precision)
+    return z
+
+
+@_op("Gemm")
+def _gemm(ex, i, node, args):
+    z, a, x, y, b = args
+    z, x, y = _as_dev_inputs(ex, i, Node("Gemm", [node.inputs[0], node.inputs[2], node.inputs[3]], []), [z, x, y])
+    a, b = _scalar_value(a), _scalar_value(b)
+    if x.shape[1] != y.shape[0]:
+        raise ValueError(f"Shape mismatch: x has {x.shape[1]} cols (and {x.shape[0]} rows) but y has "
+                         f"{y.shape[0]} rows (and {y.shape[1]} cols)")
+    m, n = x.shape[0], y.shape[1]
+    if z.shape != (m, n):
+        if z.shape[0] in (1, m) and z.shape[1] in (1, n):  # z broadcast (blas.py:995-999)
+            zz = DeviceArray.empty((m, n), z.dtype)
+            K.copy_into(zz, z)
+            z = zz
+        else:
+            raise ValueError(f"Shape mismatch: z has shape {z.shape} but x.y has shape {(m, n)}")
+    elif not node.params["inplace"] or is_host(args[0]):
+        zz = DeviceArray.empty((m, n), z.dtype)
+        if b != 0.0:
+            K.copy_into(zz, z)
+        z = zz
+    K.gemm(z, a, x, y, b, ex.precision)
+    return z
+
+
+@_op("Gemv")
+def _gemv(ex, i, node, args):
+    y, alpha, A, x, beta = args
+    y, A, x = _as_dev_inputs(ex, i, Node("Gemv", [node.inputs[0], node.inputs[2], node.inputs[3]], []), [y, A, x])
+    alpha, beta = _scalar_value(alpha), _scalar_value(beta)
+    if A.shape[0] != y.shape[0] or A.shape[1] != x.shape[0]:
+        raise ValueError(
+            "Incompatible shapes for gemv "
+            f"(beta * y + alpha * dot(A, x)). y: {y.shape}, A: {A.shape}, x: {x.shape}"
+        )
+    if not node.params["inplace"] or is_host(args[0]):
+        yy = DeviceArray.empty(y.shape, y.dtype)
+        if beta != 0.0:
+            K.copy_into(yy, y)
+        y = yy
+    K.gemv(y, alpha, A, x, beta)
+    return y
+
+
+@_op("Ger")
+def _ger(ex, i, node, args):
+    A, alpha, x, y = args
+    A, x, y = _as_dev_inputs(ex, i, Node("Ger", [node.inputs[0], node.inputs[2], node.inputs[3]], []), [A, x, y])
+    alpha = _scalar_value(alpha)
+    if A.shape != (x.shape[0], y.shape[0]):
+        raise ValueError("Shape mismatch in Ger: A %s, x %s, y %s" % (A.shape, x.shape, y.shape))
+    if not node.params["inplace"] or is_host(args[0]):
+        A = K.contiguous_copy(A)
+    K.ger(A, alpha, x, y)
+    return A
+
+
+@_op("Dot")
+def _dot(ex, i, node, args):
+    x, y = _as_dev_inputs(ex, i, node, args)
+    if x.ndim == 1 and y.ndim == 1:
+        if x.shape != y.shape:
+            raise ValueError(f"shapes {x.shape} and {y.shape} not aligned")
+        out = DeviceArray.empty((1,), x.dtype)
+        K.gemv(out, 1.0, x.view((1, x.shape[0]), (0, x.strides[0])), y, 0.0)
+        return out.view((), ())
+    if x.ndim == 2 and y.ndim == 1:
+        out = DeviceArray.empty((x.shape[0],), x.dtype)
+        K.gemv(out, 1.0, x, y, 0.0)
+        return out
+    if x.ndim == 1 and y.ndim == 2:
+        out = DeviceArray.empty((y.shape[1],), x.dtype)
+        K.gemv(out, 1.0, y.dimshuffle([1, 0]), x, 0.0)
+        return out
+    if x.ndim == 2 and y.ndim == 2:
+        z = DeviceArray.empty((x.shape[0], y.shape[1]), x.dtype)
+        K.gemm(z, 1.0, x, y, 0.0, ex.precision)
+        return z
+    raise NotImplementedError("Dot with ndim > 2")
+
+
+# -- allocation / copies ---------------------------------------------------------------
+def _int(v):
+    if isinstance(v, DeviceArray):
+        return int(v.item())
+    return int(np.asarray(v).item())
+
+
+@_op("AllocEmpty")
+def _allocempty(ex, i, node, args):
+    return DeviceArray.empty([_int(s) for s in args], node.params["dtype"])
+
+
+@_op("Alloc")
+def _alloc(ex, i, node, args):
+    v, *shape = args
+    shape = [_int(s) for s in shape]
+    vid = node.inputs[0]
+    var = ex.program.vars[node.outputs[0]]
+    n = int(np.prod(shape)) if shape else 1
+    if is_host(v) and n <= host_eval.MAX_HOST_ELEMS:
+        return np.array(np.broadcast_to(np.asarray(v, dtype=var.dtype), shape))
+    src = v if isinstance(v, DeviceArray) else (
+        ex.const_dev(vid) if vid in ex._const_host else ex.dev(v, key=(i, 0), dtype=var.dtype))
+    out = DeviceArray.empty(shape, var.dtype)
+    K.copy_into(out, src)
+    return out
+
+
+@_op("DeepCopy")
+def _deepcopy(ex, i, node, args):
+    (x,) = args
+    if isinstance(x, DeviceArray):
+        return K.contiguous_copy(x)
+    return np.array(x, copy=True)
+
+
+@_op("View")
+def _view(ex, i, node, args):
+    return args[0]
+
+
+@_op("Reshape")
+def _reshape(ex, i, node, args):
+    x, shp = args
+    shp = [int(s) for s in (shp.to_numpy() if isinstance(shp, DeviceArray) else np.asarray(shp)).reshape(-1)]
+    if is_host(x):
+        return np.reshape(x, shp)
+    if not x.is_c_contiguous():
+        x = K.contiguous_copy(x)
+    return x.reshape_view(shp)
+
+
+# -- host metadata ----------------------------------------------------------------------
+@_op("Shape_i")
+def _shape_i(ex, i, node, args):
+    (x,) = args
+    return np.asarray(np.shape(x)[node.params["i"]] if is_host(x) else x.shape[node.params["i"]],
+                      dtype="int64")
+
+
+@_op("Shape")
+def _shape(ex, i, node, args):
+    (x,) = args
+    return np.asarray(np.shape(x) if is_host(x) else x.shape, dtype="int64")
+
+
+@_op("ScalarFromTensor")
+def _sft(ex, i, node, args):
+    (x,) = args
+    a = x.to_numpy() if isinstance(x, DeviceArray) else np.asarray(x)
+    return a.dtype.type(a.item())
+
+
+@_op("TensorFromScalar")
+def _tfs(ex, i, node, args):
+    return np.asarray(args[0])
+
+
+@_op("MakeVector")
+def _makevector(ex, i, node, args):
+    vals = [a.item() if isinstance(a, DeviceArray) else np.asarray(a).item() for a in args]
+    return np.asarray(vals, dtype=node.params["dtype"]).reshape(len(vals))
+
+
+@_op("Assert")
+def _assert(ex, i, node, args):
+    val, *conds = args
+    for c in conds:
+        c = c.to_numpy() if isinstance(c, DeviceArray) else np.asarray(c)
+        if not bool(np.all(c)):
+            exc = {"ValueError": ValueError, "TypeError": TypeError}.get(node.params.get("exc"), AssertionError)
+            raise exc(node.params["msg"])
+    return val
+
+
+# -- indexing -----------------------------------------------------------------------------
+def _build_index(idx_list, runtime):
+    it = iter(runtime)
+
+    def elem(e):
+        if e is None:
+            return None
+        if e == "in":
+            return _int(next(it))
+        return int(e)
+
+    out = []
+    for entry in idx_list:
+        if "slice" in entry:
+            out.append(slice(*[elem(e) for e in entry["slice"]]))
+        else:
+            out.append(elem(entry["index"]))
+    return tuple(out)
+
+
+@_op("Subtensor")
+def _subtensor(ex, i, node, args):
+    x, *rt = args
+    idx = _build_index(node.params["idx_list"], rt)
+    if is_host(x):
+        return np.asarray(x)[idx]
+    return x.index(idx)
+
+
+@_op("IncSubtensor")
+def _incsubtensor(ex, i, node, args):
+    x, y, *rt = args
+    p = node.params
+    idx = _build_index(p["idx_list"], rt)
+    if is_host(x) and is_host(y):
+        x = np.array(x, copy=True)
+        if p["set"]:
+            x[idx] = y
+        else:
+            x[idx] += y
+        return x
+    vx = ex.program.vars[node.inputs[0]]
+    xd = x if isinstance(x, DeviceArray) else ex.dev(x, dtype=vx.dtype)
+    if not p["inplace"] or is_host(x):
+        xd = K.contiguous_copy(xd)
+    yd = y if isinstance(y, DeviceArray) else ex.dev(y, key=(i, 1), dtype=ex.program.vars[node.inputs[1]].dtype)
+    view = xd.index(idx)
+    if p["set"]:
+        K.copy_into(view, yd)
+    else:
+        K.add_into(view, yd)
+    return xd
+
+
+@_op("Scan")
+def _scan(ex, i, node, args):
+    return ex._state[i]["runner"].run(args)

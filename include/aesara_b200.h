@@ -1,0 +1,152 @@
+/* aesara_b200.h — C ABI of libaesara_b200.so, the B200 (sm_100a) device runtime
+ * behind Aesara's Linker/Op plugin surface.
+ *
+ * Conventions (they mirror the reference's native thunk ABI,
+ * aesara/link/c/basic.py:1668-1709 and lazylinker_c.c:501-520: "0 = success,
+ * non-zero = failure id"):
+ *   - every function returns 0 on success, a non-zero ab_status otherwise;
+ *     ab_last_error() returns the message of the last failure on this thread;
+ *   - no exceptions cross the ABI, no torch / Python types in any signature;
+ *   - the caller owns all descriptors and device buffers it passes in; the
+ *     library owns only what it hands out as opaque handles (ab_module);
+ *   - every launch is asynchronous on the caller-supplied stream (a CUDA
+ *     stream handle cast to void*, NULL = default stream);
+ *   - strides are in ELEMENTS (not bytes); a broadcast dimension has stride 0
+ *     (the run-time broadcast rule of aesara/tensor/elemwise_cgen.py:72-76).
+ */
+#ifndef AESARA_B200_H
+#define AESARA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB_MAX_DIMS 8      /* after collapsing; callers may pass up to 32 raw dims */
+#define AB_MAX_RAW_DIMS 32
+#define AB_MAX_OPERANDS 40 /* inputs + outputs of one fused Elemwise */
+
+typedef enum {
+  AB_OK = 0,
+  AB_ERR_CUDA = 1,        /* a CUDA runtime/driver call failed */
+  AB_ERR_NVRTC = 2,       /* JIT compilation failed (log in ab_last_error) */
+  AB_ERR_INVALID = 3,     /* bad argument (maps to ValueError/TypeError) */
+  AB_ERR_SHAPE = 4,       /* shape mismatch (maps to the reference's ValueError texts) */
+  AB_ERR_UNSUPPORTED = 5, /* valid request the device path does not implement */
+  AB_ERR_NO_DEVICE = 6    /* no usable GPU */
+} ab_status;
+
+/* dtype codes — the dtype set of aesara/tensor/type.py:39-54 minus complex */
+typedef enum {
+  AB_BOOL = 0, AB_I8 = 1, AB_I16 = 2, AB_I32 = 3, AB_I64 = 4,
+  AB_U8 = 5, AB_U16 = 6, AB_U32 = 7, AB_U64 = 8,
+  AB_F16 = 9, AB_F32 = 10, AB_F64 = 11, AB_BF16 = 12
+} ab_dtype;
+
+typedef struct ab_module ab_module; /* a loaded JIT module (one fused Composite / one reduction) */
+
+typedef struct {
+  int sm_count;
+  int cc_major, cc_minor;
+  size_t total_mem;
+  size_t l2_bytes;
+  int max_smem_per_block_optin;
+  char name[128];
+} ab_device_info;
+
+/* ---- runtime ----------------------------------------------------------- */
+/* Select the device and create the context.  Idempotent.  Replaces nothing in
+ * the reference (it has no device); called once from B200Linker.make_all. */
+int ab_init(int device_ordinal);
+int ab_get_device_info(int device_ordinal, ab_device_info* out);
+const char* ab_last_error(void);
+const char* ab_version(void);
+int ab_stream_synchronize(void* stream);
+int ab_device_synchronize(void);
+
+/* Stream-ordered device memory for hosts that do not bring their own
+ * allocator (the Python host uses torch's caching allocator instead). */
+int ab_malloc(void** dptr, size_t bytes, void* stream);
+int ab_free(void* dptr, void* stream);
+int ab_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int ab_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int ab_memset(void* dst, int value, size_t bytes, void* stream);
+
+/* CUDA-event timing on the launching stream (replaces the call_times/call_counts
+ * host timers of aesara/link/vm.py:389-406 — host timers are meaningless for
+ * asynchronous launches). */
+int ab_event_create(void** ev);
+int ab_event_record(void* ev, void* stream);
+int ab_event_elapsed_ms(void* start, void* stop, float* ms);
+int ab_event_destroy(void* ev);
+
+/* ---- JIT: generated kernel per fused Elemwise{Composite} / CAReduce ------ */
+/* Compile CUDA C++ to an sm_100a cubin with NVRTC.  Needs no GPU.  Replaces
+ * GCC_compiler.compile_str (aesara/link/c/cmodule.py:2482).  *cubin is
+ * malloc()ed; release with ab_buffer_free. */
+int ab_nvrtc_compile(const char* src, const char* name, const char* const* extra_opts,
+                     int n_extra_opts, void** cubin, size_t* cubin_size);
+void ab_buffer_free(void* p);
+/* Load a cubin on the current device (replaces dlimport of the compiled module,
+ * aesara/link/c/cmodule.py:ModuleCache). */
+int ab_module_load(const void* cubin, size_t cubin_size, ab_module** out);
+int ab_module_unload(ab_module* m);
+
+/* ---- Elemwise (aesara/tensor/elemwise.py:304, C thunk _c_all :835-1168) ---
+ * Launch the fused scalar expression compiled in `m` over an ndim-dimensional
+ * index space.  operand k (inputs first, then outputs) is ptrs[k] with
+ * strides[k*ndim + d] (elements; 0 = broadcast).  The launcher squeezes and
+ * merges dimensions, then picks the vectorised flat / row / generic kernel.
+ * In-place outputs simply alias an input pointer.  `vec`/`unroll` are the
+ * AB_VEC / AB_UNROLL the module was generated with. */
+int ab_elemwise_launch(ab_module* m, int n_in, int n_out, int ndim, const int64_t* shape,
+                       void* const* ptrs, const int64_t* strides, const int32_t* itemsizes,
+                       int vec, int unroll, void* stream);
+
+/* ---- CAReduce (aesara/tensor/elemwise.py:1221, C loop elemwise_cgen.py:502) -
+ * Reduce `in` over the axes flagged in reduce_mask into a C-contiguous `out`
+ * of the remaining dims.  The module fixes (scalar op, in/acc/out dtype).
+ * `workspace` must hold ab_careduce_workspace_bytes() bytes. */
+int ab_careduce_workspace_bytes(int ndim, const int64_t* shape, const int32_t* reduce_mask,
+                                int acc_itemsize, size_t* bytes);
+int ab_careduce_launch(ab_module* m, int ndim, const int64_t* shape, const int64_t* in_strides,
+                       const int32_t* reduce_mask, const void* in, void* out, void* workspace,
+                       size_t workspace_bytes, int in_itemsize, int acc_itemsize,
+                       int out_itemsize, void* stream);
+
+/* ---- BLAS family ------------------------------------------------------------
+ * Gemv  (aesara/tensor/blas.py:231, blas_c.py:369-577):  y <- beta*y + alpha*A@x
+ *   A is [m,n] with element strides (a_rs, a_cs); when beta == 0, y is not read.
+ * Ger   (aesara/tensor/blas.py:330, blas_c.py:45-357):    A <- A + alpha*x*y^T
+ * Gemm / Dot22 (aesara/tensor/blas.py:872 / :1659, C template :518-869):
+ *   C[m,n] <- beta*C + alpha * A[m,k] @ B[k,n]; arbitrary 2-D element strides
+ *   (the eight stride cases of blas.py:765-776 plus copies for the rest);
+ *   tcgen05/TMEM tensor-core tiles fed by TMA.  `precision`:
+ *     0 = fp32-faithful (3xTF32 split, rtol 1e-5 vs sgemm),
+ *     1 = single TF32 pass, 2 = BF16 operands / FP32 accumulate (policy mode).
+ *   dtype is AB_F32 or AB_F64 (the only dtypes the reference Gemm accepts,
+ *   blas.py:613-629); f64 runs on the FP64 pipe. */
+int ab_gemv(int dtype, int64_t m, int64_t n, double alpha, const void* A, int64_t a_rs,
+            int64_t a_cs, const void* x, int64_t x_s, double beta, void* y, int64_t y_s,
+            void* workspace, size_t workspace_bytes, void* stream);
+int ab_gemv_workspace_bytes(int dtype, int64_t m, int64_t n, int64_t a_rs, int64_t a_cs,
+                            size_t* bytes);
+int ab_ger(int dtype, int64_t m, int64_t n, double alpha, const void* x, int64_t x_s,
+           const void* y, int64_t y_s, void* A, int64_t a_rs, int64_t a_cs, void* stream);
+int ab_gemm(int dtype, int precision, int64_t m, int64_t n, int64_t k, double alpha,
+            const void* A, int64_t a_rs, int64_t a_cs, const void* B, int64_t b_rs,
+            int64_t b_cs, double beta, void* C, int64_t c_rs, int64_t c_cs, void* workspace,
+            size_t workspace_bytes, void* stream);
+int ab_gemm_workspace_bytes(int dtype, int precision, int64_t m, int64_t n, int64_t k,
+                            int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs,
+                            size_t* bytes);
+
+/* number of kernels this library has launched since load (bench.py reports it) */
+uint64_t ab_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AESARA_B200_H */

@@ -1,0 +1,315 @@
+"""Generate the golden fixtures under tests/golden/ with the REFERENCE itself.
+
+Run in the build container only (it imports /root/reference through the
+overlay in aesara_b200.compat):
+
+    PYTHONPATH=. python tests/golden/make_golden.py
+
+For every case it
+  1. builds the symbolic graph with the reference front-end,
+  2. lets the reference rewriter optimise it (``fast_run``) and compiles it with
+     the reference C linker (``Mode("cvm")`` = g++-compiled thunks driven by the C VM),
+  3. lowers the *same* optimised graph with ``aesara_b200.lower`` → ``<case>.json``,
+  4. evaluates the reference function on seeded inputs → ``<case>.npz``
+     (``in_<k>`` arrays in program-input order, ``out_<k>`` reference outputs).
+
+The fixtures pin both the oracle (tests/test_oracle.py, CPU) and the CUDA path
+(tests/test_gpu_parity.py, ``-m gpu``).  The reference publishes no golden
+vectors of its own for this path, so these are "outputs of the
+reference itself run here".
+"""
+
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+warnings.simplefilter("ignore")
+
+from aesara_b200 import graphs as G  # noqa: E402
+from aesara_b200.compat.bootstrap import load_aesara  # noqa: E402
+
+aesara = load_aesara()
+import aesara.tensor as at  # noqa: E402
+
+RNG = np.random.default_rng(666)  # the reference's unittests__rseed (configdefaults.py:1197)
+CASES = {}
+
+
+def case(name):
+    def deco(fn):
+        CASES[name] = fn
+        return fn
+
+    return deco
+
+
+def rnd(shape, dtype="float32", lo=-3.0, hi=3.0):
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        return (RNG.random(shape) * (hi - lo) + lo).astype(dt)
+    if dt.kind == "b":
+        return RNG.random(shape) < 0.5
+    info = np.iinfo(dt)
+    return RNG.integers(max(info.min, -50), min(info.max, 50), size=shape, endpoint=True).astype(dt)
+
+
+# ---------------------------------------------------------------- BASELINE configs
+@case("cfg1_readme")
+def _():
+    i, o = G.cfg1_readme()
+    return i, o, G.cfg1_inputs(96, seed=1)
+
+
+@case("cfg2_fused")
+def _():
+    i, o = G.cfg2_fused_elemwise()
+    return i, o, G.cfg2_inputs(4099, seed=2)
+
+
+@case("cfg2_fused_allbranches")
+def _():
+    i, o = G.cfg2_fused_elemwise()
+    return i, o, G.cfg2_inputs(4096, seed=3, yscale=20.0)
+
+
+@case("cfg3_mlp")
+def _():
+    i, o = G.cfg3_mlp()
+    return i, o, G.cfg3_inputs(256, 128, seed=4)
+
+
+@case("cfg4_lstm")
+def _():
+    i, o = G.cfg4_lstm_scan()
+    return i, o, G.cfg4_inputs(6, 64, 32, seed=5)
+
+
+@case("cfg5_logreg")
+def _():
+    i, o = G.cfg5_logreg()
+    return i, o, G.cfg5_inputs(1000, 48, seed=6)
+
+
+# ---------------------------------------------------------------- Elemwise tables
+# shapes follow tests/tensor/test_elemwise.py:214-229 (TestBroadcast)
+@case("ew_broadcast_f64")
+def _():
+    a, b = at.dmatrix("a"), at.dmatrix("b")
+    c, d = at.dtensor4("c"), at.dtensor4("d")
+    outs = [a + b, a * b - a, c / (d * d + 1.0), at.exp(a) + at.sqrt(abs(b))]
+    return [a, b, c, d], outs, [rnd((3, 5), "float64"), rnd((1, 5), "float64"),
+                                rnd((2, 3, 4, 5), "float64"), rnd((1, 3, 1, 5), "float64")]
+
+
+@case("ew_outer_broadcast")
+def _():
+    a, b = at.fmatrix("a"), at.fmatrix("b")
+    return [a, b], [a + b, at.maximum(a, b) * 2], [rnd((1, 7)), rnd((5, 1))]
+
+
+@case("ew_transposed_views")
+def _():
+    a, b = at.fmatrix("a"), at.fmatrix("b")
+    t = at.tensor3("t", dtype="float32")
+    outs = [a.T * b + 1, at.tanh(t.dimshuffle(2, 0, 1)) - t.dimshuffle(2, 0, 1) ** 2,
+            (a.T + b)[::-1, ::2]]
+    return [a, b, t], outs, [rnd((6, 4)), rnd((4, 6)), rnd((3, 4, 5))]
+
+
+@case("ew_int_arith")
+def _():
+    x, y = at.ivector("x"), at.ivector("y")
+    b8 = at.bvector("b8")
+    outs = [x + y, x * y - x, x // y, x % y, abs(x), -x, at.sgn(x), x & y, x | y, x ^ y, ~x,
+            at.maximum(x, y), at.minimum(x, y), b8 + b8, b8 * b8, at.cast(x, "int8"),
+            at.cast(x * 1000, "int16"), x / y, at.switch(x > y, x, y), at.clip(x, -5, 5)]
+    xv = rnd(257, "int32")
+    yv = rnd(257, "int32")
+    yv[yv == 0] = 7
+    return [x, y, b8], outs, [xv, yv, rnd(257, "int8")]
+
+
+@case("ew_uint_bool")
+def _():
+    u, v = at.vector("u", dtype="uint8"), at.vector("v", dtype="uint16")
+    p, q = at.vector("p", dtype="bool"), at.vector("q", dtype="bool")
+    outs = [u + u, u * u, v - v // 3, u // 3, u % 7, p & q, p | q, p ^ q, ~p, at.eq(u, 3),
+            at.neq(v, u), at.lt(u, v), at.cast(p, "float32") + 1, at.switch(p, u, 9),
+            at.cast(v, "uint8"), at.cast(u, "int64") - 200]
+    return [u, v, p, q], outs, [rnd(130, "uint8"), rnd(130, "uint16"), rnd(130, "bool"), rnd(130, "bool")]
+
+
+@case("ew_int64_mixed")
+def _():
+    x, y = at.lvector("x"), at.wvector("y")
+    f = at.fvector("f")
+    outs = [x * y, x // (abs(y) + 1), x % (abs(y) + 1), x + f, at.cast(f * 10, "int64") + x,
+            at.floor(f), at.ceil(f), at.round(f), at.trunc(f), at.cast(f, "int32"),
+            at.int_div(f, at.cast(abs(y) + 1, "float32")), at.mod(f, 1.5)]
+    return [x, y, f], outs, [rnd(100, "int64"), rnd(100, "int16"), rnd(100, "float32", -9.5, 9.5)]
+
+
+@case("ew_math_f32")
+def _():
+    x = at.fvector("x")
+    px = abs(x) + 0.1
+    outs = [at.exp(x), at.log(px), at.log1p(px), at.expm1(x), at.sqrt(px), at.sin(x), at.cos(x),
+            at.tan(x * 0.4), at.tanh(x), at.sinh(x), at.cosh(x), at.arctan(x), at.arcsinh(x),
+            at.sigmoid(x), at.softplus(x * 15), at.erf(x), at.erfc(x), at.log2(px), at.log10(px),
+            at.exp2(x), at.sqr(x), at.reciprocal(px), at.arctan2(x, px), at.pow(px, x * 0.5),
+            at.log1mexp(-px), at.isnan(x / (x - x)), at.deg2rad(x)]
+    return [x], outs, [rnd(513, "float32", -4.0, 4.0)]
+
+
+@case("ew_math_f64")
+def _():
+    x = at.dvector("x")
+    px = abs(x) + 0.1
+    outs = [at.exp(x), at.log(px), at.log1p(px), at.tanh(x), at.sigmoid(x), at.softplus(x * 15),
+            at.erf(x), at.sqrt(px), at.sin(x) * at.cos(x), at.pow(px, x), at.arccosh(px + 1),
+            at.arctanh(at.tanh(x) * 0.9), at.arcsin(at.sin(x)), at.arccos(at.cos(x))]
+    return [x], outs, [rnd(300, "float64", -4.0, 4.0)]
+
+
+@case("ew_fusion_multi")
+def _():
+    # a few rows in the spirit of tests/tensor/rewriting/test_elemwise.py:300-903
+    x, y, z = at.fmatrix("x"), at.fmatrix("y"), at.fmatrix("z")
+    iv = at.imatrix("iv")
+    outs = [x + y + z, x * y * z - (x + y), (x + y) / (abs(z) + 1), at.exp(x + y + z),
+            x + at.cast(iv, "float32") * y, at.switch(at.gt(x, y), x * 2, y / 2),
+            at.sqr(x) + at.sqr(y) + at.sqr(z), at.eq(iv, 2) * x]
+    return [x, y, z, iv], outs, [rnd((17, 9)), rnd((17, 9)), rnd((17, 9)), rnd((17, 9), "int32")]
+
+
+@case("ew_scalar_0d")
+def _():
+    a, b = at.fscalar("a"), at.dscalar("b")
+    x = at.fvector("x")
+    return [a, b, x], [a * x + a, at.exp(b) * b, a + b, x.sum() * a], [np.float32(1.5), np.float64(-0.25), rnd(33)]
+
+
+# ---------------------------------------------------------------- CAReduce tables
+# axes table of tests/tensor/test_elemwise.py:412-428 (TestCAReduce)
+@case("careduce_sum_axes")
+def _():
+    x = at.ftensor3("x")
+    m = at.fmatrix("m")
+    outs = [x.sum(), x.sum(axis=0), x.sum(axis=1), x.sum(axis=2), x.sum(axis=(0, 2)),
+            x.sum(axis=(1, 2)), x.sum(axis=(0, 1)), m.sum(axis=0), m.sum(axis=1), m.T.sum(axis=0),
+            m.mean(), x.mean(axis=1)]
+    return [x, m], outs, [rnd((5, 67, 9)), rnd((300, 130))]
+
+
+@case("careduce_ops_dtypes")
+def _():
+    f = at.fmatrix("f")
+    d = at.dmatrix("d")
+    i8 = at.bmatrix("i8")
+    i32 = at.imatrix("i32")
+    bo = at.matrix("bo", dtype="bool")
+    u8 = at.matrix("u8", dtype="uint8")
+    outs = [f.max(), f.max(axis=0), f.min(axis=1), d.prod(axis=0), d.sum(), i8.sum(), i8.sum(axis=0),
+            i8.max(axis=1), i8.min(), i32.prod(axis=1), i32.sum(axis=0), bo.all(), bo.any(axis=0),
+            bo.all(axis=1), bo.sum(), u8.sum(axis=1), u8.max(), at.max(i32, axis=0), d.max(axis=1)]
+    return [f, d, i8, i32, bo, u8], outs, [rnd((33, 65)), rnd((20, 11), "float64", 0.5, 1.5),
+                                           rnd((40, 33), "int8"), rnd((9, 6), "int32"),
+                                           rnd((12, 40), "bool"), rnd((30, 70), "uint8")]
+
+
+@case("careduce_big_1d")
+def _():
+    x = at.fvector("x")
+    return [x], [x.sum(), x.max(), (x * x).sum(), x.mean()], [rnd(300001)]
+
+
+@case("careduce_nan")
+def _():
+    x = at.fmatrix("x")
+    xv = rnd((8, 9))
+    xv[2, 3] = np.nan
+    return [x], [x.max(axis=0), x.min(axis=1), x.sum(axis=0), x.max()], [xv]
+
+
+# ---------------------------------------------------------------- BLAS family
+@case("blas_dot22_layouts")
+def _():
+    a, b, c = at.fmatrix("a"), at.fmatrix("b"), at.fmatrix("c")
+    outs = [at.dot(a, b), at.dot(a.T, c), at.dot(b.T, a.T), at.dot(a, b) * 0.5]
+    return [a, b, c], outs, [rnd((130, 70)), rnd((70, 96)), rnd((130, 40))]
+
+
+@case("blas_gemm_alpha_beta")
+def _():
+    z, x, y = at.fmatrix("z"), at.fmatrix("x"), at.fmatrix("y")
+    a, b = at.fscalar("a"), at.fscalar("b")
+    outs = [b * z + a * at.dot(x, y), z - at.dot(x, y), z + 2.0 * at.dot(x, y)]
+    return [z, x, y, a, b], outs, [rnd((150, 200)), rnd((150, 64)), rnd((64, 200)), np.float32(0.8), np.float32(0.4)]
+
+
+@case("blas_gemm_f64")
+def _():
+    z, x, y = at.dmatrix("z"), at.dmatrix("x"), at.dmatrix("y")
+    outs = [0.4 * z + 0.8 * at.dot(x, y), at.dot(x.T, z)]
+    return [z, x, y], outs, [rnd((50, 60), "float64"), rnd((50, 33), "float64"), rnd((33, 60), "float64")]
+
+
+@case("blas_gemv_ger")
+def _():
+    A, x, y = at.fmatrix("A"), at.fvector("x"), at.fvector("y")
+    outs = [at.dot(A, x), at.dot(A.T, y), y + 0.5 * at.dot(A, x), A + at.outer(y, x) * 2.0,
+            at.dot(y, A), at.dot(x, x)]
+    return [A, x, y], outs, [rnd((300, 129)), rnd(129), rnd(300)]
+
+
+@case("blas_gemv_f64")
+def _():
+    A, x, y = at.dmatrix("A"), at.dvector("x"), at.dvector("y")
+    return [A, x, y], [at.dot(A, x) * 2 + y, at.dot(A.T, y)], [rnd((77, 50), "float64"), rnd(50, "float64"), rnd(77, "float64")]
+
+
+# ---------------------------------------------------------------- Scan
+@case("scan_cumsum_allsteps")
+def _():
+    x = at.fmatrix("x")
+    s0 = at.fvector("s0")
+    res, _ = aesara.scan(lambda x_t, s: s * 0.5 + x_t, sequences=[x], outputs_info=[s0])
+    return [x, s0], [res, res[-1]], [rnd((7, 40)), rnd(40)]
+
+
+@case("scan_two_taps_nitsot")
+def _():
+    x = at.fvector("x")
+    init = at.fvector("init")  # two initial values
+
+    def step(x_t, f_tm2, f_tm1):
+        f = f_tm1 + f_tm2 * 0.5 + x_t
+        return f, f * 2
+
+    (f, g), _ = aesara.scan(step, sequences=[x], outputs_info=[dict(initial=init, taps=[-2, -1]), None])
+    return [x, init], [f, g], [rnd(9), rnd(2)]
+
+
+def main(names):
+    from aesara_b200.graphs import optimized_program
+
+    for name in names:
+        ins, outs, values = CASES[name]()
+        prog, f = optimized_program(ins, outs, name=name)
+        ref = f(*values)
+        prog.save(os.path.join(HERE, name + ".json"))
+        blob = {}
+        for k, v in enumerate(values):
+            blob[f"in_{k}"] = np.asarray(v)
+        for k, v in enumerate(ref):
+            blob[f"out_{k}"] = np.asarray(v)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+        print(f"{name}: {len(prog.nodes)} nodes {prog.op_counts()}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or list(CASES))

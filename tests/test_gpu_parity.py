@@ -1,0 +1,105 @@
+"""GPU: the CUDA path (through the C ABI) reproduces the reference outputs in
+tests/golden/ and agrees with the oracle on the same inputs.  Bit-exact for
+integer/bool outputs, rtol 1e-5 for floats (see tests/_cases.py)."""
+import numpy as np
+import pytest
+
+from tests._cases import assert_matches, case_names, load_case, uses_blas
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt():
+    import torch
+
+    from aesara_b200.runtime import lib
+    from aesara_b200.runtime.vm import ProgramExecutor
+
+    lib.check(lib.load().ab_init(0))
+    torch.cuda.set_device(0)
+    return ProgramExecutor
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_cuda_matches_reference_and_oracle(rt, name):
+    from oracle.program_np import run_program
+
+    prog, ins, want = load_case(name)
+    ex = rt(prog)
+    got = ex(*[np.array(a) for a in ins])
+    oracle = run_program(prog, [np.array(a) for a in ins])
+    blas = uses_blas(prog)
+    for k, (g, w, o) in enumerate(zip(got, want, oracle)):
+        assert_matches(g, w, blas=blas, what=f"{name} output {k} vs reference")
+        assert_matches(g, o, blas=blas, what=f"{name} output {k} vs oracle")
+
+
+@pytest.mark.parametrize("name", ["cfg2_fused", "cfg3_mlp", "cfg5_logreg"])
+def test_device_resident_call(rt, name):
+    """Inputs given as DeviceArrays, outputs left on the device."""
+    from aesara_b200.runtime.device import DeviceArray
+
+    prog, ins, want = load_case(name)
+    ex = rt(prog, host_outputs=False)
+    dins = [DeviceArray.from_numpy(a) if np.ndim(a) > 0 else a for a in ins]
+    got = ex(*dins)
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert isinstance(g, DeviceArray) or np.ndim(g) == 0
+        assert_matches(np.asarray(g), w, blas=uses_blas(prog), what=f"{name} out {k}")
+
+
+@pytest.mark.parametrize("n", [1, 3, 1023, 1 << 20, (1 << 22) + 5])
+def test_fused_elemwise_sizes(rt, n):
+    """cfg2 graph at ragged sizes, incl. misaligned views (scalar fallback path)."""
+    from oracle.program_np import run_program
+    from aesara_b200.runtime.device import DeviceArray
+
+    prog, _, _ = load_case("cfg2_fused")
+    rng = np.random.default_rng(n)
+    ins = [rng.standard_normal(n + 1).astype("float32") for _ in range(3)]
+    ex = rt(prog)
+    want = run_program(prog, [a[:n] for a in ins])[0]
+    got = ex(*[a[:n] for a in ins])[0]
+    assert_matches(got, want, what="aligned")
+    dins = [DeviceArray.from_numpy(a).index((slice(1, None),)) for a in ins]  # 4-byte offset views
+    got2 = ex(*dins)[0]
+    want2 = run_program(prog, [a[1:] for a in ins])[0]
+    assert_matches(got2, want2, what="misaligned")
+
+
+def test_empty_inputs(rt):
+    prog, _, _ = load_case("cfg2_fused")
+    ex = rt(prog)
+    z = np.zeros(0, "float32")
+    assert ex(z, z, z)[0].shape == (0,)
+
+
+def test_shape_mismatch_raises(rt):
+    prog, _, _ = load_case("cfg2_fused")
+    ex = rt(prog)
+    a = np.zeros(8, "float32")
+    b = np.zeros(9, "float32")
+    with pytest.raises(Exception, match="dimension mismatch"):
+        ex(a, b, a)
+
+
+def test_full_size_properties(rt):
+    """cfg2 at 2^26 elements: linearity in z and agreement of two launch geometries."""
+    import torch
+
+    from aesara_b200.runtime.device import DeviceArray
+
+    prog, _, _ = load_case("cfg2_fused")
+    ex = rt(prog, host_outputs=False)
+    n = 1 << 26
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x, y, z = (torch.randn(n, device="cuda", generator=g) for _ in range(3))
+    o1 = ex(DeviceArray.from_torch(x), DeviceArray.from_torch(y), DeviceArray.from_torch(z))[0]
+    o2 = ex(DeviceArray.from_torch(x), DeviceArray.from_torch(y), DeviceArray.from_torch(2 * z))[0]
+    t1 = torch.frombuffer(o1.owner, dtype=torch.float32) if False else o1.owner.view(torch.float32)
+    t2 = o2.owner.view(torch.float32)
+    assert torch.equal(t2[:n], 2 * t1[:n])  # exact: scaling by 2 commutes with rounding
+    ref = (torch.nn.functional.softplus(torch.tanh(x.double()) + y.double()) * z.double())
+    err = ((t1[:n].double() - ref).abs() / (ref.abs() + 1e-6)).max().item()
+    assert err < 1e-5

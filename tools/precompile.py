@@ -1,0 +1,27 @@
+"""NVRTC-compile (no GPU needed) every kernel the committed fixtures use, so the
+cubins in aesara_b200/_kcache/ travel with the tree."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from concurrent.futures import ThreadPoolExecutor
+
+from aesara_b200.runtime.vm import ProgramExecutor
+from aesara_b200.runtime import kernels as K
+from tests._cases import case_names, load_case
+
+
+def main():
+    t = time.time()
+    exs = [ProgramExecutor(load_case(n)[0]) for n in case_names()]
+    kerns = list(K.ElemwiseKernel._by_key.values()) + list(K.CAReduceKernel._by_key.values())
+    for dt in ("float32", "float64", "int64", "int32", "int8", "bool"):
+        kerns.append(K._identity_kernel(dt))
+    with ThreadPoolExecutor(8) as pool:
+        list(pool.map(lambda k: k.compile(), kerns))
+    print(f"compiled {len(kerns)} modules in {time.time() - t:.1f}s")
+
+
+if __name__ == "__main__":
+    main()
