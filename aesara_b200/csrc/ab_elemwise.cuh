@@ -111,7 +111,7 @@ __device__ __forceinline__ void ab_ew_flat_impl(const AbEwParams& p) {
   }
 }
 
-extern "C" __global__ void __launch_bounds__(AB_THREADS)
+extern "C" __global__ void __launch_bounds__(AB_THREADS, AB_MIN_BLOCKS)
 ab_ew_flat_vec(const __grid_constant__ AbEwParams p) {
   ab_ew_flat_impl<AB_VEC, AB_UNROLL>(p);
 }
@@ -185,7 +185,7 @@ __device__ __forceinline__ void ab_ew_rows_impl(const AbEwParams& p) {
   }
 }
 
-extern "C" __global__ void __launch_bounds__(AB_THREADS)
+extern "C" __global__ void __launch_bounds__(AB_THREADS, AB_MIN_BLOCKS)
 ab_ew_rows_vec(const __grid_constant__ AbEwParams p) {
   ab_ew_rows_impl<AB_VEC, AB_UNROLL>(p);
 }

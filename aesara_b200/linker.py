@@ -1,0 +1,175 @@
+"""``B200Linker`` — the drop-in boundary.
+
+A subclass of ``aesara.link.basic.LocalLinker`` (``aesara/link/basic.py:240``):
+``accept(fgraph, no_recycling, profile)`` then ``make_all(input_storage,
+output_storage, storage_map) -> (fn, [Container in], [Container out], thunks,
+order)``, the contract ``FunctionMaker`` drives (``compile/function/types.py:1586-1595,
+1708``) and ``VMLinker.make_all`` implements for the C-linker
+(``aesara/link/vm.py:1212-1324``).  Any graph compiles unchanged::
+
+    import aesara_b200
+    f = aesara.function([x, y], out, mode="B200")           # or mode=aesara_b200.mode()
+
+The returned ``fn`` reproduces the VM semantics ``Function.__call__`` relies on
+(``types.py:969-1048``): reads the input cells, writes the output cells, applies
+the ``update_mapping`` output->input copies itself (``need_update_inputs = False``,
+``vm.py:284-335``), exposes ``allow_gc``, ``storage_map``, ``nodes``, ``thunks`` and
+``position_of_error`` so errors are re-raised through ``raise_with_op``.
+
+Inputs may be NumPy arrays (uploaded each call, like any host-typed linker) or
+``DeviceArray``s when ``Function.trust_input`` is set; outputs are
+NumPy arrays by default, device arrays with ``device_outputs=True``.
+"""
+
+from __future__ import annotations
+
+from copy import copy
+
+from .compat.bootstrap import load_aesara
+
+load_aesara()
+
+from aesara.compile.mode import Mode, predefined_linkers, predefined_modes, register_linker  # noqa: E402
+from aesara.graph.rewriting.db import RewriteDatabaseQuery  # noqa: E402
+from aesara.link.basic import Container, LocalLinker  # noqa: E402
+from aesara.link.utils import map_storage  # noqa: E402
+
+from .lower import lower_fgraph  # noqa: E402
+
+
+class _NodeThunk:
+    """Per-node placeholder kept for ``raise_with_op`` (``link/utils.py:270``)."""
+
+    lazy = False
+
+    def __init__(self, node, storage_map):
+        self.inputs = [storage_map[v] for v in node.inputs]
+        self.outputs = [storage_map[v] for v in node.outputs]
+
+
+class B200VM:
+    """The callable returned by :meth:`B200Linker.make_all`."""
+
+    need_update_inputs = False
+
+    def __init__(self, linker, fgraph, order, executor, input_storage, output_storage, storage_map):
+        self.fgraph = fgraph
+        self.nodes = order
+        self.executor = executor
+        self.input_storage = input_storage
+        self.output_storage = output_storage
+        self.storage_map = storage_map
+        self.thunks = [_NodeThunk(n, storage_map) for n in order]
+        self.allow_gc = linker.allow_gc
+        self.position_of_error = -1
+        self.time_thunks = False
+        self.call_counts = [0] * len(order)
+        self.call_times = [0.0] * len(order)
+        upd = getattr(fgraph, "update_mapping", None) or {}
+        self._updates = [(int(o), int(i)) for o, i in upd.items()]
+        self._host_out = not linker.device_outputs
+
+    def __call__(self, output_subset=None):
+        from .runtime.device import DeviceArray
+        from .runtime.vm import NodeError
+
+        try:
+            outs = self.executor(*[cell[0] for cell in self.input_storage])
+        except NodeError as e:
+            self.position_of_error = e.position
+            raise e.original from None
+        if self._host_out:
+            outs = [o.to_numpy() if isinstance(o, DeviceArray) else o for o in outs]
+        for cell, val in zip(self.output_storage, outs):
+            cell[0] = val
+        for out_idx, in_idx in self._updates:  # UpdatingVM.perform_updates, vm.py:326-335
+            self.input_storage[in_idx][0] = outs[out_idx]
+        return outs
+
+    def update_profile(self, profile):
+        for i, node in enumerate(self.nodes):
+            profile.apply_callcount[node] = profile.apply_callcount.get(node, 0) + self.call_counts[i]
+
+
+class B200Linker(LocalLinker):
+    """Link an optimised ``FunctionGraph`` to hand-written sm_100a kernels."""
+
+    def __init__(self, allow_gc=True, precision="fp32", device_outputs=False, schedule=None):
+        super().__init__(allow_gc=allow_gc, scheduler=schedule)
+        self.fgraph = None
+        self.precision = precision
+        self.device_outputs = device_outputs
+        self.no_recycling = []
+        self.program = None
+
+    def accept(self, fgraph, no_recycling=None, profile=None):
+        if no_recycling is None:
+            no_recycling = []
+        if self.fgraph is not None and self.fgraph is not fgraph:
+            # a linker instance is bound to one graph (pattern of link/basic.py:300-326)
+            return type(self)(allow_gc=self.allow_gc, precision=self.precision,
+                              device_outputs=self.device_outputs).accept(fgraph, no_recycling, profile)
+        self.fgraph = fgraph
+        self.no_recycling = no_recycling
+        self.profile = profile
+        return self
+
+    def clone(self, allow_gc=None):
+        new = copy(self)
+        if allow_gc is not None:
+            new._allow_gc = allow_gc
+        return new
+
+    def make_all(self, input_storage=None, output_storage=None, storage_map=None):
+        from .runtime.vm import ProgramExecutor
+
+        fgraph = self.fgraph
+        order = self.schedule(fgraph)
+        input_storage, output_storage, storage_map = map_storage(
+            fgraph, order, input_storage, output_storage, storage_map
+        )
+        self.program = lower_fgraph(fgraph, order=order)
+        prec = {"fp32": 0, "tf32": 1, "bf16": 2}.get(self.precision, self.precision)
+        executor = ProgramExecutor(self.program, precision=prec, host_outputs=False)
+        fn = B200VM(self, fgraph, order, executor, input_storage, output_storage, storage_map)
+        return (
+            fn,
+            [Container(i, s) for i, s in zip(fgraph.inputs, input_storage)],
+            [Container(o, s, readonly=True) for o, s in zip(fgraph.outputs, output_storage)],
+            fn.thunks,
+            order,
+        )
+
+
+def mode(precision="fp32", device_outputs=False, optimizer=None):
+    """An Aesara ``Mode`` using this backend with the ``fast_run`` rewrites the
+    C-linker gets."""
+    if optimizer is None:
+        optimizer = RewriteDatabaseQuery(include=["fast_run"])
+    return Mode(B200Linker(precision=precision, device_outputs=device_outputs), optimizer)
+
+
+def register():
+    """``register_linker("b200")`` + ``register_mode("B200")`` (mode.py:54-58, 525-532)."""
+    if "b200" not in predefined_linkers:
+        register_linker("b200", B200Linker())
+    if "B200" not in predefined_modes:
+        predefined_modes["B200"] = mode()
+    # get_target_language() (mode.py:535-555) raises for linker classes it does not
+    # know; rewrites that consult it (local_careduce_fusion) treat us like a C target
+    import aesara.compile.mode as _m
+
+    if not getattr(_m.get_target_language, "_b200", False):
+        _orig = _m.get_target_language
+
+        def get_target_language(mode=None):
+            m = _m.get_default_mode() if mode is None else mode
+            if isinstance(getattr(m, "linker", None), B200Linker):
+                return ("c",)
+            return _orig(mode)
+
+        get_target_language._b200 = True
+        _m.get_target_language = get_target_language
+
+
+register()

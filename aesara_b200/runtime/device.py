@@ -72,7 +72,8 @@ class DeviceArray:
     @staticmethod
     def from_numpy(a, device=None, pinned_ok=True):
         a = np.asarray(a)
-        src = np.ascontiguousarray(a)
+        # (np.ascontiguousarray would promote 0-d arrays to 1-d)
+        src = a if a.flags.c_contiguous else np.array(a, order="C")
         out = DeviceArray.empty(src.shape, src.dtype, device=device)
         if src.size:
             hb = torch.from_numpy(src.reshape(-1).view(np.uint8))

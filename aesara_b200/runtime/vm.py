@@ -570,4 +570,5 @@ def _incsubtensor(ex, i, node, args):
 
 @_op("Scan")
 def _scan(ex, i, node, args):
-    return ex._state[i]["runner"].run(args)
+    outs = ex._state[i]["runner"].run(args)
+    return outs[0] if len(node.outputs) == 1 else outs

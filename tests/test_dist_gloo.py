@@ -1,0 +1,87 @@
+"""CPU, world_size 2 over gloo: the host-side sharding logic (row blocks, packed
+exchange layout, mean-of-shards weights) reproduces the unsharded result.  The
+per-shard evaluation uses the oracle interpreter here; on the GPU box the same
+logic drives the device executor (bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from aesara_b200.shard import combine_weights, pack_layout, row_block
+
+
+def test_row_blocks_cover_and_balance():
+    for n, w in [(10, 3), (7, 8), (1 << 20, 8), (0, 2)]:
+        blocks = [row_block(n, w, r) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        sizes = [b - a for a, b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_pack_layout_alignment():
+    L = pack_layout([(), (5,), (3, 3)])
+    assert L.offsets == [0, 4, 12] and L.total == 24
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_rows, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.program_np import run_program
+    from tests._cases import load_case
+
+    prog, _, _ = load_case("cfg5_logreg")
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((n_rows, 16)).astype("float32")
+    y = (rng.random(n_rows) < 0.5).astype("float32")
+    w = (rng.standard_normal(16) * 0.1).astype("float32")
+    a, b = row_block(n_rows, world, rank)
+    outs = run_program(prog, [X[a:b], y[a:b], w, np.float32(0.1)])
+    L = pack_layout([np.shape(o) for o in outs])
+    flat = torch.zeros(L.total, dtype=torch.float32)
+    for o, off in zip(outs, L.offsets):
+        o = np.asarray(o, "float32").reshape(-1)
+        flat[off : off + o.size] = torch.from_numpy(o.copy())
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    rows = [row_block(n_rows, world, r) for r in range(world)]
+    wts = combine_weights("mean", [e - s for s, e in rows])
+    comb = sum(wt * g for wt, g in zip(wts, gathered)).numpy()
+    if rank == 0:
+        full = run_program(prog, [X, y, w, np.float32(0.1)])
+        res = []
+        for o, s, off in zip(full, L.shapes, L.offsets):
+            n = int(np.prod(s)) if s else 1
+            res.append((np.asarray(o, "float32").reshape(-1), comb[off : off + n]))
+        q.put([(a.tolist(), b.tolist()) for a, b in res])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_logreg_matches_unsharded_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 101, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=100)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for full, comb in res:
+        np.testing.assert_allclose(comb, full, rtol=2e-5, atol=1e-6)
