@@ -137,6 +137,7 @@ struct GemmParams {
   float* C;
   long long c_rs, c_cs;
   int block_n;            // 64 / 128 / 256
+  int acc_stages;         // TMEM accumulator stages (2 -> epilogue overlaps the next tile)
   int stages;
   int nparts;             // 1, or 2 for the hi/lo split (3 MMAs per k-step)
   int k_elems_per_row;    // elements per 128-byte smem row: 32 (tf32) or 64 (bf16)
@@ -157,30 +158,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
                                              ~static_cast<uintptr_t>(1023));
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stage_bytes = p.nparts * (p.a_tile_bytes + p.b_tile_bytes);
-  const long long m0 = (long long)blockIdx.y * BLOCK_M;
-  const long long n0 = (long long)blockIdx.x * p.block_n;
   const int num_k_blocks = (int)((p.K + p.k_elems_per_row - 1) / p.k_elems_per_row);
+  // persistent tile scheduler: CTA b handles tiles b, b + gridDim.x, ...; N-tiles are
+  // consecutive so the CTAs resident at one time share A row panels and all of B in L2
+  const long long tiles_n = (p.N + p.block_n - 1) / p.block_n;
+  const long long num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * tiles_n;
+  const uint32_t tmem_cols = (uint32_t)(p.acc_stages * p.block_n);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);  // every epilogue thread arrives
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    // allocate the accumulator columns (power of two >= 32)
+    // allocate the accumulator columns (power of two >= 32): acc_stages x block_n
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_slot)),
-                 "r"((uint32_t)p.block_n)
+                 "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -196,19 +204,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b0)) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sbase = smem + (size_t)stage * stage_bytes;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-        const int kc = kb * p.k_elems_per_row;
-        tma_load_2d(sbase, &map_a0, &full_bar[stage], kc, (int)m0);
-        tma_load_2d(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, (int)n0);
-        if (p.nparts == 2) {
-          tma_load_2d(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, (int)m0);
-          tma_load_2d(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc,
-                      (int)n0);
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (int)((tile / tiles_n) * BLOCK_M);
+        const int n0 = (int)((tile % tiles_n) * p.block_n);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sbase = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          const int kc = kb * p.k_elems_per_row;
+          tma_load_2d(sbase, &map_a0, &full_bar[stage], kc, m0);
+          tma_load_2d(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0);
+          if (p.nparts == 2) {
+            tma_load_2d(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0);
+            tma_load_2d(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc,
+                        n0);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -216,43 +228,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      uint32_t it = 0;  // tiles processed by this CTA
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it % (uint32_t)p.acc_stages;
+        const uint32_t aphase = (it / (uint32_t)p.acc_stages) & 1u;
+        // wait until the epilogue has drained this accumulator stage
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         tcgen05_fence_after();
-        const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t a_hi = sbase;
-        const uint32_t a_lo = sbase + p.a_tile_bytes;
-        const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
-        const uint32_t b_lo = b_hi + p.b_tile_bytes;
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t a_hi = sbase;
+          const uint32_t a_lo = sbase + p.a_tile_bytes;
+          const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
+          const uint32_t b_lo = b_hi + p.b_tile_bytes;
 #pragma unroll
-        for (int k = 0; k < SW_BYTES / 32; ++k) {  // 32 bytes of K per instruction
-          const uint32_t koff = k * 32;
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          if (p.nparts == 2) {
-            // small cross terms first, the dominant hi*hi term last
-            umma<KIND>(tmem_base, make_smem_desc(a_lo + koff), make_smem_desc(b_hi + koff), p.idesc, acc);
-            umma<KIND>(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(b_lo + koff), p.idesc, 1u);
-            umma<KIND>(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(b_hi + koff), p.idesc, 1u);
-          } else {
-            umma<KIND>(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(b_hi + koff), p.idesc, acc);
+          for (int k = 0; k < SW_BYTES / 32; ++k) {  // 32 bytes of K per instruction
+            const uint32_t koff = k * 32;
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            if (p.nparts == 2) {
+              // small cross terms first, the dominant hi*hi term last
+              umma<KIND>(d_tmem, make_smem_desc(a_lo + koff), make_smem_desc(b_hi + koff), p.idesc, acc);
+              umma<KIND>(d_tmem, make_smem_desc(a_hi + koff), make_smem_desc(b_lo + koff), p.idesc, 1u);
+              umma<KIND>(d_tmem, make_smem_desc(a_hi + koff), make_smem_desc(b_hi + koff), p.idesc, 1u);
+            } else {
+              umma<KIND>(d_tmem, make_smem_desc(a_hi + koff), make_smem_desc(b_hi + koff), p.idesc, acc);
+            }
           }
+          tcgen05_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        tcgen05_commit(&tmem_full_bar[as]);  // accumulator complete
       }
-      tcgen05_commit(&tmem_full_bar);  // accumulator complete
     }
   } else {
     // ================= epilogue (warps 2..5) =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    mbar_wait(&tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const long long row = m0 + q * 32 + lane;
     const bool vec_ok = (p.c_cs == 1) && ((p.c_rs & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t as = it % (uint32_t)p.acc_stages;
+    const uint32_t aphase = (it / (uint32_t)p.acc_stages) & 1u;
+    const long long m0 = (tile / tiles_n) * BLOCK_M;
+    const long long n0 = (tile % tiles_n) * p.block_n;
+    mbar_wait(&tmem_full_bar[as], aphase);
+    tcgen05_fence_after();
+    const long long row = m0 + q * 32 + lane;
+    const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
     for (int c0 = 0; c0 < p.block_n; c0 += 32) {
       uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_32x32b_x32(t_acc + (uint32_t)c0, r);
+      if (c0 + 32 >= p.block_n) {
+        // last chunk is in registers: hand the accumulator stage back to the MMA warp
+        tcgen05_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
+                     : "memory");
+      }
       if (row < p.M) {
         const long long col0 = n0 + c0;
         float* crow = p.C + row * p.c_rs;
@@ -285,13 +319,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
         }
       }
     }
+    }  // tile loop
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)p.block_n)
+                 "r"(tmem_cols)
                  : "memory");
   }
 }
@@ -466,6 +501,7 @@ int gemm_tcgen05_f32(int precision, long long M, long long N, long long K, float
   p.b_tile_bytes = p.block_n * SW_BYTES;
   const int stage_bytes = parts * (p.a_tile_bytes + p.b_tile_bytes);
   p.stages = std::max(2, std::min(8, (kMaxSmem - 1024) / stage_bytes));
+  p.acc_stages = 2;  // 2 x block_n <= 512 TMEM columns
   // cute UMMA::InstrDescriptor: c_format F32=1 @[4,6), a/b format @[7,10)/[10,13)
   // (TF32=2, BF16=1), K-major both (@15, @16 = 0), N>>3 @[17,23), M>>4 @[24,29)
   const uint32_t fmt = bf16 ? 1u : 2u;
@@ -481,8 +517,14 @@ int gemm_tcgen05_f32(int precision, long long M, long long N, long long K, float
     if ((rc = make_map(&mb1, b_plane[1], bf16, N, K, b_pitch, p.block_n))) return rc;
   }
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  dim3 grid((unsigned)((N + p.block_n - 1) / p.block_n), (unsigned)((M + BLOCK_M - 1) / BLOCK_M));
-  if (grid.y > 65535) return fail(AB_ERR_UNSUPPORTED, "gemm with more than 8M rows");
+  const long long num_tiles = ((N + p.block_n - 1) / p.block_n) * ((M + BLOCK_M - 1) / BLOCK_M);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  dim3 grid((unsigned)std::min<long long>(num_tiles, sms));  // persistent: one CTA per SM
   if (bf16) {
     static bool attr1 = false;
     if (!attr1) {

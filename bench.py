@@ -49,10 +49,49 @@ def workload_spec(name, args):
             elemwise_bytes=16.0 * n,                   # 4 arrays x N x 4 B
             gemm_flops=0.0, n_gemm=0,
         )
+    if name == "lstm":
+        T, B, H = args.steps_t or 128, args.batch or 8192, args.hidden or 1024
+        return dict(
+            name="lstm", program="cfg4_lstm", T=T, B=B, H=H, graph=True,
+            desc=f"cfg4: Scan LSTM cell, T={T} steps, batch {B}, hidden {H}, f32",
+            gemm_flops=2.0 * T * B * H * 4 * H, n_gemm=T,      # 8.80 TFLOP
+            elemwise_bytes=(T * B * 4 * H + 4 * B * H + H * 4 * H) * 4.0,  # 17.33 GB ideal
+        )
+    if name == "logreg":
+        N, D = args.n or (1 << 24), args.hidden or 512
+        return dict(
+            name="logreg", program="cfg5_logreg", N=N, D=D, graph=True,
+            desc=f"cfg5: logistic-regression cost+grad, {N} rows x {D} f32 per GPU",
+            gemm_flops=0.0, n_gemm=0,
+            elemwise_bytes=(2.0 * N * D + 12.0 * N) * 4,      # SURVEY §8d graph-as-optimised
+        )
+    if name == "readme":
+        n = args.n or 1000
+        return dict(
+            name="readme", program="cfg1_readme", n=n, graph=True,
+            desc=f"cfg1: README a/a + (M+a).dot(v), {n}x{n} f64",
+            gemm_flops=0.0, n_gemm=0, elemwise_bytes=24.0 * n * n,
+        )
     raise SystemExit(f"unknown workload {name}")
 
 
 def make_inputs_numpy(spec, rng, scale_rows=None):
+    if spec["name"] == "lstm":
+        T, H = spec["T"], spec["H"]
+        B = scale_rows or spec["B"]
+        x = rng.standard_normal((T, B, 4 * H), dtype=np.float32)
+        U = (rng.standard_normal((H, 4 * H), dtype=np.float32) / np.sqrt(H)).astype(np.float32)
+        return [x, np.zeros((B, H), np.float32), np.zeros((B, H), np.float32), U]
+    if spec["name"] == "logreg":
+        N = scale_rows or spec["N"]
+        D = spec["D"]
+        X = rng.standard_normal((N, D), dtype=np.float32)
+        y = (rng.random(N) < 0.5).astype(np.float32)
+        w = (rng.standard_normal(D) * 0.01).astype(np.float32)
+        return [X, y, w, np.float32(0.0)]
+    if spec["name"] == "readme":
+        n = spec["n"]
+        return [np.float64(1.5), rng.standard_normal(n), rng.standard_normal((n, n))]
     if spec["name"] == "mlp":
         B = scale_rows or spec["B"]
         H = spec["H"]
@@ -80,6 +119,24 @@ def make_inputs_device(spec, seed):
         b1 = torch.zeros(H, device="cuda")
         b2 = torch.zeros(H, device="cuda")
         ts = [X, Y, W1, b1, W2, b2]
+    elif spec["name"] == "lstm":
+        T, B, H = spec["T"], spec["B"], spec["H"]
+        x = torch.randn(T, B, 4 * H, device="cuda", generator=g)
+        U = torch.randn(H, 4 * H, device="cuda", generator=g) / H ** 0.5
+        ts = [x, torch.zeros(B, H, device="cuda"), torch.zeros(B, H, device="cuda"), U]
+    elif spec["name"] == "logreg":
+        N, D = spec["N"], spec["D"]
+        X = torch.randn(N, D, device="cuda", generator=g)
+        y = (torch.rand(N, device="cuda", generator=g) < 0.5).float()
+        w = torch.randn(D, device="cuda", generator=g) * 0.01
+        ts = [X, y, w]
+        return [DeviceArray.from_torch(t) for t in ts] + [np.float32(0.0)], ts
+    elif spec["name"] == "readme":
+        n = spec["n"]
+        v = torch.randn(n, device="cuda", generator=g, dtype=torch.float64)
+        M = torch.randn(n, n, device="cuda", generator=g, dtype=torch.float64)
+        ts = [v, M]
+        return [np.float64(1.5)] + [DeviceArray.from_torch(t) for t in ts], ts
     else:
         ts = [torch.randn(spec["n"], device="cuda", generator=g) for _ in range(3)]
     return [DeviceArray.from_torch(t) for t in ts], ts
@@ -163,6 +220,15 @@ def cpu_baseline(spec, seconds_budget=20.0):
     if spec["name"] == "mlp":
         rows, full = min(spec["B"], 1024), spec["B"]
         sample = f"B={rows} rows of {full} (H={spec['H']}); time scaled by {full}/{rows}"
+    elif spec["name"] == "lstm":
+        rows, full = min(spec["B"], 128), spec["B"]
+        sample = f"B={rows} batch rows of {full} (T={spec['T']}, H={spec['H']}); time scaled by {full}/{rows}"
+    elif spec["name"] == "logreg":
+        rows, full = min(spec["N"], 1 << 18), spec["N"]
+        sample = f"{rows} of {full} rows (D={spec['D']}); time scaled by {full}/{rows}"
+    elif spec["name"] == "readme":
+        rows, full = None, 1
+        sample = "full size"
     else:
         rows, full = min(spec["n"], 1 << 22), spec["n"]
         sample = f"{rows} of {full} elements; time scaled by {full}/{rows}"
@@ -174,7 +240,7 @@ def cpu_baseline(spec, seconds_budget=20.0):
         t0 = time.perf_counter()
         run_program(prog, ins)
         times.append(time.perf_counter() - t0)
-    t = float(np.median(times)) * (full / rows)
+    t = float(np.median(times)) * ((full / rows) if rows else 1.0)
     return {"value": 1.0 / t, "unit": "graph-evals/s", "cores": os.cpu_count(), "kind": "port",
             "sample": sample, "ms_per_eval_extrapolated": t * 1e3}
 
@@ -212,8 +278,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="mlp", choices=["mlp", "elemwise"])
-    ap.add_argument("--precision", default="bf16", choices=list(PRECISIONS))
+    ap.add_argument("--workload", default="mlp", choices=["mlp", "elemwise", "lstm", "logreg", "readme"])
+    ap.add_argument("--steps-t", type=int, default=0, help="Scan length for --workload lstm")
+    ap.add_argument("--graph", type=int, default=-1, help="1/0: replay the evaluation as a CUDA graph")
+    ap.add_argument("--precision", default=None, choices=list(PRECISIONS),
+                    help="GEMM compute policy; default: bf16 for mlp (BASELINE cfg3), fp32 (3xTF32) otherwise")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--hidden", type=int, default=0)
     ap.add_argument("--n", type=int, default=0)
@@ -221,6 +290,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     spec = workload_spec(args.workload, args)
+    if args.precision is None:
+        args.precision = "bf16" if args.workload == "mlp" else "fp32"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -244,8 +315,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     prec = PRECISIONS[args.precision]
     prog = Program.load(os.path.join(GOLDEN, spec["program"] + ".json"))
-    ex = ProgramExecutor(prog, precision=prec, host_outputs=False, time_nodes=True)
+    use_graph = bool(spec.get("graph")) if args.graph < 0 else bool(args.graph)
+    ex = ProgramExecutor(prog, precision=prec, host_outputs=False, time_nodes=not use_graph)
     dev_in, keep = make_inputs_device(spec, seed=1234 + rank)
+    run = ex
+    if use_graph:
+        from aesara_b200.runtime.graph import GraphReplay
+
+        run = GraphReplay(ex)
 
     combiner = None
     if world > 1:
@@ -254,7 +331,7 @@ def main():
         combiner = OutputCombiner(world, mode="mean")
 
     def step():
-        outs = ex(*dev_in)
+        outs = run(*dev_in)
         if combiner is not None:
             outs = combiner(outs)
         return outs
@@ -277,12 +354,19 @@ def main():
     pending = []
     for _ in range(args.steps):
         step()
-        pending.append(ex.node_events)
+        if not use_graph:
+            pending.append(ex.node_events)
     e1.record()
     barrier()
     clk = clocks.stop()
     ms_total = e0.elapsed_time(e1)
     launches = lib.load().ab_launch_count() - launches0
+    if use_graph:
+        # a replayed graph re-issues the kernels captured once: count them from one eager call
+        l0 = lib.load().ab_launch_count()
+        ex(*dev_in)
+        torch.cuda.synchronize()
+        launches = (lib.load().ab_launch_count() - l0) * args.steps if run.replays else launches
     for evs in pending:
         for i, a, b in evs:
             node_ms.setdefault(i, []).append(a.elapsed_time(b))
@@ -304,7 +388,29 @@ def main():
         else:
             other_ms += t
     peaks = measured_peaks()
-    if spec["n_gemm"]:
+    if use_graph:
+        # no per-node events inside a replayed graph: the roofline is taken over the whole
+        # step (conservative: every kernel of the evaluation is charged to the bound resource)
+        roofline_hbm = None
+        if spec["n_gemm"]:
+            ach = spec["gemm_flops"] / (ms_step * 1e-3) / 1e12
+            peak = peaks["bf16"] if args.precision == "bf16" else peaks["bf16"] / 2.0
+            roofline = {"bound": "tensor", "kernel": "whole evaluation (CUDA-graph replay); Gemm = gemm_tcgen05_kernel",
+                        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "peak_source": peaks["src"] + ("" if args.precision == "bf16" else "; tf32 = bf16/2 (nominal ratio)"),
+                        "traffic": None, "ms_per_step": ms_step}
+            ach_h = spec["elemwise_bytes"] / (ms_step * 1e-3) / 1e9
+            roofline_hbm = {"bound": "hbm", "kernel": "whole evaluation", "achieved": ach_h,
+                            "peak": peaks["hbm"], "unit": "GB/s", "frac": ach_h / peaks["hbm"],
+                            "peak_source": peaks["src"], "traffic": None, "ms_per_step": ms_step}
+        else:
+            ach_h = spec["elemwise_bytes"] / (ms_step * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "whole evaluation (CUDA-graph replay)",
+                        "achieved": ach_h, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": ach_h / peaks["hbm"], "peak_source": peaks["src"], "traffic": None,
+                        "ms_per_step": ms_step}
+        gemm_ms = hbm_ms = other_ms = None
+    elif spec["n_gemm"]:
         ach = spec["gemm_flops"] / (gemm_ms * 1e-3) / 1e12
         peak = peaks["bf16"] if args.precision == "bf16" else peaks["bf16"] / 2.0
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (+operand pack) per Gemm/Dot22 node",
@@ -334,14 +440,21 @@ def main():
             h.copy_(t)
             host_in.append(h)
             h2d += h.numel() * h.element_size()
+        template = [None if isinstance(a, DeviceArray) else a for a in dev_in]
         del keep[:]
         del dev_in[:]
+        run = None
         torch.cuda.empty_cache()
         ex2 = ProgramExecutor(prog, precision=prec, host_outputs=False)
 
         def e2e_step():
             dins = []
-            for h in host_in:
+            it = iter(host_in)
+            for slot in template:
+                if slot is not None:
+                    dins.append(slot)  # host scalar argument
+                    continue
+                h = next(it)
                 d = torch.empty(h.shape, dtype=h.dtype, device="cuda")
                 d.copy_(h, non_blocking=True)
                 dins.append(DeviceArray.from_torch(d))
@@ -373,9 +486,11 @@ def main():
             if spec["n_gemm"] else "f32",
             "data": "synthetic",
             "config": {"workload": spec["desc"], "parallelism": par,
-                       "l2": "inputs >> 126 MB L2, no flush needed",
+                       "l2": ("working set fits L2: launch-latency bound, reported as evals/s only"
+                              if spec["name"] == "readme" else "inputs >> 126 MB L2, no flush needed"),
+                       "executor": "cuda-graph replay" if use_graph else "eager launches + per-node CUDA events",
                        "gemm_precision": args.precision if spec["n_gemm"] else None,
-                       "per_gpu": {k: spec[k] for k in ("B", "H", "n") if k in spec}},
+                       "per_gpu": {k: spec[k] for k in ("B", "H", "n", "N", "D", "T") if k in spec}},
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "device_ms": {"gemm": gemm_ms, "elemwise_careduce": hbm_ms, "other": other_ms},
             "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,

@@ -1,0 +1,162 @@
+"""GPU: the BLAS-family kernels called directly through the C ABI, over the
+shape / stride / alpha-beta cases of tests/tensor/test_blas.py (TestGemm :118-422,
+TestGemv :1545-1752, TestGer :1861-2083) — ragged tiles, K tails, transposed and
+padded operands, all three GEMM precisions.  Truth is a float64 NumPy product;
+fp32-faithful mode must stay within rtol 1e-5 norm-wise (the bar vs sgemm)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import torch
+
+    from aesara_b200.runtime import kernels, lib
+
+    lib.check(lib.load().ab_init(0))
+    torch.cuda.set_device(0)
+    return kernels
+
+
+def _dev(a):
+    from aesara_b200.runtime.device import DeviceArray
+
+    return DeviceArray.from_numpy(a)
+
+
+def _normwise(got, want):
+    return float(np.max(np.abs(got - want)) / max(np.max(np.abs(want)), 1e-30))
+
+
+GEMM_SHAPES = [
+    (128, 256, 64), (130, 70, 96), (64, 64, 32), (257, 513, 100), (1000, 300, 36),
+    (4096, 512, 1024), (300, 2000, 129), (128, 256, 33),
+]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+@pytest.mark.parametrize("layout", ["nn", "tn", "nt", "tt", "padded"])
+def test_gemm_fp32_faithful(K, m, n, k, layout):
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    a = rng.standard_normal((m, k)).astype("float32")
+    b = rng.standard_normal((k, n)).astype("float32")
+    c0 = rng.standard_normal((m, n)).astype("float32")
+    A, B = _dev(a), _dev(b)
+    if layout[0] == "t":
+        A = _dev(np.ascontiguousarray(a.T)).dimshuffle([1, 0])
+    if layout[1] == "t":
+        B = _dev(np.ascontiguousarray(b.T)).dimshuffle([1, 0])
+    if layout == "padded":
+        ap = np.zeros((m, k + 3), "float32"); ap[:, :k] = a
+        bp = np.zeros((k, n + 5), "float32"); bp[:, :n] = b
+        A = _dev(ap).index((slice(None), slice(0, k)))
+        B = _dev(bp).index((slice(None), slice(0, n)))
+    C = _dev(c0)
+    K.gemm(C, 0.8, A, B, 0.4, precision=0)
+    want = 0.4 * c0.astype(np.float64) + 0.8 * (a.astype(np.float64) @ b.astype(np.float64))
+    err = _normwise(C.to_numpy(), want)
+    assert err < 1e-5, f"3xTF32 gemm normwise error {err}"
+
+
+@pytest.mark.parametrize("precision,tol", [(1, 2e-3), (2, 2e-2)])
+def test_gemm_reduced_precision_policies(K, precision, tol):
+    """TF32 / BF16 compute policies: stated looser tolerances."""
+    rng = np.random.default_rng(5)
+    m, n, k = 512, 384, 256
+    a = rng.standard_normal((m, k)).astype("float32")
+    b = rng.standard_normal((k, n)).astype("float32")
+    C = _dev(np.zeros((m, n), "float32"))
+    K.gemm(C, 1.0, _dev(a), _dev(b), 0.0, precision=precision)
+    err = _normwise(C.to_numpy(), a.astype(np.float64) @ b.astype(np.float64))
+    assert err < tol
+
+
+def test_gemm_beta_zero_ignores_uninitialised_c(K):
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((256, 128)).astype("float32")
+    b = rng.standard_normal((128, 256)).astype("float32")
+    C = _dev(np.full((256, 256), np.nan, "float32"))
+    K.gemm(C, 1.0, _dev(a), _dev(b), 0.0)
+    assert np.isfinite(C.to_numpy()).all()
+
+
+def test_gemm_strided_output(K):
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal((200, 64)).astype("float32")
+    b = rng.standard_normal((64, 150)).astype("float32")
+    cbuf = np.zeros((150, 200), "float32")
+    Ct = _dev(cbuf).dimshuffle([1, 0])  # column-major C
+    K.gemm(Ct, 1.0, _dev(a), _dev(b), 0.0)
+    assert _normwise(Ct.to_numpy(), a.astype(np.float64) @ b.astype(np.float64)) < 1e-5
+
+
+@pytest.mark.parametrize("m,n,k", [(50, 60, 33), (300, 200, 150)])
+def test_gemm_f64(K, m, n, k):
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal((m, k)), rng.standard_normal((k, n))
+    c0 = rng.standard_normal((m, n))
+    C = _dev(c0)
+    K.gemm(C, -1.5, _dev(a), _dev(np.ascontiguousarray(b.T)).dimshuffle([1, 0]), 2.0)
+    np.testing.assert_allclose(C.to_numpy(), 2.0 * c0 - 1.5 * (a @ b), rtol=1e-12, atol=1e-11)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("m,n", [(1, 1), (7, 3), (300, 129), (129, 300), (4096, 512), (33, 10000)])
+@pytest.mark.parametrize("trans", [False, True])
+def test_gemv(K, dtype, m, n, trans):
+    rng = np.random.default_rng(m + n)
+    a = rng.standard_normal((m, n)).astype(dtype)
+    x = rng.standard_normal(n).astype(dtype)
+    y0 = rng.standard_normal(m).astype(dtype)
+    A = _dev(np.ascontiguousarray(a.T)).dimshuffle([1, 0]) if trans else _dev(a)
+    for alpha, beta in [(1.0, 0.0), (0.5, 2.0)]:
+        y = _dev(np.full(m, np.nan, dtype) if beta == 0.0 else y0)
+        K.gemv(y, alpha, A, _dev(x), beta)
+        want = alpha * (a.astype(np.float64) @ x) + (beta * y0 if beta else 0)
+        tol = 1e-5 if dtype == "float32" else 1e-12
+        assert _normwise(y.to_numpy(), want) < tol
+
+
+def test_gemv_strided_vectors(K):
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal((64, 48)).astype("float32")
+    xb = rng.standard_normal(96).astype("float32")
+    yb = np.zeros(128, "float32")
+    x = _dev(xb).index((slice(None, None, 2),))
+    y = _dev(yb).index((slice(None, None, 2),))
+    K.gemv(y, 1.0, _dev(a), x, 0.0)
+    assert _normwise(y.to_numpy(), a.astype(np.float64) @ xb[::2]) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_ger(K, dtype):
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((130, 77)).astype(dtype)
+    x = rng.standard_normal(130).astype(dtype)
+    y = rng.standard_normal(77).astype(dtype)
+    A = _dev(a)
+    K.ger(A, 0.7, _dev(x), _dev(y))
+    np.testing.assert_allclose(A.to_numpy(), a + 0.7 * np.outer(x, y), rtol=1e-5 if dtype == "float32" else 1e-12)
+    At = _dev(np.ascontiguousarray(a.T)).dimshuffle([1, 0])
+    K.ger(At, 0.7, _dev(x), _dev(y))
+    np.testing.assert_allclose(At.to_numpy(), a + 0.7 * np.outer(x, y), rtol=1e-5 if dtype == "float32" else 1e-12)
+
+
+def test_careduce_large_patterns(K):
+    """Reduction geometries at sizes where the split / two-stage paths engage."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((3000, 1030)).astype("float32")
+    X = _dev(x)
+    k = K.CAReduceKernel.get("add", "float32", "float64", "float32")
+    for axis in [(0,), (1,), (0, 1)]:
+        got = k.launch(X, axis).to_numpy()
+        want = x.astype(np.float64).sum(axis=axis).astype("float32")
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-4)
+    xt = _dev(np.ascontiguousarray(x.T)).dimshuffle([1, 0])
+    np.testing.assert_allclose(k.launch(xt, (0,)).to_numpy(), x.astype(np.float64).sum(0).astype("float32"),
+                               rtol=1e-6, atol=1e-4)
+    km = K.CAReduceKernel.get("maximum", "float32", "float32", "float32")
+    np.testing.assert_array_equal(km.launch(X, (0,)).to_numpy(), x.max(0))
+    np.testing.assert_array_equal(km.launch(X, (0, 1)).to_numpy(), x.max())
