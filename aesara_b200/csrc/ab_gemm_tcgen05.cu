@@ -121,10 +121,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 // field layout): start address >>4 in [0,14), LBO>>4 in [16,30), SBO>>4 in
 // [32,46), version=1 in [46,48), layout type SWIZZLE_128B=2 in [61,64).
 // Rows are 128 bytes apart, groups of 8 rows 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+//
+// MN-major operands (the operand's M/N index is the contiguous one in memory — a
+// DimShuffle{1,0} view, or B given as [K,N] row-major) use the canonical layout
+// ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)): 128-byte chunks of the MN index, one row
+// per K index (128 B apart), 8-row groups SBO = 1024 B apart, and the next MN
+// chunk LBO bytes further — exactly what one 2-D TMA box {128 B of MN, BLOCK_K
+// rows} per chunk writes.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major) = 16 B
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // LBO: 16 B (unused) for K-major
   d |= (uint64_t)(1024 >> 4) << 32;   // SBO = 8 rows * 128 B
   d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;             // SWIZZLE_128B
@@ -136,14 +143,34 @@ struct GemmParams {
   float alpha, beta;
   float* C;
   long long c_rs, c_cs;
+  const float* Cin;       // beta term source (== C for the in-place Gemm, another buffer otherwise)
+  long long cin_rs, cin_cs;
   int block_n;            // 64 / 128 / 256
   int acc_stages;         // TMEM accumulator stages (2 -> epilogue overlaps the next tile)
   int stages;
   int nparts;             // 1, or 2 for the hi/lo split (3 MMAs per k-step)
-  int k_elems_per_row;    // elements per 128-byte smem row: 32 (tf32) or 64 (bf16)
+  int k_elems_per_row;    // K elements per stage = per 128-byte K-major row: 32 (tf32) / 64 (bf16)
   int a_tile_bytes, b_tile_bytes;
+  int a_mn, b_mn;         // operand is MN-major
+  int a_chunks, b_chunks; // MN-major: 128-byte MN chunks per tile (tile_rows * elem_size / 128)
+  int chunk_bytes;        // MN-major: k_elems_per_row rows * 128 B
+  int mn_per_chunk;       // MN-major: elements per chunk (128 / elem_size)
+  int a_kstep, b_kstep;   // descriptor advance per MMA K-step: 32 B (K-major) or umma_k rows * 128 B
   uint32_t idesc;
 };
+
+// one operand tile -> shared memory.  K-major: a single box {128 B of K, tile rows};
+// MN-major: one box {128 B of MN, BLOCK_K rows} per chunk.
+__device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
+                                          int kc, int mn0, int mn_major, int chunks,
+                                          const GemmParams& p) {
+  if (!mn_major) {
+    tma_load_2d(dst, map, bar, kc, mn0);
+  } else {
+    for (int c = 0; c < chunks; ++c)
+      tma_load_2d(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
+  }
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -212,12 +239,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
           uint8_t* sbase = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           const int kc = kb * p.k_elems_per_row;
-          tma_load_2d(sbase, &map_a0, &full_bar[stage], kc, m0);
-          tma_load_2d(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0);
+          load_tile(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
+          load_tile(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0, p.b_mn,
+                    p.b_chunks, p);
           if (p.nparts == 2) {
-            tma_load_2d(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0);
-            tma_load_2d(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc,
-                        n0);
+            load_tile(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
+            load_tile(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc, n0,
+                      p.b_mn, p.b_chunks, p);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -245,16 +273,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
           const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
           const uint32_t b_lo = b_hi + p.b_tile_bytes;
 #pragma unroll
+          const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
+          const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
           for (int k = 0; k < SW_BYTES / 32; ++k) {  // 32 bytes of K per instruction
-            const uint32_t koff = k * 32;
+            const uint32_t ka = k * (uint32_t)p.a_kstep, kb_off = k * (uint32_t)p.b_kstep;
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
             if (p.nparts == 2) {
               // small cross terms first, the dominant hi*hi term last
-              umma<KIND>(d_tmem, make_smem_desc(a_lo + koff), make_smem_desc(b_hi + koff), p.idesc, acc);
-              umma<KIND>(d_tmem, make_smem_desc(a_hi + koff), make_smem_desc(b_lo + koff), p.idesc, 1u);
-              umma<KIND>(d_tmem, make_smem_desc(a_hi + koff), make_smem_desc(b_hi + koff), p.idesc, 1u);
+              umma<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
+              umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kb_off, b_lbo), p.idesc, 1u);
+              umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, 1u);
             } else {
-              umma<KIND>(d_tmem, make_smem_desc(a_hi + koff), make_smem_desc(b_hi + koff), p.idesc, acc);
+              umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
             }
           }
           tcgen05_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
@@ -267,7 +297,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
     // ================= epilogue (warps 2..5) =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const bool vec_ok = (p.c_cs == 1) && ((p.c_rs & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
+                                            ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const uint32_t as = it % (uint32_t)p.acc_stages;
@@ -290,6 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
       if (row < p.M) {
         const long long col0 = n0 + c0;
         float* crow = p.C + row * p.c_rs;
+        const float* irow = p.Cin + row * p.cin_rs;
         if (vec_ok && col0 + 32 <= p.N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -300,7 +333,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
             v.w = p.alpha * __uint_as_float(r[j + 3]);
             float4* dst = reinterpret_cast<float4*>(crow + col0 + j);
             if (p.beta != 0.0f) {
-              const float4 o = *dst;
+              const float4 o = *reinterpret_cast<const float4*>(irow + col0 + j);
               v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
             }
             *dst = v;
@@ -312,7 +345,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
             if (col < p.N) {
               float* dst = crow + col * p.c_cs;
               float v = p.alpha * __uint_as_float(r[j]);
-              if (p.beta != 0.0f) v += p.beta * (*dst);
+              if (p.beta != 0.0f) v += p.beta * irow[col * p.cin_cs];
               *dst = v;
             }
           }
@@ -395,14 +428,16 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_map(CUtensorMap* map, const void* base, bool bf16, long long rows, long long kc,
-             long long pitch_elems, int box_rows) {
+// tensor map over a plane whose contiguous ("inner") index has `inner` elements and whose
+// rows are `pitch_elems` apart; box = {128 bytes of the inner index, box_outer rows}
+int make_map(CUtensorMap* map, const void* base, bool bf16, long long inner, long long outer,
+             long long pitch_elems, int box_outer) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(AB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int es = bf16 ? 2 : 4;
-  cuuint64_t dims[2] = {(cuuint64_t)kc, (cuuint64_t)rows};
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * es};
-  cuuint32_t box[2] = {(cuuint32_t)(SW_BYTES / es), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(SW_BYTES / es), (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -414,40 +449,183 @@ int make_map(CUtensorMap* map, const void* base, bool bf16, long long rows, long
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct OperandPlan {
-  bool pack;          // needs the pack pre-pass
-  long long pitch;    // elements per packed row
-  size_t plane_bytes; // bytes of one packed plane
-};
-
-// logical operand [R, Kc] with element strides (s_r, s_c)
-OperandPlan plan_operand(int precision, long long R, long long Kc, long long s_r, long long s_c,
-                         const void* ptr) {
-  OperandPlan o{};
-  const bool direct_ok = (precision == 1) && (s_c == 1 || Kc == 1) && (s_r % 4 == 0) && s_r >= Kc &&
-                         (reinterpret_cast<uintptr_t>(ptr) % 16 == 0);
-  o.pack = !direct_ok;
-  const int es = precision == 2 ? 2 : 4;
-  o.pitch = (long long)align_up((size_t)Kc, 16 / es);
-  o.plane_bytes = o.pack ? align_up((size_t)R * o.pitch * es, 1024) : 0;
-  return o;
-}
-
 bool eligible(long long M, long long N, long long K) {
   return M >= 64 && N >= 64 && K >= 32 && (double)M * N * K >= (double)(1 << 21) &&
          M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31);
 }
 
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
 }  // namespace
+
+// A GEMM operand in tensor-core form: logical [rows, k] (rows = M for A, N for B).
+//   mn_major == 0: planes are [rows, pitch] with K contiguous;
+//   mn_major == 1: planes are [k, pitch] with the M/N index contiguous.
+// plane[1] is the tf32 "lo" plane of the 3xTF32 split (precision 0), else null.
+struct PackedOperand {
+  const void* plane[2];
+  long long rows, k, pitch;
+  int mn_major;
+  int precision;
+};
+
+// Decide how the logical operand [rows, k] with element strides (s_r, s_k) is presented
+// to the tensor cores.  `direct` = usable in place (precision 1 only: raw fp32, aligned).
+static void plan_operand(int precision, long long rows, long long k, long long s_r, long long s_k,
+                         const void* ptr, bool* direct, int* mn_major, long long* pitch,
+                         size_t* plane_bytes) {
+  const int es = precision == 2 ? 2 : 4;
+  const bool aligned = (reinterpret_cast<uintptr_t>(ptr) % 16 == 0);
+  if (s_k == 1 || k == 1) {
+    *mn_major = 0;
+    *direct = precision == 1 && aligned && (s_r % 4 == 0) && s_r >= k;
+    *pitch = *direct ? s_r : (long long)align_up((size_t)k, 16 / es);
+    *plane_bytes = *direct ? 0 : align_up((size_t)rows * (size_t)*pitch * es, 1024);
+  } else if (s_r == 1) {
+    *mn_major = 1;
+    *direct = precision == 1 && aligned && (s_k % 4 == 0) && s_k >= rows;
+    *pitch = *direct ? s_k : (long long)align_up((size_t)rows, 16 / es);
+    *plane_bytes = *direct ? 0 : align_up((size_t)k * (size_t)*pitch * es, 1024);
+  } else {  // doubly strided: gather into a K-major plane
+    *mn_major = 0;
+    *direct = false;
+    *pitch = (long long)align_up((size_t)k, 16 / es);
+    *plane_bytes = align_up((size_t)rows * (size_t)*pitch * es, 1024);
+  }
+}
+
+size_t gemm_pack_bytes(int precision, long long rows, long long k, long long s_r, long long s_k) {
+  bool direct;
+  int mn;
+  long long pitch;
+  size_t pb;
+  plan_operand(precision, rows, k, s_r, s_k, reinterpret_cast<const void*>(1), &direct, &mn, &pitch, &pb);
+  return (precision == 0 ? 2 : 1) * pb + 1024;
+}
+
+int gemm_pack(int precision, const float* src, long long rows, long long k, long long s_r,
+              long long s_k, void* dst, size_t dst_bytes, PackedOperand* out, cudaStream_t st) {
+  bool direct;
+  int mn;
+  long long pitch;
+  size_t pb;
+  plan_operand(precision, rows, k, s_r, s_k, src, &direct, &mn, &pitch, &pb);
+  out->rows = rows; out->k = k; out->pitch = pitch; out->mn_major = mn; out->precision = precision;
+  out->plane[0] = src; out->plane[1] = nullptr;
+  if (direct) return AB_OK;
+  const int parts = precision == 0 ? 2 : 1;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(dst), 1024));
+  if (!dst || ws + parts * pb > reinterpret_cast<uint8_t*>(dst) + dst_bytes)
+    return fail(AB_ERR_INVALID, "Gemm pack buffer too small: need %zu bytes, have %zu",
+                parts * pb + 1024, dst_bytes);
+  void* o0 = ws;
+  void* o1 = parts == 2 ? ws + pb : nullptr;
+  // plane rows/cols: K-major plane is [rows, k]; MN-major plane is [k, rows]
+  const long long R = mn ? k : rows, Cc = mn ? rows : k;
+  const long long sr = mn ? s_k : s_r, sc = mn ? s_r : s_k;
+  dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((R + 31) / 32));
+  if (grid.y > 65535) {
+    // tall planes: fold the row-tile index into x instead (both are limited to 2^31-1 / 65535)
+    return fail(AB_ERR_UNSUPPORTED, "gemm operand with more than 2M rows in the pack plane");
+  }
+  if (precision == 0) pack_kernel<0><<<grid, 256, 0, st>>>(src, R, Cc, sr, sc, o0, o1, pitch);
+  else if (precision == 1) pack_kernel<1><<<grid, 256, 0, st>>>(src, R, Cc, sr, sc, o0, o1, pitch);
+  else pack_kernel<2><<<grid, 256, 0, st>>>(src, R, Cc, sr, sc, o0, o1, pitch);
+  g_launches++;
+  AB_CUDA(cudaGetLastError());
+  out->plane[0] = o0;
+  out->plane[1] = o1;
+  return AB_OK;
+}
+
+bool gemm_tcgen05_eligible(long long M, long long N, long long K) { return eligible(M, N, K); }
+
+int gemm_run(int precision, long long M, long long N, long long K, float alpha,
+             const PackedOperand& A, const PackedOperand& B, float beta, float* C, long long c_rs,
+             long long c_cs, cudaStream_t st, const float* Cin = nullptr, long long cin_rs = 0,
+             long long cin_cs = 0) {
+  if (precision < 0 || precision > 2) return fail(AB_ERR_INVALID, "bad gemm precision %d", precision);
+  if (A.precision != precision || B.precision != precision || A.rows != M || B.rows != N ||
+      A.k != K || B.k != K)
+    return fail(AB_ERR_INVALID, "packed operands do not match the gemm call");
+  const int parts = precision == 0 ? 2 : 1;
+  const bool bf16 = precision == 2;
+  const int es = bf16 ? 2 : 4;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.alpha = alpha; p.beta = beta;
+  p.C = C; p.c_rs = c_rs; p.c_cs = c_cs;
+  p.Cin = Cin ? Cin : C; p.cin_rs = Cin ? cin_rs : c_rs; p.cin_cs = Cin ? cin_cs : c_cs;
+  p.block_n = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
+  p.nparts = parts;
+  p.k_elems_per_row = SW_BYTES / es;          // K elements per stage (64 bf16 / 32 tf32)
+  p.a_tile_bytes = BLOCK_M * SW_BYTES;
+  p.b_tile_bytes = p.block_n * SW_BYTES;
+  p.a_mn = A.mn_major; p.b_mn = B.mn_major;
+  p.mn_per_chunk = SW_BYTES / es;
+  p.chunk_bytes = p.k_elems_per_row * SW_BYTES;
+  p.a_chunks = BLOCK_M / p.mn_per_chunk;
+  p.b_chunks = p.block_n / p.mn_per_chunk;
+  const int umma_k = 32 / es;                  // K per instruction: 16 (bf16) / 8 (tf32)
+  p.a_kstep = A.mn_major ? umma_k * SW_BYTES : 32;
+  p.b_kstep = B.mn_major ? umma_k * SW_BYTES : 32;
+  const int stage_bytes = parts * (p.a_tile_bytes + p.b_tile_bytes);
+  p.stages = std::max(2, std::min(8, (kMaxSmem - 1024) / stage_bytes));
+  p.acc_stages = 2;  // 2 x block_n <= 512 TMEM columns
+  // cute UMMA::InstrDescriptor: c_format F32=1 @[4,6), a/b format @[7,10)/[10,13)
+  // (TF32=2, BF16=1), a_major @15, b_major @16 (1 = MN-major), N>>3 @[17,23), M>>4 @[24,29)
+  const uint32_t fmt = bf16 ? 1u : 2u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(A.mn_major ? 1 : 0) << 15) |
+            ((uint32_t)(B.mn_major ? 1 : 0) << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
+            ((uint32_t)(BLOCK_M >> 4) << 24);
+
+  CUtensorMap ma[2], mb[2];
+  int rc;
+  for (int i = 0; i < parts; ++i) {
+    if (A.mn_major) rc = make_map(&ma[i], A.plane[i], bf16, M, K, A.pitch, p.k_elems_per_row);
+    else rc = make_map(&ma[i], A.plane[i], bf16, K, M, A.pitch, BLOCK_M);
+    if (rc) return rc;
+    if (B.mn_major) rc = make_map(&mb[i], B.plane[i], bf16, N, K, B.pitch, p.k_elems_per_row);
+    else rc = make_map(&mb[i], B.plane[i], bf16, K, N, B.pitch, p.block_n);
+    if (rc) return rc;
+  }
+  if (parts == 1) { ma[1] = ma[0]; mb[1] = mb[0]; }
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const long long num_tiles = ((N + p.block_n - 1) / p.block_n) * ((M + BLOCK_M - 1) / BLOCK_M);
+  dim3 grid((unsigned)std::min<long long>(num_tiles, sm_count()));  // persistent: one CTA per SM
+  if (bf16) {
+    static bool attr1 = false;
+    if (!attr1) {
+      AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      attr1 = true;
+    }
+    gemm_tcgen05_kernel<1><<<grid, kThreads, smem, st>>>(ma[0], ma[1], mb[0], mb[1], p);
+  } else {
+    static bool attr0 = false;
+    if (!attr0) {
+      AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      attr0 = true;
+    }
+    gemm_tcgen05_kernel<0><<<grid, kThreads, smem, st>>>(ma[0], ma[1], mb[0], mb[1], p);
+  }
+  g_launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB_OK;
+}
 
 size_t gemm_tcgen05_workspace(int precision, long long M, long long N, long long K, long long a_rs,
                               long long a_cs, long long b_rs, long long b_cs) {
   if (!eligible(M, N, K)) return 0;
-  // pointer alignment is unknown here: assume packing is needed
-  const int parts = precision == 0 ? 2 : 1;
-  OperandPlan a = plan_operand(precision, M, K, a_rs, a_cs, reinterpret_cast<const void*>(1));
-  OperandPlan b = plan_operand(precision, N, K, b_cs, b_rs, reinterpret_cast<const void*>(1));
-  return parts * (a.plane_bytes + b.plane_bytes) + 2048;
+  return gemm_pack_bytes(precision, M, K, a_rs, a_cs) + gemm_pack_bytes(precision, N, K, b_cs, b_rs);
 }
 
 int gemm_tcgen05_f32(int precision, long long M, long long N, long long K, float alpha,
@@ -458,91 +636,55 @@ int gemm_tcgen05_f32(int precision, long long M, long long N, long long K, float
   if (precision < 0 || precision > 2) return fail(AB_ERR_INVALID, "bad gemm precision %d", precision);
   if (!eligible(M, N, K)) return AB_OK;
   *handled = true;
-  const int parts = precision == 0 ? 2 : 1;
-  const bool bf16 = precision == 2;
-  OperandPlan pa = plan_operand(precision, M, K, a_rs, a_cs, A);
-  OperandPlan pb = plan_operand(precision, N, K, b_cs, b_rs, B);
-  const size_t need = parts * (pa.plane_bytes + pb.plane_bytes) + 2048;
-  if ((pa.pack || pb.pack) && (!workspace || workspace_bytes < need))
-    return fail(AB_ERR_INVALID, "Gemm workspace too small: need %zu bytes, have %zu", need, workspace_bytes);
-  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
-  const void* a_plane[2] = {A, nullptr};
-  const void* b_plane[2] = {B, nullptr};
-  long long a_pitch = a_rs, b_pitch = b_cs;
-  auto run_pack = [&](const float* src, long long R, long long s_r, long long s_c, OperandPlan& pl,
-                      const void** planes, long long* pitch) -> int {
-    void* o0 = ws;
-    void* o1 = parts == 2 ? ws + pl.plane_bytes : nullptr;
-    ws += parts * pl.plane_bytes;
-    dim3 grid((unsigned)((K + 31) / 32), (unsigned)((R + 31) / 32));
-    if (grid.y > 65535) return fail(AB_ERR_UNSUPPORTED, "gemm operand with more than 2M rows");
-    if (precision == 0) pack_kernel<0><<<grid, 256, 0, st>>>(src, R, K, s_r, s_c, o0, o1, pl.pitch);
-    else if (precision == 1) pack_kernel<1><<<grid, 256, 0, st>>>(src, R, K, s_r, s_c, o0, o1, pl.pitch);
-    else pack_kernel<2><<<grid, 256, 0, st>>>(src, R, K, s_r, s_c, o0, o1, pl.pitch);
-    g_launches++;
-    AB_CUDA(cudaGetLastError());
-    planes[0] = o0;
-    planes[1] = o1;
-    *pitch = pl.pitch;
-    return AB_OK;
-  };
-  int rc;
-  if (pa.pack && (rc = run_pack(A, M, a_rs, a_cs, pa, a_plane, &a_pitch))) return rc;
-  if (pb.pack && (rc = run_pack(B, N, b_cs, b_rs, pb, b_plane, &b_pitch))) return rc;
-
-  GemmParams p{};
-  p.M = M; p.N = N; p.K = K;
-  p.alpha = alpha; p.beta = beta;
-  p.C = C; p.c_rs = c_rs; p.c_cs = c_cs;
-  p.block_n = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
-  p.nparts = parts;
-  p.k_elems_per_row = bf16 ? 64 : 32;
-  p.a_tile_bytes = BLOCK_M * SW_BYTES;
-  p.b_tile_bytes = p.block_n * SW_BYTES;
-  const int stage_bytes = parts * (p.a_tile_bytes + p.b_tile_bytes);
-  p.stages = std::max(2, std::min(8, (kMaxSmem - 1024) / stage_bytes));
-  p.acc_stages = 2;  // 2 x block_n <= 512 TMEM columns
-  // cute UMMA::InstrDescriptor: c_format F32=1 @[4,6), a/b format @[7,10)/[10,13)
-  // (TF32=2, BF16=1), K-major both (@15, @16 = 0), N>>3 @[17,23), M>>4 @[24,29)
-  const uint32_t fmt = bf16 ? 1u : 2u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
-            ((uint32_t)(BLOCK_M >> 4) << 24);
-
-  CUtensorMap ma0, ma1, mb0, mb1;
-  if ((rc = make_map(&ma0, a_plane[0], bf16, M, K, a_pitch, BLOCK_M))) return rc;
-  if ((rc = make_map(&mb0, b_plane[0], bf16, N, K, b_pitch, p.block_n))) return rc;
-  ma1 = ma0; mb1 = mb0;
-  if (parts == 2) {
-    if ((rc = make_map(&ma1, a_plane[1], bf16, M, K, a_pitch, BLOCK_M))) return rc;
-    if ((rc = make_map(&mb1, b_plane[1], bf16, N, K, b_pitch, p.block_n))) return rc;
-  }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  const long long num_tiles = ((N + p.block_n - 1) / p.block_n) * ((M + BLOCK_M - 1) / BLOCK_M);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
-  dim3 grid((unsigned)std::min<long long>(num_tiles, sms));  // persistent: one CTA per SM
-  if (bf16) {
-    static bool attr1 = false;
-    if (!attr1) {
-      AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      attr1 = true;
-    }
-    gemm_tcgen05_kernel<1><<<grid, kThreads, smem, st>>>(ma0, ma1, mb0, mb1, p);
-  } else {
-    static bool attr0 = false;
-    if (!attr0) {
-      AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      attr0 = true;
-    }
-    gemm_tcgen05_kernel<0><<<grid, kThreads, smem, st>>>(ma0, ma1, mb0, mb1, p);
-  }
-  g_launches++;
-  AB_CUDA(cudaGetLastError());
-  return AB_OK;
+  PackedOperand pa{}, pb{};
+  const size_t a_bytes = gemm_pack_bytes(precision, M, K, a_rs, a_cs);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int rc = gemm_pack(precision, A, M, K, a_rs, a_cs, ws, std::min(a_bytes, workspace_bytes), &pa, st);
+  if (rc) return rc;
+  const size_t rest = workspace_bytes > a_bytes ? workspace_bytes - a_bytes : 0;
+  rc = gemm_pack(precision, B, N, K, b_cs, b_rs, ws ? ws + a_bytes : nullptr, rest, &pb, st);
+  if (rc) return rc;
+  return gemm_run(precision, M, N, K, alpha, pa, pb, beta, C, c_rs, c_cs, st);
 }
 
 }  // namespace ab
+
+// ---- C ABI for callers that keep packed operands across several products -------------
+extern "C" int ab_gemm_pack_bytes(int precision, int64_t rows, int64_t k, int64_t s_r, int64_t s_k,
+                                  size_t* bytes) {
+  if (!bytes) return ab::fail(AB_ERR_INVALID, "null out pointer");
+  *bytes = ab::gemm_pack_bytes(precision, rows, k, s_r, s_k);
+  return AB_OK;
+}
+
+extern "C" int ab_gemm_pack(int precision, const void* src, int64_t rows, int64_t k, int64_t s_r,
+                            int64_t s_k, void* dst, size_t dst_bytes, ab_gemm_operand* out,
+                            void* stream) {
+  if (!out) return ab::fail(AB_ERR_INVALID, "null ab_gemm_operand");
+  ab::PackedOperand po{};
+  int rc = ab::gemm_pack(precision, static_cast<const float*>(src), rows, k, s_r, s_k, dst,
+                         dst_bytes, &po, ab::as_stream(stream));
+  if (rc) return rc;
+  out->plane0 = po.plane[0]; out->plane1 = po.plane[1];
+  out->rows = po.rows; out->k = po.k; out->pitch = po.pitch;
+  out->mn_major = po.mn_major; out->precision = po.precision;
+  return AB_OK;
+}
+
+extern "C" int ab_gemm_packed(int precision, int64_t m, int64_t n, int64_t k, double alpha,
+                              const ab_gemm_operand* A, const ab_gemm_operand* B, double beta,
+                              const void* Cin, int64_t cin_rs, int64_t cin_cs, void* C,
+                              int64_t c_rs, int64_t c_cs, void* stream) {
+  if (!A || !B) return ab::fail(AB_ERR_INVALID, "null packed operand");
+  if (!ab::gemm_tcgen05_eligible(m, n, k))
+    return ab::fail(AB_ERR_UNSUPPORTED, "problem too small for the tensor-core path; use ab_gemm");
+  ab::PackedOperand pa{{A->plane0, A->plane1}, A->rows, A->k, A->pitch, A->mn_major, A->precision};
+  ab::PackedOperand pb{{B->plane0, B->plane1}, B->rows, B->k, B->pitch, B->mn_major, B->precision};
+  return ab::gemm_run(precision, m, n, k, (float)alpha, pa, pb, (float)beta, static_cast<float*>(C),
+                      c_rs, c_cs, ab::as_stream(stream), static_cast<const float*>(Cin), cin_rs,
+                      cin_cs);
+}
+
+extern "C" int ab_gemm_tensorcore_eligible(int64_t m, int64_t n, int64_t k) {
+  return ab::gemm_tcgen05_eligible(m, n, k) ? 1 : 0;
+}

@@ -246,12 +246,75 @@ def ger(A: DeviceArray, alpha, x: DeviceArray, y: DeviceArray):
                           y.strides[0], A.ptr, A.strides[0], A.strides[1], stream_handle()))
 
 
-def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision=0):
-    """In place: C <- beta*C + alpha*A@B."""
+class PackCache:
+    """Tensor-core operand planes (bf16 / TF32 hi+lo) packed during one program
+    evaluation.  Keyed by the source buffer's memory layout, so a matrix and its
+    DimShuffle{1,0} view (X and X^T, h and h^T in an MLP backward pass) share one
+    pack: the transposed use reads the same planes as an MN-major operand."""
+
+    def __init__(self):
+        self._e = {}
+
+    def clear(self):
+        self._e.clear()
+
+    def invalidate(self, owner):
+        """Drop the packs of a buffer that a destructive (in-place) node just rewrote."""
+        if self._e:
+            dead = [k for k, e in self._e.items() if e[0]() is owner]
+            for k in dead:
+                del self._e[k]
+
+    def operand(self, arr: DeviceArray, rows, k, s_r, s_k, precision):
+        import weakref
+
+        lib = _lib.load()
+        if s_k == 1 or k == 1:
+            canon = (arr.ptr, rows, k, s_r, 0)
+        elif s_r == 1:
+            canon = (arr.ptr, k, rows, s_k, 0)
+        else:
+            canon = (arr.ptr, rows, k, s_r, s_k)
+        key = canon + (precision,)
+        ent = self._e.get(key)
+        if ent is not None and ent[0]() is arr.owner:
+            _, p0, p1, pitch, _buf = ent
+        else:
+            nbytes = C.c_size_t()
+            _lib.check(lib.ab_gemm_pack_bytes(precision, rows, k, s_r, s_k, C.byref(nbytes)))
+            buf = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=arr.owner.device)
+            op = _lib.GemmOperand()
+            _lib.check(lib.ab_gemm_pack(precision, arr.ptr, rows, k, s_r, s_k, buf.data_ptr(),
+                                        nbytes.value, C.byref(op), stream_handle()))
+            p0, p1, pitch = op.plane0, op.plane1, op.pitch
+            try:
+                ref = weakref.ref(arr.owner)
+            except TypeError:
+                ref = (lambda o: (lambda: o))(arr.owner)
+            self._e[key] = (ref, p0, p1, pitch, buf)
+        mn = 0 if (s_k == 1 or k == 1) else (1 if s_r == 1 else 0)
+        return _lib.GemmOperand(p0, p1, rows, k, pitch, mn, precision)
+
+
+def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision=0, cache=None,
+         cin: DeviceArray = None):
+    """C <- beta*Cin + alpha*A@B (Cin = C, i.e. in place, unless ``cin`` is given)."""
     lib = _lib.load()
     m, k = A.shape
     k2, n = B.shape
     code = _blas_code(C_.dtype)
+    if C_.dtype == np.float32 and lib.ab_gemm_tensorcore_eligible(m, n, k):
+        cache = cache if cache is not None else PackCache()
+        opa = cache.operand(A, m, k, A.strides[0], A.strides[1], precision)
+        opb = cache.operand(B, n, k, B.strides[1], B.strides[0], precision)
+        cin_args = (None, 0, 0) if cin is None else (cin.ptr, cin.strides[0], cin.strides[1])
+        _lib.check(lib.ab_gemm_packed(precision, m, n, k, float(alpha), C.byref(opa), C.byref(opb),
+                                      float(beta), *cin_args, C_.ptr, C_.strides[0], C_.strides[1],
+                                      stream_handle()))
+        return
+    if cin is not None:
+        if float(beta) != 0.0:
+            copy_into(C_, cin)
     ws_bytes = C.c_size_t()
     _lib.check(lib.ab_gemm_workspace_bytes(code, precision, m, n, k, A.strides[0], A.strides[1],
                                            B.strides[0], B.strides[1], C.byref(ws_bytes)))

@@ -101,8 +101,34 @@ SIGNATURES = {
         [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
          C.c_int64, C.POINTER(C.c_size_t)],
     ),
+    "ab_gemm_pack_bytes": (
+        C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]
+    ),
+    "ab_gemm_pack": (
+        C.c_int,
+        [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t,
+         C.c_void_p, C.c_void_p],
+    ),
+    "ab_gemm_packed": (
+        C.c_int,
+        [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_double,
+         C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p],
+    ),
+    "ab_gemm_tensorcore_eligible": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "ab_launch_count": (C.c_uint64, []),
 }
+
+
+class GemmOperand(C.Structure):
+    _fields_ = [
+        ("plane0", C.c_void_p),
+        ("plane1", C.c_void_p),
+        ("rows", C.c_int64),
+        ("k", C.c_int64),
+        ("pitch", C.c_int64),
+        ("mn_major", C.c_int32),
+        ("precision", C.c_int32),
+    ]
 
 
 def load():

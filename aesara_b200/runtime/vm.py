@@ -84,6 +84,19 @@ class ProgramExecutor:
             if v not in keep and v not in self._const_host:
                 self._free_after[i].append(v)
         self.node_events = None
+        self.pack_cache = K.PackCache()
+        # input positions each node rewrites in place (destroy_map): their cached GEMM
+        # packs must be dropped after the node ran
+        self._destroys = []
+        for n in program.nodes:
+            d = []
+            if n.op == "Elemwise":
+                d = sorted(set(int(v) for v in n.params.get("inplace", {}).values()))
+            elif n.op in ("Gemm", "Gemv", "Ger", "IncSubtensor") and n.params.get("inplace"):
+                d = [0]
+            elif n.op == "Scan":
+                d = sorted({int(i) for v in n.params.get("destroy_map", {}).values() for i in v})
+            self._destroys.append(d)
         self.prepare()
 
     # ------------------------------------------------------------------
@@ -145,6 +158,7 @@ class ProgramExecutor:
         if len(inputs) != len(prog.inputs):
             raise TypeError(f"expected {len(prog.inputs)} inputs, got {len(inputs)}")
         env = dict(self._const_host)
+        self.pack_cache.clear()
         for vid, val in zip(prog.inputs, inputs):
             var = prog.vars[vid]
             if isinstance(val, DeviceArray):
@@ -192,9 +206,14 @@ class ProgramExecutor:
             else:
                 for vid, o in zip(node.outputs, outs):
                     env[vid] = o
+            for pos in self._destroys[i]:
+                d = env.get(node.inputs[pos])
+                if isinstance(d, DeviceArray):
+                    self.pack_cache.invalidate(d.owner)
             for v in self._free_after[i]:
                 env.pop(v, None)
         self.node_events = events
+        self.pack_cache.clear()
         outs = [env[v] for v in prog.outputs]
         if self.host_outputs:
             outs = [o.to_numpy() if isinstance(o, DeviceArray) else np.asarray(o) for o in outs]
@@ -323,7 +342,7 @@ def _dot22(ex, i, node, args):
         raise ValueError(f"Shape mismatch: x has {x.shape[1]} cols (and {x.shape[0]} rows) but y has "
                          f"{y.shape[0]} rows (and {y.shape[1]} cols)")
     z = DeviceArray.empty((x.shape[0], y.shape[1]), x.dtype)
-    K.gemm(z, 1.0, x, y, 0.0, ex.precision)
+    K.gemm(z, 1.0, x, y, 0.0, ex.precision, cache=ex.pack_cache)
     return z
 
 
@@ -334,7 +353,7 @@ def _dot22scalar(ex, i, node, args):
     if x.shape[1] != y.shape[0]:
         raise ValueError("Shape mismatch in Dot22Scalar")
     z = DeviceArray.empty((x.shape[0], y.shape[1]), x.dtype)
-    K.gemm(z, a, x, y, 0.0, ex.precision)
+    K.gemm(z, a, x, y, 0.0, ex.precision, cache=ex.pack_cache)
     return z
 
 
@@ -355,11 +374,12 @@ def _gemm(ex, i, node, args):
         else:
             raise ValueError(f"Shape mismatch: z has shape {z.shape} but x.y has shape {(m, n)}")
     elif not node.params["inplace"] or is_host(args[0]):
-        zz = DeviceArray.empty((m, n), z.dtype)
-        if b != 0.0:
-            K.copy_into(zz, z)
-        z = zz
-    K.gemm(z, a, x, y, b, ex.precision)
+        # Gemm{no_inplace}: out = b*z + a*x.y without first copying z (blas.py:1065-1093
+        # copies z into the output and calls BLAS with beta): the epilogue reads z directly
+        out = DeviceArray.empty((m, n), z.dtype)
+        K.gemm(out, a, x, y, b, ex.precision, cache=ex.pack_cache, cin=z)
+        return out
+    K.gemm(z, a, x, y, b, ex.precision, cache=ex.pack_cache)
     return z
 
 
@@ -414,7 +434,7 @@ def _dot(ex, i, node, args):
         return out
     if x.ndim == 2 and y.ndim == 2:
         z = DeviceArray.empty((x.shape[0], y.shape[1]), x.dtype)
-        K.gemm(z, 1.0, x, y, 0.0, ex.precision)
+        K.gemm(z, 1.0, x, y, 0.0, ex.precision, cache=ex.pack_cache)
         return z
     raise NotImplementedError("Dot with ndim > 2")
 

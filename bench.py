@@ -381,7 +381,7 @@ def main():
     for i, lst in node_ms.items():
         op = prog.nodes[i].op
         t = float(np.mean(lst))
-        if op in ("Dot22", "Gemm", "Dot22Scalar"):
+        if op in ("Dot22", "Gemm", "Dot22Scalar", "Scan"):
             gemm_ms += t
         elif op in ("Elemwise", "CAReduce"):
             hbm_ms += t

@@ -143,6 +143,32 @@ int ab_gemm_workspace_bytes(int dtype, int precision, int64_t m, int64_t n, int6
                             int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs,
                             size_t* bytes);
 
+/* Packed tensor-core operands.  ab_gemm converts its operands on every call
+ * (hi/lo TF32 split, bf16, or a K-/MN-major copy).  A caller that multiplies the
+ * same matrix several times (X and X^T, h and h^T in an MLP backward pass) packs
+ * it once: logical operand [rows, k] (rows = M for A, N for B; element strides
+ * s_r, s_k) -> ab_gemm_operand, then ab_gemm_packed.  A transposed view of the
+ * same memory yields the same planes with mn_major flipped, so one pack serves
+ * both products (the operand is handed to tcgen05.mma as MN-major). */
+typedef struct {
+  const void* plane0;   /* hi / only plane */
+  const void* plane1;   /* lo plane of the 3xTF32 split, else NULL */
+  int64_t rows, k, pitch;
+  int32_t mn_major;     /* 0: planes are [rows,pitch] K-contiguous; 1: [k,pitch] rows-contiguous */
+  int32_t precision;
+} ab_gemm_operand;
+int ab_gemm_pack_bytes(int precision, int64_t rows, int64_t k, int64_t s_r, int64_t s_k,
+                       size_t* bytes);
+int ab_gemm_pack(int precision, const void* src, int64_t rows, int64_t k, int64_t s_r,
+                 int64_t s_k, void* dst, size_t dst_bytes, ab_gemm_operand* out, void* stream);
+/* C <- beta*Cin + alpha*A@B.  Cin == NULL means in place (Cin = C); a separate Cin is
+ * the Gemm{no_inplace} case (blas.py:1065-1093) without the copy of z. */
+int ab_gemm_packed(int precision, int64_t m, int64_t n, int64_t k, double alpha,
+                   const ab_gemm_operand* A, const ab_gemm_operand* B, double beta,
+                   const void* Cin, int64_t cin_rs, int64_t cin_cs, void* C, int64_t c_rs,
+                   int64_t c_cs, void* stream);
+int ab_gemm_tensorcore_eligible(int64_t m, int64_t n, int64_t k);
+
 /* number of kernels this library has launched since load (bench.py reports it) */
 uint64_t ab_launch_count(void);
 
