@@ -364,6 +364,264 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
   }
 }
 
+// ------------------------------------------------------------------ 2-CTA variant
+// cta_group::2: a cluster of two CTAs (same TPC) computes one 256 x 256 tile.  Each
+// CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), the
+// leader CTA issues tcgen05.mma.cta_group::2 (M = 256) that reads both CTAs' shared
+// memory, and each CTA's TMEM receives its 128 accumulator rows.  Per CTA and k-block
+// that is 32 KB from L2 instead of 48 KB: the 1-CTA kernel is L2->SM bandwidth bound
+// (profiles/r01_gemm_bf16_v2_persistent.txt: lts2xbar 13.7 TB/s, tensor pipe 72 %).
+//   * full barriers live in the leader; both CTAs' TMA loads complete_tx on them
+//     (cp.async.bulk.tensor...cta_group::2 with the peer bit of the barrier address
+//     cleared), the leader arms expect_tx for the bytes of both;
+//   * tcgen05.commit.cta_group::2 ... multicast::cluster arrives on the empty /
+//     tmem_full barriers of both CTAs;
+//   * all 256 epilogue threads arrive on the leader's tmem_empty barrier.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the even CTA of a pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map,
+                                                uint64_t* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void load_tile_2sm(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
+                                              int kc, int mn0, int mn_major, int chunks,
+                                              const GemmParams& p) {
+  if (!mn_major) {
+    tma_load_2d_2sm(dst, map, bar, kc, mn0);
+  } else {
+    for (int c = 0; c < chunks; ++c)
+      tma_load_2d_2sm(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
+  }
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// GemmParams here: block_n = 256 (the pair's N tile), b_tile_bytes = 128 rows * 128 B
+// (this CTA's half), b_chunks = chunks of the half, idesc encodes M = 256, N = 256.
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
+                         const __grid_constant__ CUtensorMap map_a1,
+                         const __grid_constant__ CUtensorMap map_b0,
+                         const __grid_constant__ CUtensorMap map_b1,
+                         const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int stage_bytes = p.nparts * (p.a_tile_bytes + p.b_tile_bytes);
+  const int num_k_blocks = (int)((p.K + p.k_elems_per_row - 1) / p.k_elems_per_row);
+  constexpr int TILE_M = 2 * BLOCK_M;
+  const long long tiles_n = (p.N + p.block_n - 1) / p.block_n;
+  const long long num_tiles = ((p.M + TILE_M - 1) / TILE_M) * tiles_n;
+  const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const uint32_t tmem_cols = (uint32_t)(p.acc_stages * p.block_n);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 256);  // the epilogue threads of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote signal
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (one per CTA) =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        const int m0 = (int)((tile / tiles_n) * TILE_M) + (int)rank * BLOCK_M;
+        const int n0 = (int)((tile % tiles_n) * p.block_n) + (int)rank * (p.block_n / 2);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sbase = smem + (size_t)stage * stage_bytes;
+          if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
+          const int kc = kb * p.k_elems_per_row;
+          load_tile_2sm(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
+          load_tile_2sm(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0,
+                        p.b_mn, p.b_chunks, p);
+          if (p.nparts == 2) {
+            load_tile_2sm(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn,
+                          p.a_chunks, p);
+            load_tile_2sm(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc,
+                          n0, p.b_mn, p.b_chunks, p);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+        const uint32_t as = it % (uint32_t)p.acc_stages;
+        const uint32_t aphase = (it / (uint32_t)p.acc_stages) & 1u;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t a_hi = sbase;
+          const uint32_t a_lo = sbase + p.a_tile_bytes;
+          const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
+          const uint32_t b_lo = b_hi + p.b_tile_bytes;
+          const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
+          const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
+#pragma unroll
+          for (int k = 0; k < SW_BYTES / 32; ++k) {
+            const uint32_t ka = k * (uint32_t)p.a_kstep, kbo = k * (uint32_t)p.b_kstep;
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            if (p.nparts == 2) {
+              umma_2sm<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
+              umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kbo, b_lbo), p.idesc, 1u);
+              umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, 1u);
+            } else {
+              umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
+            }
+          }
+          tcgen05_commit_2sm(&empty_bar[stage]);  // frees the stage in both CTAs
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit_2sm(&tmem_full_bar[as]);  // both CTAs' epilogues may read
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5 of both CTAs) =================
+    const int q = warp & 3;
+    const bool vec_ok = (p.c_cs == 1) && ((p.c_rs & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
+                                            ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
+    uint32_t it = 0;
+    for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+      const uint32_t as = it % (uint32_t)p.acc_stages;
+      const uint32_t aphase = (it / (uint32_t)p.acc_stages) & 1u;
+      const long long m0 = (tile / tiles_n) * TILE_M + (long long)rank * BLOCK_M;
+      const long long n0 = (tile % tiles_n) * p.block_n;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tcgen05_fence_after();
+      const long long row = m0 + q * 32 + lane;
+      const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_acc + (uint32_t)c0, r);
+        if (c0 + 32 >= p.block_n) {
+          tcgen05_fence_before();
+          asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(
+                           smem_u32(&tmem_empty_bar[as]) & kPeerBitMask)
+                       : "memory");
+        }
+        if (row < p.M) {
+          const long long col0 = n0 + c0;
+          float* crow = p.C + row * p.c_rs;
+          const float* irow = p.Cin + row * p.cin_rs;
+          if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v;
+              v.x = p.alpha * __uint_as_float(r[j]);
+              v.y = p.alpha * __uint_as_float(r[j + 1]);
+              v.z = p.alpha * __uint_as_float(r[j + 2]);
+              v.w = p.alpha * __uint_as_float(r[j + 3]);
+              if (p.beta != 0.0f) {
+                const float4 o = *reinterpret_cast<const float4*>(irow + col0 + j);
+                v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
+              }
+              *reinterpret_cast<float4*>(crow + col0 + j) = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long col = col0 + j;
+              if (col < p.N) {
+                float v = p.alpha * __uint_as_float(r[j]);
+                if (p.beta != 0.0f) v += p.beta * irow[col * p.cin_cs];
+                crow[col * p.c_cs] = v;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody signals the peer's barriers / reads its smem after this
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(tmem_cols)
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ operand packing
 // out planes are [R, pitch] row-major (K-major): out[r*pitch + c] = f(in[r*s_r + c*s_c]).
 // MODE 0: hi/lo tf32 split (two f32 planes), 1: f32 copy, 2: bf16.
@@ -490,7 +748,10 @@ static void plan_operand(int precision, long long rows, long long k, long long s
     *direct = precision == 1 && aligned && (s_r % 4 == 0) && s_r >= k;
     *pitch = *direct ? s_r : (long long)align_up((size_t)k, 16 / es);
     *plane_bytes = *direct ? 0 : align_up((size_t)rows * (size_t)*pitch * es, 1024);
-  } else if (s_r == 1) {
+  } else if (s_r == 1 && precision == 2 && getenv("AB_GEMM_NO_MN") == nullptr) {
+    // MN-major is used for 16-bit operands only: a 32-bit (TF32) MN-major operand needs the
+    // SWIZZLE_128B_BASE32B shared-memory layout (and the matching 32B-atom TMA swizzle);
+    // TF32 operands that are not K-contiguous are gathered into a K-major plane below.
     *mn_major = 1;
     *direct = precision == 1 && aligned && (s_k % 4 == 0) && s_k >= rows;
     *pitch = *direct ? s_k : (long long)align_up((size_t)rows, 16 / es);
@@ -578,6 +839,15 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   const int umma_k = 32 / es;                  // K per instruction: 16 (bf16) / 8 (tf32)
   p.a_kstep = A.mn_major ? umma_k * SW_BYTES : 32;
   p.b_kstep = B.mn_major ? umma_k * SW_BYTES : 32;
+  // 2-CTA mode (cta_group::2, 256 x 256 tile per CTA pair) for large problems
+  static const bool allow_2cta = getenv("AB_GEMM_1CTA") == nullptr;
+  const bool two_cta = allow_2cta && M >= 256 && N >= 256 && (sm_count() % 2 == 0);
+  if (two_cta) {
+    p.block_n = 256;
+    p.b_tile_bytes = (p.block_n / 2) * SW_BYTES;  // this CTA's half of the B tile
+    p.b_chunks = (p.block_n / 2) / p.mn_per_chunk;
+  }
+  const int tile_m = two_cta ? 2 * BLOCK_M : BLOCK_M;
   const int stage_bytes = parts * (p.a_tile_bytes + p.b_tile_bytes);
   p.stages = std::max(2, std::min(8, (kMaxSmem - 1024) / stage_bytes));
   p.acc_stages = 2;  // 2 x block_n <= 512 TMEM columns
@@ -586,7 +856,7 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   const uint32_t fmt = bf16 ? 1u : 2u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(A.mn_major ? 1 : 0) << 15) |
             ((uint32_t)(B.mn_major ? 1 : 0) << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
-            ((uint32_t)(BLOCK_M >> 4) << 24);
+            ((uint32_t)(tile_m >> 4) << 24);
 
   CUtensorMap ma[2], mb[2];
   int rc;
@@ -595,11 +865,44 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     else rc = make_map(&ma[i], A.plane[i], bf16, K, M, A.pitch, BLOCK_M);
     if (rc) return rc;
     if (B.mn_major) rc = make_map(&mb[i], B.plane[i], bf16, N, K, B.pitch, p.k_elems_per_row);
-    else rc = make_map(&mb[i], B.plane[i], bf16, K, N, B.pitch, p.block_n);
+    else rc = make_map(&mb[i], B.plane[i], bf16, K, N, B.pitch, two_cta ? p.block_n / 2 : p.block_n);
     if (rc) return rc;
   }
   if (parts == 1) { ma[1] = ma[0]; mb[1] = mb[0]; }
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  if (two_cta) {
+    const long long tiles2 = ((N + p.block_n - 1) / p.block_n) * ((M + tile_m - 1) / tile_m);
+    const long long clusters = std::min<long long>(tiles2, sm_count() / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (bf16) {
+      static bool a1 = false;
+      if (!a1) {
+        AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        a1 = true;
+      }
+      AB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<1>, ma[0], ma[1], mb[0], mb[1], p));
+    } else {
+      static bool a0 = false;
+      if (!a0) {
+        AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        a0 = true;
+      }
+      AB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<0>, ma[0], ma[1], mb[0], mb[1], p));
+    }
+    g_launches++;
+    return AB_OK;
+  }
   const long long num_tiles = ((N + p.block_n - 1) / p.block_n) * ((M + BLOCK_M - 1) / BLOCK_M);
   dim3 grid((unsigned)std::min<long long>(num_tiles, sm_count()));  // persistent: one CTA per SM
   if (bf16) {

@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -269,9 +270,12 @@ class PackCache:
         import weakref
 
         lib = _lib.load()
+        # bf16 planes serve both orientations of a matrix (K-major / MN-major operand);
+        # TF32 planes are always K-major, so a transposed use is a different pack
+        share = precision == 2 and not os.environ.get("AB_GEMM_NO_MN")
         if s_k == 1 or k == 1:
             canon = (arr.ptr, rows, k, s_r, 0)
-        elif s_r == 1:
+        elif s_r == 1 and share:
             canon = (arr.ptr, k, rows, s_k, 0)
         else:
             canon = (arr.ptr, rows, k, s_r, s_k)
@@ -292,7 +296,7 @@ class PackCache:
             except TypeError:
                 ref = (lambda o: (lambda: o))(arr.owner)
             self._e[key] = (ref, p0, p1, pitch, buf)
-        mn = 0 if (s_k == 1 or k == 1) else (1 if s_r == 1 else 0)
+        mn = 0 if (s_k == 1 or k == 1) else (1 if (s_r == 1 and share) else 0)
         return _lib.GemmOperand(p0, p1, rows, k, pitch, mn, precision)
 
 
