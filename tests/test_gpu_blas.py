@@ -89,11 +89,14 @@ def test_pack_cache_shares_one_pack_between_a_matrix_and_its_transpose(K, precis
     K.gemm(out1, 1.0, X, W, 0.0, precision, cache=cache)
     n_after_first = len(cache._e)
     K.gemm(out2, 1.0, X.dimshuffle([1, 0]), D, 0.0, precision, cache=cache)
-    assert len(cache._e) == n_after_first + 1  # only D was packed; X's planes were reused
+    # bf16: only D was packed, X's planes were reused as an MN-major operand;
+    # TF32 planes are K-major only, so X^T is a second (transposing) pack
+    x_packs = 1 if precision == 2 else 2
+    assert len(cache._e) == n_after_first + x_packs
     assert _normwise(out1.to_numpy(), x.astype(np.float64) @ w) < tol
     assert _normwise(out2.to_numpy(), x.T.astype(np.float64) @ d) < tol
     cache.invalidate(X.owner)
-    assert len(cache._e) == n_after_first  # W and D stay, X is gone
+    assert len(cache._e) == n_after_first  # W and D stay, every pack of X is gone
 
 
 def test_gemm_beta_zero_ignores_uninitialised_c(K):
