@@ -215,6 +215,12 @@ def cpu_baseline(spec, seconds_budget=20.0):
     from aesara_b200.ir import Program
     from oracle.program_np import run_program
 
+    try:  # torchrun pins OMP_NUM_THREADS=1: give the BLAS under NumPy every host core back
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     prog = Program.load(os.path.join(GOLDEN, spec["program"] + ".json"))
     rng = np.random.default_rng(0)
     if spec["name"] == "mlp":

@@ -103,3 +103,33 @@ def test_full_size_properties(rt):
     ref = (torch.nn.functional.softplus(torch.tanh(x.double()) + y.double()) * z.double())
     err = ((t1[:n].double() - ref).abs() / (ref.abs() + 1e-6)).max().item()
     assert err < 1e-5
+
+
+def test_output_combiner_device_path_single_rank(rt):
+    """shard.OutputCombiner on the device (NCCL, world_size 1): pack -> all_gather ->
+    weighted sum by the backend's own Elemwise/CAReduce kernels == identity."""
+    import os
+    import socket
+
+    import torch.distributed as dist
+
+    from aesara_b200.runtime.device import DeviceArray
+    from aesara_b200.shard import OutputCombiner
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        rng = np.random.default_rng(0)
+        outs = [rng.standard_normal(()).astype("float32"), rng.standard_normal((7, 5)).astype("float32"),
+                rng.standard_normal(33).astype("float32")]
+        comb = OutputCombiner(1, mode="mean")
+        got = comb([DeviceArray.from_numpy(o) for o in outs])
+        for g, w in zip(got, outs):
+            np.testing.assert_allclose(g.to_numpy(), w, rtol=1e-6)
+    finally:
+        dist.destroy_process_group()
