@@ -74,6 +74,8 @@ def _numpy2_aliases():
                 return fn
 
         np.cast = _Cast()
+    if not hasattr(np, "MAXDIMS"):  # aesara/tensor/special.py (Softmax axis=None), = NPY_MAXDIMS
+        np.MAXDIMS = 64
     for name, val in (
         ("bool8", np.bool_),
         ("float_", np.float64),

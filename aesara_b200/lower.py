@@ -277,6 +277,42 @@ def _l_careduce(op, apply):
     }
 
 
+# -- row ops -------------------------------------------------------
+def _axis_or_none(op):
+    return None if op.axis is None else int(op.axis)
+
+
+@lowers("Softmax")
+def _l_softmax(op, apply):
+    return "Softmax", {"axis": _axis_or_none(op), "mode": 0}
+
+
+@lowers("LogSoftmax")
+def _l_logsoftmax(op, apply):
+    return "Softmax", {"axis": _axis_or_none(op), "mode": 1}
+
+
+@lowers("SoftmaxGrad")
+def _l_softmaxgrad(op, apply):
+    return "Softmax", {"axis": _axis_or_none(op), "mode": 2}
+
+
+@lowers("MaxAndArgmax")
+def _l_maxandargmax(op, apply):
+    ndim = apply.inputs[0].type.ndim
+    axis = op.axis
+    axes = list(range(ndim)) if axis is None else sorted(int(a) % ndim for a in axis)
+    return "MaxAndArgmax", {"axes": axes}
+
+
+@lowers("Argmax")
+def _l_argmax(op, apply):
+    ndim = apply.inputs[0].type.ndim
+    axis = op.axis
+    axes = list(range(ndim)) if axis is None else sorted(int(a) % ndim for a in axis)
+    return "MaxAndArgmax", {"axes": axes, "argmax_only": True}
+
+
 # -- BLAS family -----------------------------------------------------------------
 @lowers("Dot22")
 def _l_dot22(op, apply):

@@ -115,6 +115,15 @@ SIGNATURES = {
          C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p],
     ),
     "ab_gemm_tensorcore_eligible": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    "ab_softmax": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p],
+    ),
+    "ab_max_and_argmax": (
+        C.c_int,
+        [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
     "ab_launch_count": (C.c_uint64, []),
 }
 

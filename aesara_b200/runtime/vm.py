@@ -324,6 +324,66 @@ def _careduce(ex, i, node, args):
     return ex._state[i]["kernel"].launch(x, axis)
 
 
+# -- row ops -------------------------------------------------------------------------
+def _as_c_contiguous(x):
+    return x if x.is_c_contiguous() else K.contiguous_copy(x)
+
+
+@_op("Softmax")
+def _softmax(ex, i, node, args):
+    import ctypes as C
+
+    from ..ir import DTYPE_CODE
+    from . import lib as _lib
+    from .device import stream_handle
+
+    p = node.params
+    ins = [_as_c_contiguous(a) for a in _as_dev_inputs(ex, i, node, args)]
+    x = ins[-1] if p["mode"] == 2 else ins[0]  # SoftmaxGrad(dy, sm): shapes agree
+    if p["mode"] == 2 and ins[0].shape != ins[1].shape:
+        raise ValueError(f"SoftmaxGrad: shapes {ins[0].shape} and {ins[1].shape} differ")
+    if x.dtype.name not in ("float32", "float64"):
+        raise TypeError(f"Softmax on dtype {x.dtype.name}")
+    axis = p["axis"]
+    if axis is None:
+        outer, r, inner = 1, x.size, 1
+    else:
+        axis = axis % x.ndim
+        outer = int(np.prod(x.shape[:axis])) if axis else 1
+        r = x.shape[axis]
+        inner = int(np.prod(x.shape[axis + 1:])) if axis + 1 < x.ndim else 1
+    out = DeviceArray.empty(x.shape, x.dtype)
+    a0 = ins[0].ptr
+    a1 = ins[1].ptr if p["mode"] == 2 else None
+    _lib.check(_lib.load().ab_softmax(DTYPE_CODE[x.dtype.name], p["mode"], outer, r, inner, a0, a1,
+                                      out.ptr, stream_handle()))
+    return out
+
+
+@_op("MaxAndArgmax")
+def _maxandargmax(ex, i, node, args):
+    from ..ir import DTYPE_CODE
+    from . import lib as _lib
+    from .device import stream_handle
+
+    (x,) = _as_dev_inputs(ex, i, node, args)
+    axes = node.params["axes"]
+    keep = [d for d in range(x.ndim) if d not in axes]
+    # kept axes in front, reduced axes flattened at the back (math.py:175-184)
+    xt = x.dimshuffle(keep + list(axes)) if keep + list(axes) != list(range(x.ndim)) else x
+    xt = _as_c_contiguous(xt)
+    kept_shape = tuple(x.shape[d] for d in keep)
+    outer = int(np.prod(kept_shape)) if kept_shape else 1
+    r = int(np.prod([x.shape[d] for d in axes])) if axes else 1
+    only_arg = node.params.get("argmax_only", False)
+    omax = None if only_arg else DeviceArray.empty(kept_shape, x.dtype)
+    oidx = DeviceArray.empty(kept_shape, "int64")
+    _lib.check(_lib.load().ab_max_and_argmax(DTYPE_CODE[x.dtype.name], outer, r, xt.ptr,
+                                             None if omax is None else omax.ptr, oidx.ptr,
+                                             stream_handle()))
+    return oidx if only_arg else [omax, oidx]
+
+
 # -- BLAS family -------------------------------------------------------------------
 def _scalar_value(v):
     if isinstance(v, DeviceArray):

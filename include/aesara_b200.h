@@ -169,6 +169,18 @@ int ab_gemm_packed(int precision, int64_t m, int64_t n, int64_t k, double alpha,
                    int64_t c_cs, void* stream);
 int ab_gemm_tensorcore_eligible(int64_t m, int64_t n, int64_t k);
 
+/* ---- row ops ---------------------------------------------------
+ * The operand is a C-contiguous [outer, r, inner] view; the op runs along r.
+ * ab_softmax mode 0: Softmax (aesara/tensor/special.py:239), 1: LogSoftmax (:508),
+ * 2: SoftmaxGrad (:13; in = dy, in2 = sm).  float32 / float64.
+ * ab_max_and_argmax (aesara/tensor/math.py:126): per row of [outer, r] the maximum
+ * (out_max, may be NULL) and the int64 index of its first occurrence (out_argmax, may
+ * be NULL); NaN wins, like np.max / np.argmax. */
+int ab_softmax(int dtype, int mode, int64_t outer, int64_t r, int64_t inner, const void* in,
+               const void* in2, void* out, void* stream);
+int ab_max_and_argmax(int dtype, int64_t outer, int64_t r, const void* in, void* out_max,
+                      void* out_argmax, void* stream);
+
 /* number of kernels this library has launched since load (bench.py reports it) */
 uint64_t ab_launch_count(void);
 

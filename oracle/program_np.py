@@ -145,6 +145,40 @@ def _careduce(node, args, prog):
     return np.asarray(out).astype(p["out_dtype"])
 
 
+# -- row ops ---------------------------------------------------------------------------
+@_h("Softmax")
+def _softmax(node, args, prog):
+    p = node.params
+    axis = p["axis"]
+    if p["mode"] == 2:  # aesara/tensor/special.py:38-43 SoftmaxGrad.perform
+        dy, sm = args
+        t = dy * sm
+        return t - np.sum(t, axis=axis, keepdims=True) * sm
+    (x,) = args
+    x = np.asarray(x)
+    xdev = x - np.max(x, axis=axis, keepdims=True)
+    if p["mode"] == 0:  # special.py:440-478
+        e = np.exp(xdev)
+        return (e / np.sum(e, axis=axis, keepdims=True)).astype(x.dtype)
+    # special.py:715-740
+    return (xdev - np.log(np.sum(np.exp(xdev), axis=axis, keepdims=True))).astype(x.dtype)
+
+
+@_h("MaxAndArgmax")
+def _maxandargmax(node, args, prog):  # aesara/tensor/math.py:164-186
+    (x,) = args
+    x = np.asarray(x)
+    axes = tuple(node.params["axes"])
+    keep = [d for d in range(x.ndim) if d not in axes]
+    xt = np.transpose(x, keep + list(axes))
+    kept_shape = xt.shape[: len(keep)]
+    flat = xt.reshape(kept_shape + (-1,))
+    idx = np.argmax(flat, axis=-1).astype("int64")
+    if node.params.get("argmax_only"):
+        return idx
+    return [np.max(x, axis=axes).astype(x.dtype), idx]
+
+
 # -- BLAS family -------------------------------------------------------------------
 @_h("Dot22")
 def _dot22(node, args, prog):  # aesara/tensor/blas.py:1685-1694

@@ -294,6 +294,46 @@ def _():
     return [x, init], [f, g], [rnd(9), rnd(2)]
 
 
+# ---------------------------------------------------------------- Softmax family (§8f N1)
+@case("softmax_classifier")
+def _():
+    from aesara.tensor.special import log_softmax, softmax
+
+    x, t, W = at.fmatrix("x"), at.fmatrix("t"), at.fmatrix("W")
+    logits = x @ W
+    loss = -(t * log_softmax(logits, axis=1)).sum(axis=1).mean()
+    g = aesara.grad(loss, W)
+    outs = [loss, g, softmax(logits, axis=1), at.argmax(logits, axis=1), logits.max(axis=1)]
+    tv = np.eye(37, dtype="float32")[RNG.integers(0, 37, size=300)]
+    return [x, t, W], outs, [rnd((300, 64)), tv, rnd((64, 37), "float32", -0.5, 0.5)]
+
+
+@case("softmax_axes")
+def _():
+    from aesara.tensor.special import log_softmax, softmax
+
+    x3 = at.ftensor3("x3")
+    d = at.dmatrix("d")
+    big = at.fmatrix("big")
+    sm = softmax(x3, axis=1)
+    outs = [softmax(x3, axis=0), sm, softmax(x3, axis=2), softmax(x3, axis=None),
+            log_softmax(d, axis=-1), log_softmax(d, axis=0), softmax(big, axis=1),
+            aesara.grad((sm * sm).sum(), x3)]
+    return [x3, d, big], outs, [rnd((5, 7, 9)), rnd((11, 13), "float64"), rnd((3, 2500))]
+
+
+@case("max_and_argmax")
+def _():
+    x = at.ftensor3("x")
+    i = at.imatrix("i")
+    outs = [at.argmax(x, axis=0), at.argmax(x, axis=2), at.argmax(x), at.max_and_argmax(x, axis=1)[0],
+            at.max_and_argmax(x, axis=1)[1], at.argmax(i, axis=1), at.argmax(x, axis=[0, 2]),
+            at.argmin(x, axis=1)]
+    xv = rnd((6, 50, 8))
+    xv[2, 10, 3] = xv[2, 40, 3] = 9.0  # ties: first occurrence wins
+    return [x, i], outs, [xv, rnd((9, 300), "int32")]
+
+
 def main(names):
     from aesara_b200.graphs import optimized_program
 

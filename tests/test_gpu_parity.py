@@ -133,3 +133,80 @@ def test_output_combiner_device_path_single_rank(rt):
             np.testing.assert_allclose(g.to_numpy(), w, rtol=1e-6)
     finally:
         dist.destroy_process_group()
+
+
+def test_mlp_medium_size_fp32_faithful_vs_oracle(rt):
+    """cfg3 graph at B=4096, H=512 (tensor-core path engaged for every GEMM): the
+    fp32-faithful mode stays within rtol 1e-5 (norm-wise) of the NumPy oracle, the
+    bf16 compute policy within its stated 2e-2."""
+    from oracle.program_np import run_program
+
+    prog, _, _ = load_case("cfg3_mlp")
+    rng = np.random.default_rng(42)
+    B, H = 4096, 512
+    ins = [rng.standard_normal((B, H)).astype("float32"), rng.standard_normal((B, H)).astype("float32"),
+           (rng.standard_normal((H, H)) / np.sqrt(H)).astype("float32"), np.zeros(H, "float32"),
+           (rng.standard_normal((H, H)) / np.sqrt(H)).astype("float32"), np.zeros(H, "float32")]
+    want = run_program(prog, [np.array(a) for a in ins])
+    got = rt(prog, precision=0)(*ins)
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert_matches(g, w, blas=True, rtol=1e-5, what=f"fp32-faithful out {k}")
+    got_bf16 = rt(prog, precision=2)(*ins)
+    for k, (g, w) in enumerate(zip(got_bf16, want)):
+        assert_matches(g, w, blas=True, rtol=2e-2, what=f"bf16 policy out {k}")
+
+
+def test_lstm_medium_size_vs_oracle_and_graph_replay(rt):
+    """cfg4 graph at T=12, B=256, H=128: eager device loop == oracle; the CUDA-graph
+    replay of the whole evaluation returns bit-identical results."""
+    from oracle.program_np import run_program
+    from aesara_b200.runtime.device import DeviceArray
+    from aesara_b200.runtime.graph import GraphReplay
+
+    prog, _, _ = load_case("cfg4_lstm")
+    rng = np.random.default_rng(3)
+    T, B, H = 12, 256, 128
+    ins = [rng.standard_normal((T, B, 4 * H)).astype("float32"), np.zeros((B, H), "float32"),
+           np.zeros((B, H), "float32"), (rng.standard_normal((H, 4 * H)) / np.sqrt(H)).astype("float32")]
+    want = run_program(prog, [np.array(a) for a in ins])
+    ex = rt(prog, host_outputs=False)
+    dins = [DeviceArray.from_numpy(a) for a in ins]
+    eager = [o.to_numpy() for o in ex(*dins)]
+    for k, (g, w) in enumerate(zip(eager, want)):
+        assert_matches(g, w, blas=True, rtol=1e-5, what=f"lstm out {k}")
+    replay = GraphReplay(ex)
+    for _ in range(3):
+        outs = replay(*dins)
+    assert replay.replays >= 2
+    for g, e in zip(outs, eager):
+        np.testing.assert_array_equal(g.to_numpy(), e)
+
+
+def test_gemm_full_size_tile_independence(rt):
+    """BASELINE-size GEMM property (no CPU truth at this size): rows of a
+    [16384, 4096] x [4096, 4096] product equal the product of the row subset, for
+    both the 2-CTA and the ragged-tail tile paths; bf16 result is within 2e-2 of the
+    fp32-faithful one."""
+    import torch
+
+    from aesara_b200.runtime import kernels as K
+    from aesara_b200.runtime.device import DeviceArray
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, Kd = 16384, 4096, 4096
+    a = torch.randn(M, Kd, device="cuda", generator=g)
+    b = torch.randn(Kd, N, device="cuda", generator=g) / 64.0
+    A, Bm = DeviceArray.from_torch(a), DeviceArray.from_torch(b)
+    full = DeviceArray.empty((M, N), "float32")
+    K.gemm(full, 1.0, A, Bm, 0.0, precision=0)
+    sub_rows = slice(5000, 5000 + 777)
+    sub = DeviceArray.empty((777, N), "float32")
+    K.gemm(sub, 1.0, A.index((sub_rows,)), Bm, 0.0, precision=0)
+    f = full.owner.view(torch.float32).view(M, N)[sub_rows]
+    s = sub.owner.view(torch.float32)[: 777 * N].view(777, N)
+    assert torch.equal(f, s)  # identical arithmetic per output element, whatever the tiling
+    lo = DeviceArray.empty((M, N), "float32")
+    K.gemm(lo, 1.0, A, Bm, 0.0, precision=2)
+    l = lo.owner.view(torch.float32).view(M, N)
+    rel = ((l - full.owner.view(torch.float32).view(M, N)).abs().max() / f.abs().max()).item()
+    assert rel < 2e-2
