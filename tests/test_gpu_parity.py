@@ -136,9 +136,12 @@ def test_output_combiner_device_path_single_rank(rt):
 
 
 def test_mlp_medium_size_fp32_faithful_vs_oracle(rt):
-    """cfg3 graph at B=4096, H=512 (tensor-core path engaged for every GEMM): the
-    fp32-faithful mode stays within rtol 1e-5 (norm-wise) of the NumPy oracle, the
-    bf16 compute policy within its stated 2e-2."""
+    """cfg3 graph at B=4096, H=512 (tensor-core path engaged for every GEMM).  With 4096-term
+    fp32 dot products the fp32 CPU path (oracle = what the reference's sgemm path computes)
+    is itself only ~1e-5..1e-4 accurate on cancellation-prone gradient entries,
+    so the bar is stated against a float64 ground truth: the fp32-faithful (3xTF32) device
+    result is at least as close to it as the fp32 CPU path (within 2x), and both agree
+    norm-wise to 5e-5; the bf16 compute policy stays within its stated 2e-2."""
     from oracle.program_np import run_program
 
     prog, _, _ = load_case("cfg3_mlp")
@@ -147,13 +150,25 @@ def test_mlp_medium_size_fp32_faithful_vs_oracle(rt):
     ins = [rng.standard_normal((B, H)).astype("float32"), rng.standard_normal((B, H)).astype("float32"),
            (rng.standard_normal((H, H)) / np.sqrt(H)).astype("float32"), np.zeros(H, "float32"),
            (rng.standard_normal((H, H)) / np.sqrt(H)).astype("float32"), np.zeros(H, "float32")]
-    want = run_program(prog, [np.array(a) for a in ins])
+    cpu32 = run_program(prog, [np.array(a) for a in ins])
+    X, Y, W1, b1, W2, b2 = [a.astype(np.float64) for a in ins]
+    h = np.tanh(X @ W1 + b1)
+    diff = h @ W2 + b2 - Y
+    dout = 2.0 * diff / diff.size
+    dpre = (dout @ W2.T) * (1.0 - h * h)
+    truth = [np.mean(diff ** 2), X.T @ dpre, dpre.sum(0), h.T @ dout, dout.sum(0)]
+
+    def nerr(a, t):
+        return float(np.max(np.abs(np.asarray(a, np.float64) - t)) / max(np.max(np.abs(t)), 1e-300))
+
     got = rt(prog, precision=0)(*ins)
-    for k, (g, w) in enumerate(zip(got, want)):
-        assert_matches(g, w, blas=True, rtol=1e-5, what=f"fp32-faithful out {k}")
+    for k, (g, c, t) in enumerate(zip(got, cpu32, truth)):
+        e_dev, e_cpu = nerr(g, t), nerr(c, t)
+        assert e_dev <= max(2.0 * e_cpu, 1e-5), f"out {k}: device {e_dev:.2e} vs fp32 CPU {e_cpu:.2e}"
+        assert_matches(g, c, blas=True, rtol=5e-5, what=f"fp32-faithful out {k} vs fp32 CPU path")
     got_bf16 = rt(prog, precision=2)(*ins)
-    for k, (g, w) in enumerate(zip(got_bf16, want)):
-        assert_matches(g, w, blas=True, rtol=2e-2, what=f"bf16 policy out {k}")
+    for k, (g, t) in enumerate(zip(got_bf16, truth)):
+        assert nerr(g, t) < 2e-2, f"bf16 policy out {k}"
 
 
 def test_lstm_medium_size_vs_oracle_and_graph_replay(rt):
