@@ -134,7 +134,7 @@ def cfg5_inputs(N, D, seed=0):
     return [X, y, w, np.float32(0.0)]
 
 
-def optimized_program(inputs, outputs, name=None, optimizer="fast_run"):
+def optimized_program(inputs, outputs, name=None, optimizer="fast_run", linker="cvm"):
     """Run the reference rewriter and lower the resulting fgraph.  Returns
     ``(program, reference_function)``; the reference function is compiled with
     the reference C-linker (``Mode("cvm")``) and is the parity oracle."""
@@ -143,6 +143,6 @@ def optimized_program(inputs, outputs, name=None, optimizer="fast_run"):
 
     from .lower import lower_fgraph
 
-    f = aesara.function(inputs, outputs, mode=Mode("cvm", optimizer), on_unused_input="ignore")
+    f = aesara.function(inputs, outputs, mode=Mode(linker, optimizer), on_unused_input="ignore")
     prog = lower_fgraph(f.maker.fgraph, name=name)
     return prog, f

@@ -442,6 +442,26 @@ def _l_incsubtensor(op, apply):
     }
 
 
+@lowers("AdvancedSubtensor1")
+def _l_advsub1(op, apply):
+    return "AdvancedSubtensor1", {}
+
+
+@lowers("AdvancedIncSubtensor1")
+def _l_advincsub1(op, apply):
+    return "AdvancedIncSubtensor1", {"inplace": bool(op.inplace), "set": bool(op.set_instead_of_inc)}
+
+
+@lowers("Join")
+def _l_join(op, apply):
+    return "Join", {}
+
+
+@lowers("Split")
+def _l_split(op, apply):
+    return "Split", {"len_splits": int(op.len_splits)}
+
+
 # -- Scan --------------------------------------------------------------------------------
 @lowers("Scan")
 def _l_scan(op, apply):

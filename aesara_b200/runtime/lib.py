@@ -124,6 +124,16 @@ SIGNATURES = {
         C.c_int,
         [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "ab_take_rows": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+         C.c_int64, C.c_void_p, C.c_int, C.c_void_p],
+    ),
+    "ab_scatter_rows": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+         C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p],
+    ),
     "ab_launch_count": (C.c_uint64, []),
 }
 

@@ -648,6 +648,153 @@ def _incsubtensor(ex, i, node, args):
     return xd
 
 
+def _rows_view(x):
+    """x as [n_rows, inner] with a contiguous inner part (copy if needed)."""
+    inner = 1
+    for s in x.shape[1:]:
+        inner *= s
+    tail_contig = x.view(x.shape[1:], x.strides[1:]).is_c_contiguous() if x.ndim > 1 else True
+    if not tail_contig:
+        x = K.contiguous_copy(x)
+    row_stride = x.strides[0] if x.shape[0] > 1 else max(inner, 1)
+    return x, inner, row_stride
+
+
+@_op("AdvancedSubtensor1")
+def _advsub1(ex, i, node, args):
+    from ..ir import DTYPE_CODE
+    from . import lib as _lib
+    from .device import stream_handle
+
+    x, idx = args
+    if is_host(x) and is_host(idx):
+        return np.take(np.asarray(x), np.asarray(idx), axis=0)
+    x, idx = _as_dev_inputs(ex, i, node, [x, idx])
+    if idx.ndim != 1:
+        raise IndexError("AdvancedSubtensor1 needs a vector of indices")
+    if idx.dtype.kind not in "iu":
+        raise IndexError("index must be integers")
+    x, inner, row_stride = _rows_view(x)
+    out = DeviceArray.empty((idx.shape[0],) + x.shape[1:], x.dtype)
+    try:
+        _lib.check(_lib.load().ab_take_rows(x.itemsize, DTYPE_CODE[idx.dtype.name], x.ptr,
+                                            row_stride, x.shape[0], inner, idx.ptr, idx.strides[0],
+                                            idx.shape[0], out.ptr, 1, stream_handle()))
+    except _lib.AbError as e:
+        if e.code == 4:
+            raise IndexError(str(e)) from None
+        raise
+    return out
+
+
+@_op("AdvancedIncSubtensor1")
+def _advincsub1(ex, i, node, args):
+    from ..ir import DTYPE_CODE
+    from . import lib as _lib
+    from .device import stream_handle
+
+    p = node.params
+    xa, ya, ia = args
+    x, y, idx = _as_dev_inputs(ex, i, node, [xa, ya, ia])
+    if idx.ndim != 1 or idx.dtype.kind not in "iu":
+        raise IndexError("AdvancedIncSubtensor1 needs an integer vector of indices")
+    if idx.dtype.name not in ("int32", "int64"):
+        idx64 = DeviceArray.empty(idx.shape, "int64")
+        K.copy_into(idx64, idx)
+        idx = idx64
+    if not p["inplace"] or is_host(xa) or not x.view(x.shape[1:], x.strides[1:]).is_c_contiguous():
+        x = K.contiguous_copy(x)
+    inner = 1
+    for s in x.shape[1:]:
+        inner *= s
+    row_stride = x.strides[0] if x.shape[0] > 1 else max(inner, 1)
+    # y broadcasts against x[idx] (shape [n_idx] + x.shape[1:])
+    want = (idx.shape[0],) + x.shape[1:]
+    if y.ndim < len(want):
+        y = y.view((1,) * (len(want) - y.ndim) + y.shape, (0,) * (len(want) - y.ndim) + y.strides)
+    for d, (ys, ws) in enumerate(zip(y.shape, want)):
+        if ys not in (1, ws):
+            raise ValueError(f"shape mismatch: value array of shape {y.shape} could not be broadcast "
+                             f"to indexing result of shape {want}")
+    if y.dtype != x.dtype:
+        yy = DeviceArray.empty(y.shape, x.dtype)
+        K.copy_into(yy, y)
+        y = yy
+    # flatten y's trailing dims into one strided "column" index when possible, else materialise
+    yb = DeviceArray.empty(want, x.dtype)
+    K.copy_into(yb, y)
+    y_rs, y_cs = (inner, 1)
+    try:
+        _lib.check(_lib.load().ab_scatter_rows(DTYPE_CODE[x.dtype.name], DTYPE_CODE[idx.dtype.name],
+                                               1 if p["set"] else 0, x.ptr, row_stride, x.shape[0],
+                                               inner, idx.ptr, idx.strides[0], idx.shape[0], yb.ptr,
+                                               y_rs, y_cs, 1, stream_handle()))
+    except _lib.AbError as e:
+        if e.code == 4:
+            raise IndexError(str(e)) from None
+        raise
+    return x
+
+
+@_op("Join")
+def _join(ex, i, node, args):
+    axis, *tensors = args
+    axis = _int(axis)
+    if all(is_host(t) for t in tensors):
+        return np.concatenate([np.asarray(t) for t in tensors], axis=axis)
+    ts = _as_dev_inputs(ex, i, Node("Join", list(node.inputs[1:]), []), tensors)
+    nd = ts[0].ndim
+    if axis < -nd or axis >= nd:
+        raise IndexError(f"Join axis {axis} out of bounds [0, {nd})")
+    axis %= nd
+    shape = list(ts[0].shape)
+    for t in ts[1:]:
+        if t.ndim != nd or any(t.shape[d] != shape[d] for d in range(nd) if d != axis):
+            raise ValueError("all the input array dimensions except for the concatenation axis must "
+                             "match exactly")
+    shape[axis] = sum(t.shape[axis] for t in ts)
+    out = DeviceArray.empty(shape, ex.program.vars[node.outputs[0]].dtype)
+    start = 0
+    for t in ts:
+        n = t.shape[axis]
+        sl = [slice(None)] * nd
+        sl[axis] = slice(start, start + n)
+        if n:
+            K.copy_into(out.index(tuple(sl)), t)
+        start += n
+    return out
+
+
+@_op("Split")
+def _split(ex, i, node, args):
+    x, axis, splits = args
+    axis = _int(axis)
+    splits = [int(s) for s in (splits.to_numpy() if isinstance(splits, DeviceArray) else np.asarray(splits)).reshape(-1)]
+    if len(splits) != node.params["len_splits"]:
+        raise ValueError("Split: wrong number of split sizes")
+    if is_host(x):
+        x = np.asarray(x)
+        if sum(splits) != x.shape[axis]:
+            raise ValueError("Split: the split sizes do not sum to the input length along the axis")
+        outs, start = [], 0
+        for s in splits:
+            sl = [slice(None)] * x.ndim
+            sl[axis] = slice(start, start + s)
+            outs.append(np.array(x[tuple(sl)]))
+            start += s
+        return outs[0] if len(outs) == 1 else outs
+    axis %= x.ndim
+    if sum(splits) != x.shape[axis] or any(s < 0 for s in splits):
+        raise ValueError("Split: the split sizes do not sum to the input length along the axis")
+    outs, start = [], 0
+    for s in splits:
+        sl = [slice(None)] * x.ndim
+        sl[axis] = slice(start, start + s)
+        outs.append(K.contiguous_copy(x.index(tuple(sl))))  # Split has no view_map: fresh buffers
+        start += s
+    return outs[0] if len(outs) == 1 else outs
+
+
 @_op("Scan")
 def _scan(ex, i, node, args):
     outs = ex._state[i]["runner"].run(args)

@@ -181,6 +181,21 @@ int ab_softmax(int dtype, int mode, int64_t outer, int64_t r, int64_t inner, con
 int ab_max_and_argmax(int dtype, int64_t outer, int64_t r, const void* in, void* out_max,
                       void* out_argmax, void* stream);
 
+/* ---- integer-array indexing ---------------------------------------
+ * ab_take_rows: AdvancedSubtensor1 (aesara/tensor/subtensor.py:1925): out[r,:] = x[idx[r],:]
+ *   over x viewed as [n_rows, inner] (inner contiguous, rows x_row_stride elements apart);
+ *   negative indices wrap.  ab_scatter_rows: AdvancedIncSubtensor1 (:2128):
+ *   x[idx[r],:] += y[r,:] (duplicates accumulate, np.add.at) or = y[r,:].
+ * check != 0: synchronise and return AB_ERR_SHAPE if an index was out of range
+ * (the reference's IndexError). */
+int ab_take_rows(int itemsize, int idx_dtype, const void* x, int64_t x_row_stride, int64_t n_rows,
+                 int64_t inner, const void* idx, int64_t idx_stride, int64_t n_idx, void* out,
+                 int check, void* stream);
+int ab_scatter_rows(int dtype, int idx_dtype, int set_instead_of_inc, void* x,
+                    int64_t x_row_stride, int64_t n_rows, int64_t inner, const void* idx,
+                    int64_t idx_stride, int64_t n_idx, const void* y, int64_t y_row_stride,
+                    int64_t y_col_stride, int check, void* stream);
+
 /* number of kernels this library has launched since load (bench.py reports it) */
 uint64_t ab_launch_count(void);
 

@@ -360,6 +360,47 @@ def _incsubtensor(node, args, prog):  # aesara/tensor/subtensor.py:1454 (perform
     return x
 
 
+@_h("AdvancedSubtensor1")
+def _advsub1(node, args, prog):  # aesara/tensor/subtensor.py:1953-1990
+    x, idx = args
+    return np.take(np.asarray(x), np.asarray(idx), axis=0)
+
+
+@_h("AdvancedIncSubtensor1")
+def _advincsub1(node, args, prog):  # aesara/tensor/subtensor.py:2128 (perform)
+    x, y, idx = args
+    p = node.params
+    if not p["inplace"]:
+        x = x.copy()
+    if p["set"]:
+        x[idx] = y
+    else:
+        np.add.at(x, idx, y)
+    return x
+
+
+@_h("Join")
+def _join(node, args, prog):  # aesara/tensor/basic.py:2142 (perform: np.concatenate)
+    axis, *tensors = args
+    return np.concatenate(tensors, axis=int(axis))
+
+
+@_h("Split")
+def _split(node, args, prog):  # aesara/tensor/basic.py:1882
+    x, axis, splits = args
+    axis = int(axis)
+    splits = [int(s) for s in np.asarray(splits)]
+    if sum(splits) != np.shape(x)[axis]:
+        raise ValueError("Split: the split sizes do not sum to the input length along the axis")
+    outs, start = [], 0
+    for s in splits:
+        sl = [slice(None)] * np.ndim(x)
+        sl[axis] = slice(start, start + s)
+        outs.append(np.array(np.asarray(x)[tuple(sl)]))
+        start += s
+    return outs
+
+
 # -- Scan ---------------------------------------------------------------------------------
 @_h("Scan")
 def _scan(node, args, prog):

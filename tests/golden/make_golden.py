@@ -334,12 +334,48 @@ def _():
     return [x, i], outs, [xv, rnd((9, 300), "int32")]
 
 
+# ---------------------------------------------------------------- indexing / layout (§8f N3)
+@case("indexing_embedding")
+def _():
+    E = at.fmatrix("E")           # embedding table
+    idx = at.lvector("idx")
+    i32 = at.ivector("i32")
+    T3 = at.ftensor3("T3")
+    iv = at.lvector("iv")         # int64 values, for the bit-exact integer scatter
+    emb = E[idx]
+    loss = (emb * emb).sum()
+    gE = aesara.grad(loss, E)     # AdvancedIncSubtensor1 with duplicate indices
+    outs = [emb, gE, E[i32], T3[idx[:4]], at.inc_subtensor(E[i32], 1.5),
+            at.set_subtensor(E[idx[:3]], 0.0), at.inc_subtensor(at.zeros_like(iv)[idx % 5], iv[idx % 7])]
+    idxv = np.array([3, 0, 7, 3, -1, 3, 2, 0, 9, -10], dtype="int64")
+    return [E, idx, i32, T3, iv], outs, [rnd((10, 24)), idxv, np.array([1, 1, -2, 5], "int32"),
+                                         rnd((10, 3, 5)), rnd(12, "int64")]
+
+
+@case("join_split_reshape")
+def _():
+    a, b, c = at.fmatrix("a"), at.fmatrix("b"), at.fmatrix("c")
+    v = at.lvector("v")
+    j0 = at.join(0, a, b)
+    j1 = at.join(1, a, c)
+    s = at.split(j1, [2, 5], n_splits=2, axis=1)
+    outs = [j0, j1 * 2, s[0] + 1, s[1] - 1, at.join(0, v, v * 2), j0.reshape((-1, 2)),
+            at.concatenate([a.T, b.T], axis=1), at.stack([a, a * 3], axis=0)]
+    return [a, b, c, v], outs, [rnd((4, 6)), rnd((3, 6)), rnd((4, 1)), rnd(5, "int64")]
+
+
+PY_LINKER_CASES = {"indexing_embedding"}
+
+
 def main(names):
     from aesara_b200.graphs import optimized_program
 
     for name in names:
         ins, outs, values = CASES[name]()
-        prog, f = optimized_program(ins, outs, name=name)
+        # AdvancedIncSubtensor1's C code needs NumPy-1 PyArrayMapIter (gone in NumPy 2):
+        # those cases run the reference's Python `perform` implementations instead
+        linker = "py" if name in PY_LINKER_CASES else "cvm"
+        prog, f = optimized_program(ins, outs, name=name, linker=linker)
         ref = f(*values)
         prog.save(os.path.join(HERE, name + ".json"))
         blob = {}
