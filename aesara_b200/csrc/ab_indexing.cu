@@ -139,7 +139,7 @@ int scatter_impl(bool set, void* x, long long x_row_stride, const void* idx, lon
   T* xp = static_cast<T*>(x);
   const T* yp = static_cast<const T*>(y);
   const IDX* ip = static_cast<const IDX*>(idx);
-  if (SMALL) {
+  if constexpr (SMALL) {
     if (set) scatter_rows_small_kernel<T, IDX, true><<<grid, kThreads, 0, st>>>(xp, x_row_stride, ip, idx_stride, yp, y_rs, y_cs, n_idx, n_rows, inner, err);
     else scatter_rows_small_kernel<T, IDX, false><<<grid, kThreads, 0, st>>>(xp, x_row_stride, ip, idx_stride, yp, y_rs, y_cs, n_idx, n_rows, inner, err);
   } else {
