@@ -1,0 +1,401 @@
+// ab_scan_lstm.cu — Scan fast path: an LSTM-cell recurrence as ONE persistent kernel.
+//
+// Reference: aesara/scan/op.py:637 (Scan), loop :1799-2103 — for every step the
+// reference calls an inner compiled function (Gemm + four column-slice Subtensors + two
+// fused Elemwise nodes) from a Python/Cython loop.  When
+// runtime/scan.py recognises that inner graph
+//     pre = x_t + h_{t-1} @ U                      (Gemm, alpha = beta = 1)
+//     c_t = sigmoid(pre_f) * c_{t-1} + sigmoid(pre_i) * tanh(pre_g)
+//     h_t = sigmoid(pre_o) * tanh(c_t)              (gate order i, f, o, g)
+// the whole T-step loop runs here without returning to the host:
+//
+//   * the grid is one CTA per SM (cooperative launch, all CTAs co-resident); every step
+//     the [B, 4H] pre-activation is produced as 128 x 256 tcgen05 tiles (3xTF32,
+//     fp32-faithful like ab_gemm) whose 256 columns are the four gates of 64 hidden units
+//     (U is packed once with its columns gate-interleaved);
+//   * the LSTM cell is the tile's epilogue: accumulators come out of TMEM, x_t and
+//     c_{t-1} are read once, c_t / h_t are written to the Scan's circular output buffers
+//     and h_t is ALSO written as the hi/lo TF32 planes the next step's TMA loads — the
+//     pre-activations never touch HBM and there is no per-step pack or copy kernel;
+//   * steps are separated by a device-wide barrier (one atomic counter); rows are
+//     independent, so the barrier only orders "h_t written" before "h_t loaded by TMA"
+//     (release: __threadfence + atomicAdd; acquire: poll + fence.proxy.async).
+//
+// State lives in L2 (h planes 2 x 2 x B x H x 4 B, c in the output ring): 8192 x 1024
+// state rows do not fit the register file / shared memory of 148 SMs at M = 128 tiles.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "ab_common.h"
+#include "ab_tcgen05.cuh"
+
+namespace ab {
+
+namespace {
+
+using namespace ab::tc;
+
+constexpr int UNITS = 64;            // hidden units per tile
+constexpr int TILE_N = 4 * UNITS;    // 256 accumulator columns = 4 gates x 64 units
+constexpr int KB = 32;               // K elements (fp32/tf32) per 128-byte smem row
+
+struct LstmParams {
+  long long T, B, H;
+  const float* x;            // [T, B, 4H]
+  long long x_ts, x_rs;      // element strides of x: step, row (columns contiguous)
+  float* hbuf;               // Scan output ring of h: [S_h, B, H] contiguous rows
+  float* cbuf;               // Scan output ring of c: [S_c, B, H]
+  long long sh, sc;          // ring lengths (store_steps)
+  long long pos_h, pos_c;    // ring position written at step 0
+  float* hplane[2][2];       // [set][hi/lo] K-major planes [B, H] of h for the tensor cores
+  unsigned int* barrier;     // device-wide step barrier counter (zero-initialised)
+  int stages;
+  int a_tile_bytes, b_tile_bytes;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ float sigmoidf_ref(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_scan_kernel(const __grid_constant__ CUtensorMap map_h00, const __grid_constant__ CUtensorMap map_h01,
+                 const __grid_constant__ CUtensorMap map_h10, const __grid_constant__ CUtensorMap map_h11,
+                 const __grid_constant__ CUtensorMap map_u0, const __grid_constant__ CUtensorMap map_u1,
+                 const __grid_constant__ LstmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stage_bytes = 2 * (p.a_tile_bytes + p.b_tile_bytes);  // hi + lo of A and B
+  const int num_k_blocks = (int)((p.H + KB - 1) / KB);
+  const long long tiles_n = p.H / UNITS;
+  const long long num_tiles = ((p.B + BLOCK_M - 1) / BLOCK_M) * tiles_n;
+  const uint32_t tmem_cols = 2 * TILE_N;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // pipeline state persists across tiles and steps
+  int stage = 0;
+  uint32_t phase = 0;
+  uint32_t it = 0;
+
+  for (long long t = 0; t < p.T; ++t) {
+    const int set = (int)(t & 1);  // h planes read this step; the other set is written
+    if (warp == 0) {
+      // ================= TMA producer =================
+      if (lane == 0) {
+        const CUtensorMap* mh0 = set ? &map_h10 : &map_h00;
+        const CUtensorMap* mh1 = set ? &map_h11 : &map_h01;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int m0 = (int)((tile / tiles_n) * BLOCK_M);
+          const int n0 = (int)((tile % tiles_n) * TILE_N);
+          for (int kb = 0; kb < num_k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sbase = smem + (size_t)stage * stage_bytes;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+            const int kc = kb * KB;
+            tma_load_2d(sbase, mh0, &full_bar[stage], kc, m0);
+            tma_load_2d(sbase + p.a_tile_bytes, mh1, &full_bar[stage], kc, m0);
+            tma_load_2d(sbase + 2 * p.a_tile_bytes, &map_u0, &full_bar[stage], kc, n0);
+            tma_load_2d(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_u1, &full_bar[stage], kc, n0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ================= MMA issuer =================
+      if (lane == 0) {
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+          const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+          mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + as * TILE_N;
+          for (int kb = 0; kb < num_k_blocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t a_hi = sbase, a_lo = sbase + p.a_tile_bytes;
+            const uint32_t b_hi = sbase + 2 * p.a_tile_bytes, b_lo = b_hi + p.b_tile_bytes;
+#pragma unroll
+            for (int k = 0; k < SW_BYTES / 32; ++k) {
+              const uint32_t ko = k * 32;
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              umma<0>(d_tmem, make_smem_desc(a_lo + ko, 16), make_smem_desc(b_hi + ko, 16), p.idesc, acc);
+              umma<0>(d_tmem, make_smem_desc(a_hi + ko, 16), make_smem_desc(b_lo + ko, 16), p.idesc, 1u);
+              umma<0>(d_tmem, make_smem_desc(a_hi + ko, 16), make_smem_desc(b_hi + ko, 16), p.idesc, 1u);
+            }
+            tcgen05_commit(&empty_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          tcgen05_commit(&tmem_full_bar[as]);
+        }
+      }
+    } else {
+      // ================= epilogue = the LSTM cell (warps 2..5) =================
+      const int q = warp & 3;
+      const long long rh = (p.pos_h + t) % p.sh;                   // ring rows written now
+      const long long rc = (p.pos_c + t) % p.sc;
+      const long long rc_prev = (p.pos_c + t - 1 + p.sc) % p.sc;   // c_{t-1}
+      float* h_out = p.hbuf + rh * p.B * p.H;
+      float* c_out = p.cbuf + rc * p.B * p.H;
+      const float* c_in = p.cbuf + rc_prev * p.B * p.H;
+      float* hp_hi = p.hplane[set ^ 1][0];
+      float* hp_lo = p.hplane[set ^ 1][1];
+      const float* xt = p.x + t * p.x_ts;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        const long long m0 = (tile / tiles_n) * BLOCK_M;
+        const long long u0 = (tile % tiles_n) * UNITS;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tcgen05_fence_after();
+        const long long row = m0 + q * 32 + lane;
+        const uint32_t t_acc = tmem_base + as * TILE_N + ((uint32_t)(q * 32) << 16);
+        for (int s = 0; s < 2; ++s) {
+          uint32_t ri[32], rf[32], ro[32], rg[32];
+          tmem_ld_32x32b_x32(t_acc + 0 * UNITS + s * 32, ri);
+          tmem_ld_32x32b_x32(t_acc + 1 * UNITS + s * 32, rf);
+          tmem_ld_32x32b_x32(t_acc + 2 * UNITS + s * 32, ro);
+          tmem_ld_32x32b_x32(t_acc + 3 * UNITS + s * 32, rg);
+          if (s == 1) {
+            tcgen05_fence_before();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
+                         : "memory");
+          }
+          if (row < p.B) {
+            const long long uc = u0 + s * 32;
+            const float* xr = xt + row * p.x_rs;
+            const long long so = row * p.H + uc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 xi = *reinterpret_cast<const float4*>(xr + 0 * p.H + uc + j);
+              const float4 xf = *reinterpret_cast<const float4*>(xr + 1 * p.H + uc + j);
+              const float4 xo = *reinterpret_cast<const float4*>(xr + 2 * p.H + uc + j);
+              const float4 xg = *reinterpret_cast<const float4*>(xr + 3 * p.H + uc + j);
+              const float4 cp = *reinterpret_cast<const float4*>(c_in + so + j);
+              float cn[4], hn[4], hh[4], hl[4];
+              const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
+              const float xov[4] = {xo.x, xo.y, xo.z, xo.w}, xgv[4] = {xg.x, xg.y, xg.z, xg.w};
+              const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // Gemm: 1*acc + 1*x_t (blas.py:984-1017), then the two Elemwise composites
+                const float pi = __uint_as_float(ri[j + e]) + xiv[e];
+                const float pf = __uint_as_float(rf[j + e]) + xfv[e];
+                const float po = __uint_as_float(ro[j + e]) + xov[e];
+                const float pg = __uint_as_float(rg[j + e]) + xgv[e];
+                cn[e] = sigmoidf_ref(pf) * cpv[e] + sigmoidf_ref(pi) * tanhf(pg);
+                hn[e] = sigmoidf_ref(po) * tanhf(cn[e]);
+                uint32_t hb, lb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(hn[e]));
+                hh[e] = __uint_as_float(hb);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(hn[e] - hh[e]));
+                hl[e] = __uint_as_float(lb);
+              }
+              *reinterpret_cast<float4*>(c_out + so + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+              *reinterpret_cast<float4*>(h_out + so + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+              *reinterpret_cast<float4*>(hp_hi + so + j) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+              *reinterpret_cast<float4*>(hp_lo + so + j) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+            }
+          }
+        }
+      }
+    }
+    // ---- device-wide step barrier: h_t is complete everywhere before step t+1 loads it ----
+    if (t + 1 < p.T) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(p.barrier, 1u);
+        const unsigned int target = (unsigned int)((t + 1) * gridDim.x);
+        while (atomicAdd(p.barrier, 0u) < target) { __nanosleep(64); }
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> TMA reads
+      }
+      __syncthreads();
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(tmem_cols)
+                 : "memory");
+  }
+}
+
+// hi/lo TF32 planes of a [R, K] row-major-able matrix; rows optionally gate-interleaved:
+// plane row n' = tile*256 + gate*64 + u  <-  source column gate*H + tile*64 + u of U[K, 4H]
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ src, long long R, long long K, long long s_r,
+                    long long s_k, int interleave_h, float* __restrict__ hi, float* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= R * K) return;
+  const long long r = i / K, k = i - r * K;
+  long long rs = r;
+  if (interleave_h > 0) {
+    const long long tile = r / TILE_N, rem = r % TILE_N;
+    const long long gate = rem / UNITS, u = rem % UNITS;
+    rs = gate * interleave_h + tile * UNITS + u;
+  }
+  const float v = src[rs * s_r + k * s_k];
+  uint32_t hb, lb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+  const float h = __uint_as_float(hb);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - h));
+  hi[i] = h;
+  lo[i] = __uint_as_float(lb);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map_f32(CUtensorMap* map, const void* base, long long k, long long rows, int box_rows) {
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return fail(AB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    enc = reinterpret_cast<EncodeTiledFn>(fp);
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 4};
+  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AB_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+  return AB_OK;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+}  // namespace ab
+
+using namespace ab;
+
+extern "C" int ab_lstm_scan_workspace_bytes(int64_t b, int64_t h, size_t* bytes) {
+  if (!bytes) return fail(AB_ERR_INVALID, "null out pointer");
+  const size_t hp = align_up((size_t)b * h * 4, 1024);
+  const size_t up = align_up((size_t)4 * h * h * 4, 1024);
+  *bytes = 4 * hp + 2 * up + 1024 + 256;
+  return AB_OK;
+}
+
+extern "C" int ab_lstm_scan_supported(int64_t t, int64_t b, int64_t h) {
+  return (t >= 1 && b >= 1 && h >= UNITS && h % UNITS == 0 && h % 4 == 0 && b < (1LL << 31) &&
+          h < (1LL << 29)) ? 1 : 0;
+}
+
+// h0 [B,H] (strides h0_rs, 1...), c0 likewise are expected to be already written into the
+// rings at row (pos - 1) by the caller (Scan's IncSubtensor{InplaceSet} initial-state
+// placement); h_init points at that row of the h ring (contiguous [B,H]).
+extern "C" int ab_lstm_scan(int64_t T, int64_t B, int64_t H, const void* x, int64_t x_ts,
+                            int64_t x_rs, const void* U, int64_t u_rs, int64_t u_cs, void* hbuf,
+                            int64_t sh, int64_t pos_h, void* cbuf, int64_t sc, int64_t pos_c,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (!ab_lstm_scan_supported(T, B, H)) return fail(AB_ERR_UNSUPPORTED, "LSTM scan shape not supported");
+  if ((x_rs % 4) || (x_ts % 4) || (reinterpret_cast<uintptr_t>(x) % 16))
+    return fail(AB_ERR_UNSUPPORTED, "x must be 16-byte aligned with 16-byte aligned rows");
+  cudaStream_t st = as_stream(stream);
+  size_t need = 0;
+  ab_lstm_scan_workspace_bytes(B, H, &need);
+  if (!workspace || workspace_bytes < need)
+    return fail(AB_ERR_INVALID, "LSTM scan workspace too small: need %zu bytes, have %zu", need, workspace_bytes);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  const size_t hp = align_up((size_t)B * H * 4, 1024);
+  const size_t up = align_up((size_t)4 * H * H * 4, 1024);
+  LstmParams p{};
+  p.T = T; p.B = B; p.H = H;
+  p.x = static_cast<const float*>(x); p.x_ts = x_ts; p.x_rs = x_rs;
+  p.hbuf = static_cast<float*>(hbuf); p.cbuf = static_cast<float*>(cbuf);
+  p.sh = sh; p.sc = sc; p.pos_h = pos_h; p.pos_c = pos_c;
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < 2; ++k) p.hplane[s][k] = reinterpret_cast<float*>(ws + (size_t)(2 * s + k) * hp);
+  float* u_hi = reinterpret_cast<float*>(ws + 4 * hp);
+  float* u_lo = reinterpret_cast<float*>(ws + 4 * hp + up);
+  p.barrier = reinterpret_cast<unsigned int*>(ws + 4 * hp + 2 * up);
+  AB_CUDA(cudaMemsetAsync(p.barrier, 0, 256, st));
+  // planes of h_{-1}: the ring row just before pos_h
+  const float* h_init = p.hbuf + ((pos_h - 1 + sh) % sh) * B * H;
+  {
+    const long long n = B * H;
+    split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h_init, B, H, H, 1, 0,
+                                                                    p.hplane[0][0], p.hplane[0][1]);
+    g_launches++;
+    // U[K=H, N=4H] -> planes [4H (gate-interleaved), K=H]: element (n, k) = U[k*u_rs + n*u_cs]
+    const long long nu = 4 * H * H;
+    split_planes_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, st>>>(
+        static_cast<const float*>(U), 4 * H, H, u_cs, u_rs, (int)H, u_hi, u_lo);
+    g_launches++;
+    AB_CUDA(cudaGetLastError());
+  }
+  p.a_tile_bytes = BLOCK_M * SW_BYTES;
+  p.b_tile_bytes = TILE_N * SW_BYTES;
+  const int stage_bytes = 2 * (p.a_tile_bytes + p.b_tile_bytes);
+  p.stages = std::max(2, std::min(8, (kMaxSmem - 1024) / stage_bytes));
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_N >> 3) << 17) |
+            ((uint32_t)(BLOCK_M >> 4) << 24);
+  CUtensorMap mh[2][2], mu[2];
+  int rc;
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < 2; ++k)
+      if ((rc = make_map_f32(&mh[s][k], p.hplane[s][k], H, B, BLOCK_M))) return rc;
+  if ((rc = make_map_f32(&mu[0], u_hi, H, 4 * H, TILE_N))) return rc;
+  if ((rc = make_map_f32(&mu[1], u_lo, H, 4 * H, TILE_N))) return rc;
+
+  static bool attr = false;
+  if (!attr) {
+    AB_CUDA(cudaFuncSetAttribute(lstm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr = true;
+  }
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  AB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_scan_kernel, kThreads, smem));
+  if (per_sm < 1) return fail(AB_ERR_CUDA, "lstm_scan_kernel does not fit on an SM");
+  const long long num_tiles = ((B + BLOCK_M - 1) / BLOCK_M) * (H / UNITS);
+  // every CTA must be resident for the device-wide barrier: cooperative launch, <= 1 per SM
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(num_tiles, sms));
+  void* args[] = {&mh[0][0], &mh[0][1], &mh[1][0], &mh[1][1], &mu[0], &mu[1], &p};
+  AB_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_scan_kernel, dim3(grid), dim3(kThreads), args,
+                                      smem, st));
+  g_launches++;
+  return AB_OK;
+}

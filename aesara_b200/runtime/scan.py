@@ -11,6 +11,8 @@ leaves the device between steps; the only host work per step is launching.
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import kernels as K
@@ -36,6 +38,16 @@ class ScanRunner:
         self.n_shared = info["n_shared_outs"]
         self.n_seqs = info["n_seqs"]
         self.mintaps = [min(t) for t in self.tap_array] + [0] * self.n_nit_sot
+        # fast path: LSTM-cell recurrence -> one persistent kernel (runtime/scan_lstm.py)
+        self.lstm = None
+        if (self.n_seqs == 1 and not self.mm_in and self.tap_array == [[-1], [-1]]
+                and self.n_nit_sot == 0 and self.n_shared == 0 and info["n_non_seqs"] == 1
+                and not info["as_while"] and parent.precision == 0
+                and not os.environ.get("AB_SCAN_NO_FAST")):
+            from .scan_lstm import LstmMatch
+
+            self.lstm = LstmMatch(self.inner)
+        self.used_fast_path = False
 
     def run(self, args):
         info = self.info
@@ -82,6 +94,18 @@ class ScanRunner:
 
         pos = [(-self.mintaps[idx]) % store_steps[idx] for idx in range(n_outs + n_nit)]
         i, cond = 0, True
+        self.used_fast_path = False
+        if self.lstm is not None and len(non_seqs) == 1:
+            from . import scan_lstm
+
+            U = dev(non_seqs[0], len(args) - 1)
+            hb, cb = bufs[0], bufs[1]
+            if (scan_lstm.eligible(seqs[0], U, hb, cb, n_steps)
+                    and self.lstm.match(hb.shape[1], hb.shape[2])):
+                scan_lstm.run_lstm(n_steps, seqs[0], U, hb, cb, pos[0], pos[1])
+                i = n_steps
+                pos = [(p + n_steps) % s for p, s in zip(pos, store_steps)]
+                self.used_fast_path = True
         while i < n_steps and cond:
             inner_in = [s.index((i,)) for s in seqs]
             for idx, taps in enumerate(self.tap_array):

@@ -196,6 +196,21 @@ int ab_scatter_rows(int dtype, int idx_dtype, int set_instead_of_inc, void* x,
                     int64_t idx_stride, int64_t n_idx, const void* y, int64_t y_row_stride,
                     int64_t y_col_stride, int check, void* stream);
 
+/* ---- Scan fast path: LSTM-cell recurrence as one persistent kernel -----------------
+ * (aesara/scan/op.py:637; inner graph of SURVEY App. A.4).  For t in [0,T):
+ *   pre = x[t] + h_{t-1} @ U;  c_t = sigmoid(pre_f)*c_{t-1} + sigmoid(pre_i)*tanh(pre_g);
+ *   h_t = sigmoid(pre_o)*tanh(c_t)      (gate column order i, f, o, g; 3xTF32 tcgen05 tiles)
+ * hbuf / cbuf are the Scan's circular output buffers [sh|sc, B, H] (contiguous); the row
+ * before pos_h / pos_c holds the initial state; step t writes row (pos + t) % s.
+ * x is [T, B, 4H] with element strides (x_ts, x_rs, 1); U is [H, 4H] with strides
+ * (u_rs, u_cs).  One cooperative launch; steps are ordered by a device-wide barrier. */
+int ab_lstm_scan_supported(int64_t t, int64_t b, int64_t h);
+int ab_lstm_scan_workspace_bytes(int64_t b, int64_t h, size_t* bytes);
+int ab_lstm_scan(int64_t T, int64_t B, int64_t H, const void* x, int64_t x_ts, int64_t x_rs,
+                 const void* U, int64_t u_rs, int64_t u_cs, void* hbuf, int64_t sh, int64_t pos_h,
+                 void* cbuf, int64_t sc, int64_t pos_c, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
 /* number of kernels this library has launched since load (bench.py reports it) */
 uint64_t ab_launch_count(void);
 

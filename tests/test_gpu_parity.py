@@ -189,6 +189,20 @@ def test_lstm_medium_size_vs_oracle_and_graph_replay(rt):
     eager = [o.to_numpy() for o in ex(*dins)]
     for k, (g, w) in enumerate(zip(eager, want)):
         assert_matches(g, w, blas=True, rtol=1e-5, what=f"lstm out {k}")
+    scan_idx = [i for i, n in enumerate(prog.nodes) if n.op == "Scan"][0]
+    assert ex._state[scan_idx]["runner"].used_fast_path  # the persistent LSTM kernel ran
+    # the general device loop (per-step launches) gives the same answer
+    import os
+
+    os.environ["AB_SCAN_NO_FAST"] = "1"
+    try:
+        ex_gen = rt(prog, host_outputs=False)
+        general = [o.to_numpy() for o in ex_gen(*dins)]
+    finally:
+        del os.environ["AB_SCAN_NO_FAST"]
+    assert not ex_gen._state[scan_idx]["runner"].used_fast_path
+    for k, (g, e) in enumerate(zip(general, eager)):
+        assert_matches(g, e, blas=True, rtol=1e-5, what=f"general loop vs fast path out {k}")
     replay = GraphReplay(ex)
     for _ in range(3):
         outs = replay(*dins)

@@ -90,3 +90,37 @@ def test_host_eval_matches_oracle_on_shape_arithmetic():
                 np.testing.assert_array_equal(x, y)
             n += 1
     assert n >= 5
+
+
+def _scan_runner(name):
+    from aesara_b200.runtime.vm import ProgramExecutor
+
+    prog, _, _ = load_case(name)
+    ex = ProgramExecutor(prog)
+    idx = [i for i, n in enumerate(prog.nodes) if n.op == "Scan"][0]
+    return ex._state[idx]["runner"]
+
+
+def test_lstm_fast_path_matcher_accepts_the_cfg4_inner_graph():
+    """The matcher traces the inner program with address-only stand-ins (no GPU needed)."""
+    r = _scan_runner("cfg4_lstm")
+    assert r.lstm is not None
+    assert r.lstm.match(256, 128) is True
+    assert r.lstm.match(8192, 1024) is True
+
+
+def test_lstm_fast_path_matcher_rejects_other_recurrences():
+    import copy
+
+    assert _scan_runner("scan_cumsum_allsteps").lstm is None
+    assert _scan_runner("scan_two_taps_nitsot").lstm is None
+    # same structure but a different cell (tanh on the output gate replaced by sigmoid)
+    r = _scan_runner("cfg4_lstm")
+    inner = r.inner.program
+    for n in inner.nodes:
+        if n.op == "Elemwise" and "tanh" in [s["op"] for s in n.params["expr"]["stmts"]]:
+            n.params = copy.deepcopy(n.params)
+            for s in n.params["expr"]["stmts"]:
+                if s["op"] == "tanh":
+                    s["op"] = "sigmoid"
+    assert r.lstm.match(256, 128) is False
