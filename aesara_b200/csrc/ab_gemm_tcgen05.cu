@@ -6,20 +6,22 @@
 //
 //   precision 0  3xTF32: each operand x is split into hi = tf32(x) and
 //                lo = tf32(x - hi); D += Ahi*Bhi + Ahi*Blo + Alo*Bhi with FP32
-//                accumulation in TMEM (error ~2^-21 relative, rtol 1e-5 holds);
+//                accumulation in TMEM over 128-element K segments that are summed
+//                round-to-nearest in registers (rtol 1e-5 holds at any K);
 //   precision 1  one TF32 pass straight from the fp32 operands;
 //   precision 2  BF16 operands, FP32 accumulation (the "bf16 compute policy"
 //                of BASELINE config 3; stated looser rtol).
 //
-// Structure (one 128 x BLOCK_N output tile per CTA, 192 threads):
+// Structure (one 128 x BLOCK_N output tile per CTA, 320 threads):
 //   warp 0     TMA producer: cp.async.bulk.tensor 2-D loads of K-major,
 //              128-byte-swizzled operand tiles into a multi-stage smem ring,
 //              completion on mbarriers (expect_tx);
 //   warp 1     allocates TMEM, then one elected lane issues tcgen05.mma
 //              (cta_group::1, M=128, N=BLOCK_N, K=32 bytes per instruction);
 //              tcgen05.commit releases smem stages / signals the epilogue;
-//   warps 2-5  epilogue: tcgen05.ld 32x32b the accumulator lanes they own,
-//              apply alpha/beta and store C with arbitrary strides.
+//   warps 2-9  epilogue: tcgen05.ld 32x32b the accumulator lanes they own (two warps
+//              per lane quarter, half of the columns each), fold K segments into FP32
+//              registers, apply alpha/beta and store C with arbitrary strides.
 //
 // Operands that are not K-major / 16-byte-pitched in global memory (the
 // DimShuffle{1,0} views of the MLP backward pass, blas.py:719-726 "unit" cases)
@@ -47,7 +49,9 @@ struct GemmParams {
   const float* Cin;       // beta term source (== C for the in-place Gemm, another buffer otherwise)
   long long cin_rs, cin_cs;
   int block_n;            // 64 / 128 / 256
-  int acc_stages;         // TMEM accumulator stages (2 -> epilogue overlaps the next tile)
+  int acc_stages;         // TMEM accumulator stages (2 -> epilogue overlaps the next segment)
+  int seg_kblocks;        // k-blocks accumulated inside the tensor core before the epilogue
+                          // folds the partial sum into its FP32 registers (see "segments")
   int stages;
   int nparts;             // 1, or 2 for the hi/lo split (3 MMAs per k-step)
   int k_elems_per_row;    // K elements per stage = per 128-byte K-major row: 32 (tf32) / 64 (bf16)
@@ -72,6 +76,84 @@ __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, 
       tma_load_2d(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
   }
 }
+
+// ---------------------------------------------------------------------- segments
+// The tensor core adds each MMA's products into the FP32 accumulator with truncation
+// (round toward zero), a bias that grows linearly with the number of accumulation steps:
+// measured on B200, an unsegmented 3xTF32 K = 4096 product is ~3e-5 from the FP64 result
+// where a true-fp32 sgemm is ~4e-7 (tests/test_gpu_blas.py::test_gemm_long_k_accuracy).
+// So the K loop is cut into segments of seg_kblocks k-blocks: each segment starts a fresh
+// TMEM accumulator, and the epilogue warps add the finished segment into FP32 registers
+// with round-to-nearest while the tensor core works on the next segment in the other
+// TMEM stage.  For precision 0 a segment is 128 K elements (48 truncating steps); the
+// tf32 / bf16 policies keep the whole K loop in one segment.
+constexpr int kAccRegs = 128;  // accumulator columns per epilogue thread (BLOCK_N 256 / 2)
+
+__device__ __forceinline__ void fold_segment(float (&acc)[kAccRegs], uint32_t t_acc, int nchunks,
+                                             bool first) {
+#pragma unroll
+  for (int c = 0; c < kAccRegs / 32; ++c) {
+    if (c < nchunks) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
+      if (first) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __uint_as_float(r[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+      }
+    }
+  }
+}
+
+// C[row, n0 + ...] = alpha * acc + beta * Cin for one thread's row and column range
+struct EpilogueOut {
+  const GemmParams& p;
+  bool vec_ok;
+  __device__ explicit EpilogueOut(const GemmParams& p_) : p(p_) {
+    vec_ok = (p.c_cs == 1) && ((p.c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+             (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
+                                 ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
+  }
+  __device__ __forceinline__ void store(const float (&acc)[kAccRegs], long long row, long long n0,
+                                        int nchunks) const {
+    if (row >= p.M) return;
+    float* crow = p.C + row * p.c_rs;
+    const float* irow = p.Cin + row * p.cin_rs;
+#pragma unroll
+    for (int c = 0; c < kAccRegs / 32; ++c) {
+      if (c < nchunks) {
+        const long long col0 = n0 + c * 32;
+        if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v;
+            v.x = p.alpha * acc[c * 32 + j];
+            v.y = p.alpha * acc[c * 32 + j + 1];
+            v.z = p.alpha * acc[c * 32 + j + 2];
+            v.w = p.alpha * acc[c * 32 + j + 3];
+            if (p.beta != 0.0f) {
+              const float4 o = *reinterpret_cast<const float4*>(irow + col0 + j);
+              v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
+            }
+            *reinterpret_cast<float4*>(crow + col0 + j) = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long col = col0 + j;
+            if (col < p.N) {
+              float v = p.alpha * acc[c * 32 + j];
+              if (p.beta != 0.0f) v += p.beta * irow[col * p.cin_cs];
+              crow[col * p.c_cs] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+};
 
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -107,7 +189,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);  // every epilogue thread arrives
+      mbar_init(&tmem_empty_bar[s], kThreads - 64);  // every epilogue thread arrives
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -157,103 +239,75 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t it = 0;  // tiles processed by this CTA
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t as = it % (uint32_t)p.acc_stages;
-        const uint32_t aphase = (it / (uint32_t)p.acc_stages) & 1u;
-        // wait until the epilogue has drained this accumulator stage
-        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+      uint32_t sit = 0;  // accumulator segments issued by this CTA
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb0 = 0; kb0 < num_k_blocks; kb0 += p.seg_kblocks, ++sit) {
+          const int kb1 = min(kb0 + p.seg_kblocks, num_k_blocks);
+          const uint32_t as = sit % (uint32_t)p.acc_stages;
+          const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+          // wait until the epilogue has drained this accumulator stage
+          mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
           tcgen05_fence_after();
-          const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t a_hi = sbase;
-          const uint32_t a_lo = sbase + p.a_tile_bytes;
-          const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
-          const uint32_t b_lo = b_hi + p.b_tile_bytes;
+          const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t a_hi = sbase;
+            const uint32_t a_lo = sbase + p.a_tile_bytes;
+            const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
+            const uint32_t b_lo = b_hi + p.b_tile_bytes;
+            const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
+            const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
 #pragma unroll
-          const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
-          const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
-          for (int k = 0; k < SW_BYTES / 32; ++k) {  // 32 bytes of K per instruction
-            const uint32_t ka = k * (uint32_t)p.a_kstep, kb_off = k * (uint32_t)p.b_kstep;
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            if (p.nparts == 2) {
-              // small cross terms first, the dominant hi*hi term last
-              umma<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
-              umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kb_off, b_lbo), p.idesc, 1u);
-              umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, 1u);
-            } else {
-              umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
+            for (int k = 0; k < SW_BYTES / 32; ++k) {  // 32 bytes of K per instruction
+              const uint32_t ka = k * (uint32_t)p.a_kstep, kb_off = k * (uint32_t)p.b_kstep;
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (p.nparts == 2) {
+                // small cross terms first, the dominant hi*hi term last
+                umma<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
+                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kb_off, b_lbo), p.idesc, 1u);
+                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, 1u);
+              } else {
+                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
+              }
             }
+            tcgen05_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          tcgen05_commit(&tmem_full_bar[as]);  // segment complete
         }
-        tcgen05_commit(&tmem_full_bar[as]);  // accumulator complete
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const bool vec_ok = (p.c_cs == 1) && ((p.c_rs & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                        (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
-                                            ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
-    uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-    const uint32_t as = it % (uint32_t)p.acc_stages;
-    const uint32_t aphase = (it / (uint32_t)p.acc_stages) & 1u;
-    const long long m0 = (tile / tiles_n) * BLOCK_M;
-    const long long n0 = (tile % tiles_n) * p.block_n;
-    mbar_wait(&tmem_full_bar[as], aphase);
-    tcgen05_fence_after();
-    const long long row = m0 + q * 32 + lane;
-    const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_acc + (uint32_t)c0, r);
-      if (c0 + 32 >= p.block_n) {
-        // last chunk is in registers: hand the accumulator stage back to the MMA warp
+    // ================= epilogue (warps 2..9) =================
+    // Two warps share each TMEM lane quarter; each owns half of the tile's columns and
+    // keeps them as FP32 register accumulators across the K segments.
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the columns
+    const int half_n = p.block_n >> 1;
+    const int nchunks = half_n >> 5;     // 32-column chunks: 1, 2 or 4
+    const EpilogueOut eo(p);
+    float acc[kAccRegs];
+    uint32_t sit = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long m0 = (tile / tiles_n) * BLOCK_M;
+      const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
+      for (int kb0 = 0; kb0 < num_k_blocks; kb0 += p.seg_kblocks, ++sit) {
+        const uint32_t as = sit % (uint32_t)p.acc_stages;
+        const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tcgen05_fence_after();
+        const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
+                               ((uint32_t)(q * 32) << 16);
+        fold_segment(acc, t_acc, nchunks, kb0 == 0);
+        // the segment is in registers: hand the accumulator stage back to the MMA warp
         tcgen05_fence_before();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
                      : "memory");
       }
-      if (row < p.M) {
-        const long long col0 = n0 + c0;
-        float* crow = p.C + row * p.c_rs;
-        const float* irow = p.Cin + row * p.cin_rs;
-        if (vec_ok && col0 + 32 <= p.N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v;
-            v.x = p.alpha * __uint_as_float(r[j]);
-            v.y = p.alpha * __uint_as_float(r[j + 1]);
-            v.z = p.alpha * __uint_as_float(r[j + 2]);
-            v.w = p.alpha * __uint_as_float(r[j + 3]);
-            float4* dst = reinterpret_cast<float4*>(crow + col0 + j);
-            if (p.beta != 0.0f) {
-              const float4 o = *reinterpret_cast<const float4*>(irow + col0 + j);
-              v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
-            }
-            *dst = v;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long col = col0 + j;
-            if (col < p.N) {
-              float* dst = crow + col * p.c_cs;
-              float v = p.alpha * __uint_as_float(r[j]);
-              if (p.beta != 0.0f) v += p.beta * irow[col * p.cin_cs];
-              *dst = v;
-            }
-          }
-        }
-      }
+      eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
     }
-    }  // tile loop
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -369,7 +423,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 256);  // the epilogue threads of both CTAs
+      mbar_init(&tmem_empty_bar[s], 2 * (kThreads - 64));  // the epilogue threads of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -418,98 +472,70 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
     if (leader && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t it = 0;
-      for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
-        const uint32_t as = it % (uint32_t)p.acc_stages;
-        const uint32_t aphase = (it / (uint32_t)p.acc_stages) & 1u;
-        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+      uint32_t sit = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        for (int kb0 = 0; kb0 < num_k_blocks; kb0 += p.seg_kblocks, ++sit) {
+          const int kb1 = min(kb0 + p.seg_kblocks, num_k_blocks);
+          const uint32_t as = sit % (uint32_t)p.acc_stages;
+          const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+          mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
           tcgen05_fence_after();
-          const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t a_hi = sbase;
-          const uint32_t a_lo = sbase + p.a_tile_bytes;
-          const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
-          const uint32_t b_lo = b_hi + p.b_tile_bytes;
-          const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
-          const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
+          const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t a_hi = sbase;
+            const uint32_t a_lo = sbase + p.a_tile_bytes;
+            const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
+            const uint32_t b_lo = b_hi + p.b_tile_bytes;
+            const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
+            const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
 #pragma unroll
-          for (int k = 0; k < SW_BYTES / 32; ++k) {
-            const uint32_t ka = k * (uint32_t)p.a_kstep, kbo = k * (uint32_t)p.b_kstep;
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            if (p.nparts == 2) {
-              umma_2sm<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
-              umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kbo, b_lbo), p.idesc, 1u);
-              umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, 1u);
-            } else {
-              umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
+            for (int k = 0; k < SW_BYTES / 32; ++k) {
+              const uint32_t ka = k * (uint32_t)p.a_kstep, kbo = k * (uint32_t)p.b_kstep;
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (p.nparts == 2) {
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kbo, b_lbo), p.idesc, 1u);
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, 1u);
+              } else {
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
+              }
             }
+            tcgen05_commit_2sm(&empty_bar[stage]);  // frees the stage in both CTAs
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit_2sm(&empty_bar[stage]);  // frees the stage in both CTAs
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          tcgen05_commit_2sm(&tmem_full_bar[as]);  // both CTAs' epilogues may fold the segment
         }
-        tcgen05_commit_2sm(&tmem_full_bar[as]);  // both CTAs' epilogues may read
       }
     }
   } else {
-    // ================= epilogue (warps 2..5 of both CTAs) =================
+    // ================= epilogue (warps 2..9 of both CTAs) =================
     const int q = warp & 3;
-    const bool vec_ok = (p.c_cs == 1) && ((p.c_rs & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                        (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
-                                            ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
-    uint32_t it = 0;
-    for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
-      const uint32_t as = it % (uint32_t)p.acc_stages;
-      const uint32_t aphase = (it / (uint32_t)p.acc_stages) & 1u;
+    const int half = (warp - 2) >> 2;
+    const int half_n = p.block_n >> 1;
+    const int nchunks = half_n >> 5;
+    const EpilogueOut eo(p);
+    float acc[kAccRegs];
+    uint32_t sit = 0;
+    for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters) {
       const long long m0 = (tile / tiles_n) * TILE_M + (long long)rank * BLOCK_M;
-      const long long n0 = (tile % tiles_n) * p.block_n;
-      mbar_wait(&tmem_full_bar[as], aphase);
-      tcgen05_fence_after();
-      const long long row = m0 + q * 32 + lane;
-      const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_acc + (uint32_t)c0, r);
-        if (c0 + 32 >= p.block_n) {
-          tcgen05_fence_before();
-          asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(
-                           smem_u32(&tmem_empty_bar[as]) & kPeerBitMask)
-                       : "memory");
-        }
-        if (row < p.M) {
-          const long long col0 = n0 + c0;
-          float* crow = p.C + row * p.c_rs;
-          const float* irow = p.Cin + row * p.cin_rs;
-          if (vec_ok && col0 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v;
-              v.x = p.alpha * __uint_as_float(r[j]);
-              v.y = p.alpha * __uint_as_float(r[j + 1]);
-              v.z = p.alpha * __uint_as_float(r[j + 2]);
-              v.w = p.alpha * __uint_as_float(r[j + 3]);
-              if (p.beta != 0.0f) {
-                const float4 o = *reinterpret_cast<const float4*>(irow + col0 + j);
-                v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
-              }
-              *reinterpret_cast<float4*>(crow + col0 + j) = v;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const long long col = col0 + j;
-              if (col < p.N) {
-                float v = p.alpha * __uint_as_float(r[j]);
-                if (p.beta != 0.0f) v += p.beta * irow[col * p.cin_cs];
-                crow[col * p.c_cs] = v;
-              }
-            }
-          }
-        }
+      const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
+      for (int kb0 = 0; kb0 < num_k_blocks; kb0 += p.seg_kblocks, ++sit) {
+        const uint32_t as = sit % (uint32_t)p.acc_stages;
+        const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tcgen05_fence_after();
+        const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
+                               ((uint32_t)(q * 32) << 16);
+        fold_segment(acc, t_acc, nchunks, kb0 == 0);
+        tcgen05_fence_before();
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(
+                         smem_u32(&tmem_empty_bar[as]) & kPeerBitMask)
+                     : "memory");
       }
+      eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
     }
   }
   tcgen05_fence_before();
@@ -752,6 +778,15 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   const int stage_bytes = parts * (p.a_tile_bytes + p.b_tile_bytes);
   p.stages = std::max(2, std::min(8, (kMaxSmem - 1024) / stage_bytes));
   p.acc_stages = 2;  // 2 x block_n <= 512 TMEM columns
+  {
+    // K segments (see "segments" above): 4 k-blocks = 128 K elements for the fp32-faithful
+    // mode; AB_GEMM_SEG_KB overrides (0 = never fold, the whole K loop stays in TMEM)
+    static const char* seg_env = getenv("AB_GEMM_SEG_KB");
+    const int num_kb = (int)((K + p.k_elems_per_row - 1) / p.k_elems_per_row);
+    int seg = precision == 0 ? 4 : num_kb;
+    if (seg_env) seg = atoi(seg_env) > 0 ? atoi(seg_env) : num_kb;
+    p.seg_kblocks = std::max(1, std::min(seg, std::max(1, num_kb)));
+  }
   // cute UMMA::InstrDescriptor: c_format F32=1 @[4,6), a/b format @[7,10)/[10,13)
   // (TF32=2, BF16=1), a_major @15, b_major @16 (1 = MN-major), N>>3 @[17,23), M>>4 @[24,29)
   const uint32_t fmt = bf16 ? 1u : 2u;

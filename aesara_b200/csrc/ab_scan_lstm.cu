@@ -17,6 +17,8 @@
 //     c_{t-1} are read once, c_t / h_t are written to the Scan's circular output buffers
 //     and h_t is ALSO written as the hi/lo TF32 planes the next step's TMA loads — the
 //     pre-activations never touch HBM and there is no per-step pack or copy kernel;
+//     K is accumulated in 128-element segments (fresh TMEM accumulator each, summed in
+//     FP32 registers) because the tensor core's own accumulate truncates;
 //   * steps are separated by a device-wide barrier (one atomic counter); rows are
 //     independent, so the barrier only orders "h_t written" before "h_t loaded by TMA"
 //     (release: __threadfence + atomicAdd; acquire: poll + fence.proxy.async).
@@ -39,6 +41,7 @@ using namespace ab::tc;
 constexpr int UNITS = 64;            // hidden units per tile
 constexpr int TILE_N = 4 * UNITS;    // 256 accumulator columns = 4 gates x 64 units
 constexpr int KB = 32;               // K elements (fp32/tf32) per 128-byte smem row
+constexpr int SEG_KB = 4;            // k-blocks per tensor-core accumulation segment (128 K)
 
 struct LstmParams {
   long long T, B, H;
@@ -56,6 +59,19 @@ struct LstmParams {
 };
 
 __device__ __forceinline__ float sigmoidf_ref(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// acc (+)= 32 accumulator columns of this thread's TMEM lane (round-to-nearest adds)
+__device__ __forceinline__ void fold32(float (&acc)[32], uint32_t taddr, bool first) {
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(taddr, r);
+  if (first) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_scan_kernel(const __grid_constant__ CUtensorMap map_h00, const __grid_constant__ CUtensorMap map_h01,
@@ -86,7 +102,7 @@ lstm_scan_kernel(const __grid_constant__ CUtensorMap map_h00, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], kThreads - 64);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -134,34 +150,43 @@ lstm_scan_kernel(const __grid_constant__ CUtensorMap map_h00, const __grid_const
     } else if (warp == 1) {
       // ================= MMA issuer =================
       if (lane == 0) {
-        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-          const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
-          mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-          tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + as * TILE_N;
-          for (int kb = 0; kb < num_k_blocks; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          // K segments: a fresh TMEM accumulator every SEG_KB k-blocks, folded into FP32
+          // registers by the epilogue (the tensor core's accumulate truncates; see
+          // ab_gemm_tcgen05.cu "segments")
+          for (int kb0 = 0; kb0 < num_k_blocks; kb0 += SEG_KB, ++it) {
+            const int kb1 = min(kb0 + SEG_KB, num_k_blocks);
+            const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+            mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
             tcgen05_fence_after();
-            const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t a_hi = sbase, a_lo = sbase + p.a_tile_bytes;
-            const uint32_t b_hi = sbase + 2 * p.a_tile_bytes, b_lo = b_hi + p.b_tile_bytes;
+            const uint32_t d_tmem = tmem_base + as * TILE_N;
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tcgen05_fence_after();
+              const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+              const uint32_t a_hi = sbase, a_lo = sbase + p.a_tile_bytes;
+              const uint32_t b_hi = sbase + 2 * p.a_tile_bytes, b_lo = b_hi + p.b_tile_bytes;
 #pragma unroll
-            for (int k = 0; k < SW_BYTES / 32; ++k) {
-              const uint32_t ko = k * 32;
-              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-              umma<0>(d_tmem, make_smem_desc(a_lo + ko, 16), make_smem_desc(b_hi + ko, 16), p.idesc, acc);
-              umma<0>(d_tmem, make_smem_desc(a_hi + ko, 16), make_smem_desc(b_lo + ko, 16), p.idesc, 1u);
-              umma<0>(d_tmem, make_smem_desc(a_hi + ko, 16), make_smem_desc(b_hi + ko, 16), p.idesc, 1u);
+              for (int k = 0; k < SW_BYTES / 32; ++k) {
+                const uint32_t ko = k * 32;
+                const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+                umma<0>(d_tmem, make_smem_desc(a_lo + ko, 16), make_smem_desc(b_hi + ko, 16), p.idesc, acc);
+                umma<0>(d_tmem, make_smem_desc(a_hi + ko, 16), make_smem_desc(b_lo + ko, 16), p.idesc, 1u);
+                umma<0>(d_tmem, make_smem_desc(a_hi + ko, 16), make_smem_desc(b_hi + ko, 16), p.idesc, 1u);
+              }
+              tcgen05_commit(&empty_bar[stage]);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            tcgen05_commit(&empty_bar[stage]);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            tcgen05_commit(&tmem_full_bar[as]);
           }
-          tcgen05_commit(&tmem_full_bar[as]);
         }
       }
     } else {
-      // ================= epilogue = the LSTM cell (warps 2..5) =================
+      // ================= epilogue = the LSTM cell (warps 2..9) =================
+      // two warps per TMEM lane quarter; warp group s owns hidden units [32 s, 32 s + 32)
+      // of the tile, i.e. 4 gates x 32 accumulator columns per thread
       const int q = warp & 3;
+      const int s = (warp - 2) >> 2;
       const long long rh = (p.pos_h + t) % p.sh;                   // ring rows written now
       const long long rc = (p.pos_c + t) % p.sc;
       const long long rc_prev = (p.pos_c + t - 1 + p.sc) % p.sc;   // c_{t-1}
@@ -171,60 +196,58 @@ lstm_scan_kernel(const __grid_constant__ CUtensorMap map_h00, const __grid_const
       float* hp_hi = p.hplane[set ^ 1][0];
       float* hp_lo = p.hplane[set ^ 1][1];
       const float* xt = p.x + t * p.x_ts;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long long m0 = (tile / tiles_n) * BLOCK_M;
         const long long u0 = (tile % tiles_n) * UNITS;
-        mbar_wait(&tmem_full_bar[as], aphase);
-        tcgen05_fence_after();
         const long long row = m0 + q * 32 + lane;
-        const uint32_t t_acc = tmem_base + as * TILE_N + ((uint32_t)(q * 32) << 16);
-        for (int s = 0; s < 2; ++s) {
-          uint32_t ri[32], rf[32], ro[32], rg[32];
-          tmem_ld_32x32b_x32(t_acc + 0 * UNITS + s * 32, ri);
-          tmem_ld_32x32b_x32(t_acc + 1 * UNITS + s * 32, rf);
-          tmem_ld_32x32b_x32(t_acc + 2 * UNITS + s * 32, ro);
-          tmem_ld_32x32b_x32(t_acc + 3 * UNITS + s * 32, rg);
-          if (s == 1) {
-            tcgen05_fence_before();
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
-                         : "memory");
-          }
-          if (row < p.B) {
-            const long long uc = u0 + s * 32;
-            const float* xr = xt + row * p.x_rs;
-            const long long so = row * p.H + uc;
+        float ai[32], af[32], ao[32], ag[32];
+        for (int kb0 = 0; kb0 < num_k_blocks; kb0 += SEG_KB, ++it) {
+          const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+          mbar_wait(&tmem_full_bar[as], aphase);
+          tcgen05_fence_after();
+          const uint32_t t_acc = tmem_base + as * TILE_N + ((uint32_t)(q * 32) << 16) + s * 32;
+          fold32(ai, t_acc + 0 * UNITS, kb0 == 0);
+          fold32(af, t_acc + 1 * UNITS, kb0 == 0);
+          fold32(ao, t_acc + 2 * UNITS, kb0 == 0);
+          fold32(ag, t_acc + 3 * UNITS, kb0 == 0);
+          tcgen05_fence_before();
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
+                       : "memory");
+        }
+        if (row < p.B) {
+          const long long uc = u0 + s * 32;
+          const float* xr = xt + row * p.x_rs;
+          const long long so = row * p.H + uc;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 xi = *reinterpret_cast<const float4*>(xr + 0 * p.H + uc + j);
-              const float4 xf = *reinterpret_cast<const float4*>(xr + 1 * p.H + uc + j);
-              const float4 xo = *reinterpret_cast<const float4*>(xr + 2 * p.H + uc + j);
-              const float4 xg = *reinterpret_cast<const float4*>(xr + 3 * p.H + uc + j);
-              const float4 cp = *reinterpret_cast<const float4*>(c_in + so + j);
-              float cn[4], hn[4], hh[4], hl[4];
-              const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
-              const float xov[4] = {xo.x, xo.y, xo.z, xo.w}, xgv[4] = {xg.x, xg.y, xg.z, xg.w};
-              const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+          for (int j = 0; j < 32; j += 4) {
+            const float4 xi = *reinterpret_cast<const float4*>(xr + 0 * p.H + uc + j);
+            const float4 xf = *reinterpret_cast<const float4*>(xr + 1 * p.H + uc + j);
+            const float4 xo = *reinterpret_cast<const float4*>(xr + 2 * p.H + uc + j);
+            const float4 xg = *reinterpret_cast<const float4*>(xr + 3 * p.H + uc + j);
+            const float4 cp = *reinterpret_cast<const float4*>(c_in + so + j);
+            float cn[4], hn[4], hh[4], hl[4];
+            const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
+            const float xov[4] = {xo.x, xo.y, xo.z, xo.w}, xgv[4] = {xg.x, xg.y, xg.z, xg.w};
+            const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                // Gemm: 1*acc + 1*x_t (blas.py:984-1017), then the two Elemwise composites
-                const float pi = __uint_as_float(ri[j + e]) + xiv[e];
-                const float pf = __uint_as_float(rf[j + e]) + xfv[e];
-                const float po = __uint_as_float(ro[j + e]) + xov[e];
-                const float pg = __uint_as_float(rg[j + e]) + xgv[e];
-                cn[e] = sigmoidf_ref(pf) * cpv[e] + sigmoidf_ref(pi) * tanhf(pg);
-                hn[e] = sigmoidf_ref(po) * tanhf(cn[e]);
-                uint32_t hb, lb;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(hn[e]));
-                hh[e] = __uint_as_float(hb);
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(hn[e] - hh[e]));
-                hl[e] = __uint_as_float(lb);
-              }
-              *reinterpret_cast<float4*>(c_out + so + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-              *reinterpret_cast<float4*>(h_out + so + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-              *reinterpret_cast<float4*>(hp_hi + so + j) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-              *reinterpret_cast<float4*>(hp_lo + so + j) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+            for (int e = 0; e < 4; ++e) {
+              // Gemm: 1*acc + 1*x_t (blas.py:984-1017), then the two Elemwise composites
+              const float pi = ai[j + e] + xiv[e];
+              const float pf = af[j + e] + xfv[e];
+              const float po = ao[j + e] + xov[e];
+              const float pg = ag[j + e] + xgv[e];
+              cn[e] = sigmoidf_ref(pf) * cpv[e] + sigmoidf_ref(pi) * tanhf(pg);
+              hn[e] = sigmoidf_ref(po) * tanhf(cn[e]);
+              uint32_t hb, lb;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(hn[e]));
+              hh[e] = __uint_as_float(hb);
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(hn[e] - hh[e]));
+              hl[e] = __uint_as_float(lb);
             }
+            *reinterpret_cast<float4*>(c_out + so + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            *reinterpret_cast<float4*>(h_out + so + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4*>(hp_hi + so + j) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<float4*>(hp_lo + so + j) = make_float4(hl[0], hl[1], hl[2], hl[3]);
           }
         }
       }

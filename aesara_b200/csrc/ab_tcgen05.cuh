@@ -10,7 +10,7 @@ namespace tc {
 
 constexpr int BLOCK_M = 128;
 constexpr int SW_BYTES = 128;  // swizzle span = smem row pitch of every operand tile
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kMaxSmem = 200 * 1024;
 
 // ----------------------------------------------------------------------------- PTX

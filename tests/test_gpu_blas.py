@@ -60,6 +60,25 @@ def test_gemm_fp32_faithful(K, m, n, k, layout):
     assert err < 1e-5, f"3xTF32 gemm normwise error {err}"
 
 
+@pytest.mark.parametrize("m,n,k", [(256, 256, 4096), (512, 256, 16384), (256, 512, 65536)])
+@pytest.mark.parametrize("layout", ["nn", "tn"])
+def test_gemm_long_k_accuracy(K, m, n, k, layout):
+    """fp32-faithful mode must stay as accurate as an fp32 sgemm however long K is.
+    The tensor core's FP32 accumulate truncates, so an unsegmented 3xTF32 product drifts
+    linearly with K (3.4e-5 at K = 4096 before the K loop was segmented); the bar here is
+    the error of NumPy's own float32 product against the float64 truth."""
+    rng = np.random.default_rng(k + m)
+    a = rng.standard_normal((m, k)).astype("float32")
+    b = rng.standard_normal((k, n)).astype("float32")
+    A = _dev(a) if layout == "nn" else _dev(np.ascontiguousarray(a.T)).dimshuffle([1, 0])
+    C = _dev(np.zeros((m, n), "float32"))
+    K.gemm(C, 1.0, A, _dev(b), 0.0, precision=0)
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    e_dev = _normwise(C.to_numpy(), want)
+    e_cpu = _normwise(a @ b, want)
+    assert e_dev <= max(4.0 * e_cpu, 2e-6), f"K={k}: device {e_dev:.3g} vs fp32 CPU {e_cpu:.3g}"
+
+
 @pytest.mark.parametrize("precision,tol", [(1, 2e-3), (2, 2e-2)])
 def test_gemm_reduced_precision_policies(K, precision, tol):
     """TF32 / BF16 compute policies: stated looser tolerances."""
