@@ -13,6 +13,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+PINNED_MIN_BYTES = 1 << 16  # device->host copies at least this big use page-locked memory
 _TORCH_BYTES = torch.uint8
 
 
@@ -79,6 +80,58 @@ class DeviceArray:
             hb = torch.from_numpy(src.reshape(-1).view(np.uint8))
             out.owner[: hb.numel()].copy_(hb, non_blocking=hb.is_pinned())
         return out
+
+    @staticmethod
+    def upload(a, copy_stream, consumer_stream):
+        """Host -> device for a function argument.  A page-locked source is copied on
+        ``copy_stream`` and the returned event marks its arrival (the consumer waits on it
+        at first use) together with the source buffer, which must stay alive until then;
+        a pageable source is copied synchronously (second result ``None``)."""
+        a = np.asarray(a)
+        src = a if a.flags.c_contiguous else np.array(a, order="C")
+        if not src.flags.writeable:
+            src = src.copy()
+        out = DeviceArray.empty(src.shape, src.dtype)
+        if not src.size:
+            return out, None
+        hb = torch.from_numpy(src.reshape(-1).view(np.uint8))
+        if not hb.is_pinned():
+            out.owner[: hb.numel()].copy_(hb)
+            return out, None
+        # the block may still be in use by earlier work of the consumer stream
+        copy_stream.wait_stream(consumer_stream)
+        with torch.cuda.stream(copy_stream):
+            out.owner[: hb.numel()].copy_(hb, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return out, (ev, hb)  # the caller keeps ``hb`` alive until the event has completed
+
+    @staticmethod
+    def download_all(values):
+        """``to_numpy`` for a list of outputs with one synchronisation."""
+        from .kernels import contiguous_copy
+
+        res, waits = [], False
+        for v in values:
+            if not isinstance(v, DeviceArray):
+                res.append(np.asarray(v))
+                continue
+            if v.nbytes < PINNED_MIN_BYTES:
+                res.append(v.to_numpy())
+                continue
+            src = v if v.is_c_contiguous() else contiguous_copy(v)
+            off = src.ptr - src.owner.data_ptr()
+            if src.owner.dtype == _TORCH_BYTES:
+                t = src.owner[off : off + src.nbytes]
+            else:
+                t = src.owner.contiguous().view(-1).view(_TORCH_BYTES)[off : off + src.nbytes]
+            host = torch.empty(src.nbytes, dtype=_TORCH_BYTES, pin_memory=True)
+            host.copy_(t, non_blocking=True)
+            waits = True
+            res.append(host.numpy().view(src.dtype).reshape(src.shape))
+        if waits:
+            torch.cuda.current_stream().synchronize()
+        return res
 
     @staticmethod
     def from_torch(t):
@@ -183,19 +236,28 @@ class DeviceArray:
 
     # -- host transfer ----------------------------------------------------------
     def to_numpy(self):
+        """Device -> host.  Large arrays land in a page-locked block from torch's caching
+        host allocator (~53 GB/s on the B200 box; a fresh pageable array page-faults at
+        ~2.6 GB/s, profiles/r01_pcie_probe.json) and the returned ndarray owns that block
+        through its base, so results are never recycled under the caller
+        (``Out(borrow=False)`` semantics, compile/function/types.py:1067-1117)."""
         from .kernels import contiguous_copy
 
         src = self if self.is_c_contiguous() else contiguous_copy(self)
-        out = np.empty(src.shape, dtype=src.dtype)
-        if src.size:
-            base_off = src.ptr - src.owner.data_ptr()
-            if isinstance(src.owner, torch.Tensor) and src.owner.dtype == _TORCH_BYTES:
-                t = src.owner[base_off : base_off + src.nbytes]
-            else:  # a wrapped typed torch tensor
-                t = src.owner.contiguous().view(-1).view(_TORCH_BYTES)[base_off : base_off + src.nbytes]
-            host = t.cpu().numpy()
-            out.reshape(-1).view(np.uint8)[:] = host
-        return out
+        if not src.size:
+            return np.empty(src.shape, dtype=src.dtype)
+        base_off = src.ptr - src.owner.data_ptr()
+        if isinstance(src.owner, torch.Tensor) and src.owner.dtype == _TORCH_BYTES:
+            t = src.owner[base_off : base_off + src.nbytes]
+        else:  # a wrapped typed torch tensor
+            t = src.owner.contiguous().view(-1).view(_TORCH_BYTES)[base_off : base_off + src.nbytes]
+        if src.nbytes >= PINNED_MIN_BYTES:
+            host = torch.empty(src.nbytes, dtype=_TORCH_BYTES, pin_memory=True)
+            host.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+        else:
+            host = t.cpu()
+        return host.numpy().view(src.dtype).reshape(src.shape)
 
     def __array__(self, dtype=None, copy=None):
         a = self.to_numpy()

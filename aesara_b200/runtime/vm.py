@@ -84,6 +84,12 @@ class ProgramExecutor:
             if v not in keep and v not in self._const_host:
                 self._free_after[i].append(v)
         self.node_events = None
+        self._first_use = {}
+        for i, n in enumerate(program.nodes):
+            for v in n.inputs:
+                self._first_use.setdefault(v, i)
+        self._copy_streams = {}
+        self._inflight = []
         self.pack_cache = K.PackCache()
         # input positions each node rewrites in place (destroy_map): their cached GEMM
         # packs must be dropped after the node ran
@@ -159,6 +165,10 @@ class ProgramExecutor:
             raise TypeError(f"expected {len(prog.inputs)} inputs, got {len(inputs)}")
         env = dict(self._const_host)
         self.pack_cache.clear()
+        # host tensors are uploaded on a copy stream in order of first use, so that a
+        # page-locked argument's transfer overlaps the nodes that do not need it yet
+        pending = {}
+        uploads = []
         for vid, val in zip(prog.inputs, inputs):
             var = prog.vars[vid]
             if isinstance(val, DeviceArray):
@@ -179,14 +189,31 @@ class ProgramExecutor:
                         f"{var.ndim}, got {val.ndim} with shape {val.shape}"
                     )
                 if val.size > host_eval.MAX_HOST_ELEMS:
-                    val = DeviceArray.from_numpy(val)
+                    uploads.append((self._first_use.get(vid, 0), vid, val))
+                    continue
             elif var.kind == "scalar":
                 val = np.dtype(var.dtype).type(val)
             env[vid] = val
+        if uploads:
+            uploads.sort(key=lambda u: u[0])
+            cur = torch.cuda.current_stream()
+            for ev, _ in self._inflight:  # sources of the previous call's uploads
+                ev.synchronize()
+            self._inflight = []
+            for _, vid, val in uploads:
+                env[vid], tok = DeviceArray.upload(val, self._copy_stream_for(cur), cur)
+                if tok is not None:
+                    pending[vid] = tok[0]
+                    self._inflight.append(tok)
         events = [] if self.time_nodes else None
         nodes = prog.nodes
         for i, step in enumerate(self._steps):
             node = nodes[i]
+            if pending:
+                for v in node.inputs:
+                    ev = pending.pop(v, None)
+                    if ev is not None:
+                        torch.cuda.current_stream().wait_event(ev)
             if events is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
@@ -214,10 +241,18 @@ class ProgramExecutor:
                 env.pop(v, None)
         self.node_events = events
         self.pack_cache.clear()
+        for ev in pending.values():  # inputs no node consumed (returned as they are)
+            torch.cuda.current_stream().wait_event(ev)
         outs = [env[v] for v in prog.outputs]
         if self.host_outputs:
-            outs = [o.to_numpy() if isinstance(o, DeviceArray) else np.asarray(o) for o in outs]
+            outs = DeviceArray.download_all(outs)
         return outs
+
+    def _copy_stream_for(self, cur):
+        st = self._copy_streams.get(cur.device)
+        if st is None:
+            st = self._copy_streams[cur.device] = torch.cuda.Stream(device=cur.device)
+        return st
 
     def node_times_ms(self):
         """Per-node device time of the last call (needs ``time_nodes=True``)."""
