@@ -355,6 +355,13 @@ def _l_alloc(op, apply):
     return "Alloc", {}
 
 
+@lowers("BroadcastTo")
+def _l_broadcast_to(op, apply):
+    # tensor/extra_ops.py:1613 BroadcastTo: a (read-only) broadcast VIEW of input 0
+    # (view_map {0: [0]}) -- stride-0 dims on device
+    return "BroadcastTo", {}
+
+
 @lowers("DeepCopyOp")
 def _l_deepcopy(op, apply):
     return "DeepCopy", {}

@@ -194,6 +194,22 @@ class DeviceArray:
         strides = [0 if o == "x" else self.strides[o] for o in new_order]
         return self.view(shape, strides)
 
+    def broadcast_to(self, shape):
+        """NumPy ``broadcast_to`` as a stride-0 view (tensor/extra_ops.py:1613)."""
+        shape = tuple(int(s) for s in shape)
+        if len(shape) < self.ndim:
+            raise ValueError("broadcast_to: input has more dimensions than the requested shape")
+        lead = len(shape) - self.ndim
+        strides = [0] * lead
+        for n, s, want in zip(self.shape, self.strides, shape[lead:]):
+            if n == want:
+                strides.append(s)
+            elif n == 1:
+                strides.append(0)
+            else:
+                raise ValueError(f"broadcast_to: cannot broadcast {self.shape} to {shape}")
+        return self.view(shape, strides)
+
     def index(self, idx):
         """Basic NumPy indexing (ints and slices) -> view."""
         idx = tuple(idx) + (slice(None),) * (self.ndim - len(idx))

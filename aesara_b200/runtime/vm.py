@@ -562,6 +562,20 @@ def _alloc(ex, i, node, args):
     return out
 
 
+@_op("BroadcastTo")
+def _broadcast_to(ex, i, node, args):
+    v, *shape = args
+    shape = [_int(s) for s in shape]
+    vid = node.inputs[0]
+    var = ex.program.vars[node.outputs[0]]
+    n = int(np.prod(shape)) if shape else 1
+    if is_host(v) and n <= host_eval.MAX_HOST_ELEMS:
+        return np.broadcast_to(np.asarray(v, dtype=var.dtype), shape)
+    src = v if isinstance(v, DeviceArray) else (
+        ex.const_dev(vid) if vid in ex._const_host else ex.dev(v, key=(i, 0), dtype=var.dtype))
+    return src.broadcast_to(shape)
+
+
 @_op("DeepCopy")
 def _deepcopy(ex, i, node, args):
     (x,) = args

@@ -267,6 +267,12 @@ def _alloc(node, args, prog):  # aesara/tensor/basic.py:1389 (perform :1468)
     return np.array(np.broadcast_to(v, shape))
 
 
+@_h("BroadcastTo")
+def _broadcast_to(node, args, prog):  # aesara/tensor/extra_ops.py:1613 (perform :1652)
+    v, *shape = args
+    return np.broadcast_to(v, tuple(int(s) for s in shape))
+
+
 @_h("DeepCopy")
 def _deepcopy(node, args, prog):  # aesara/compile/ops.py:149
     return np.array(args[0], copy=True)

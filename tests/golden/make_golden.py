@@ -294,6 +294,67 @@ def _():
     return [x, init], [f, g], [rnd(9), rnd(2)]
 
 
+# Scan gradients / while loops (§8f N2): reversed Scan with mit-mot accumulators
+# (scan/op.py:2379-3129), nit-sot outputs, `until` conditions
+@case("scan_grad_rnn")
+def _():
+    x = at.fmatrix("x")           # [T, n]
+    h0 = at.fvector("h0")
+    W = at.fmatrix("W")           # [n, n]
+
+    def step(x_t, h_tm1, W_):
+        return at.tanh(at.dot(h_tm1, W_) + x_t)
+
+    hs, _ = aesara.scan(step, sequences=[x], outputs_info=[h0], non_sequences=[W])
+    loss = (hs ** 2).sum() + hs[-1].sum()
+    gW, gx, gh0 = aesara.grad(loss, [W, x, h0])
+    return [x, h0, W], [loss, gW, gx, gh0], [rnd((6, 12), "float32", -1, 1), rnd(12, "float32", -1, 1),
+                                              rnd((12, 12), "float32", -0.4, 0.4)]
+
+
+@case("scan_grad_lstm")
+def _():
+    i, o = G.cfg4_lstm_scan()
+    x, h0, c0, U = i
+    loss = (o[0] ** 2).sum() + o[1].sum()
+    gU, gx = aesara.grad(loss, [U, x])
+    T, B, H = 5, 6, 8
+    r = np.random.default_rng(11)
+    vals = [r.standard_normal((T, B, 4 * H)).astype("float32"),
+            (r.standard_normal((B, H)) * 0.1).astype("float32"),
+            (r.standard_normal((B, H)) * 0.1).astype("float32"),
+            (r.standard_normal((H, 4 * H)) / np.sqrt(H)).astype("float32")]
+    return i, [loss, gU, gx], vals
+
+
+@case("scan_while_until")
+def _():
+    from aesara.scan.utils import until
+
+    x0 = at.fvector("x0")
+    limit = at.fscalar("limit")
+
+    def step(v, lim):
+        nv = v * 1.5 + 1.0
+        return nv, until(nv.sum() > lim)
+
+    vs, _ = aesara.scan(step, outputs_info=[x0], non_sequences=[limit], n_steps=40)
+    return [x0, limit], [vs, vs[-1], vs.shape[0]], [rnd(5, "float32", 0, 1), np.float32(300.0)]
+
+
+@case("scan_seq_taps_shared_nsteps")
+def _():
+    x = at.fvector("x")
+    k = at.lscalar("k")
+
+    def step(x_tm1, x_t, x_tp1, acc):
+        return acc + x_tm1 * x_tp1 - x_t
+
+    out, _ = aesara.scan(step, sequences=[dict(input=x, taps=[-1, 0, 1])], outputs_info=[at.zeros((), "float32")],
+                         n_steps=k)
+    return [x, k], [out, out[-1] * 2], [rnd(11), np.int64(7)]
+
+
 # ---------------------------------------------------------------- Softmax family (§8f N1)
 @case("softmax_classifier")
 def _():
