@@ -52,6 +52,9 @@ struct GemmParams {
   int acc_stages;         // TMEM accumulator stages (2 -> epilogue overlaps the next segment)
   int seg_kblocks;        // k-blocks accumulated inside the tensor core before the epilogue
                           // folds the partial sum into its FP32 registers (see "segments")
+  int k_splits;           // split-K: work unit = (tile, K range); unit u -> tile u / k_splits
+  int kb_per_split;       // k-blocks per K range
+  float* partial;         // [k_splits - 1][M][N] alpha * (A@B over K range s), s >= 1
   int stages;
   int nparts;             // 1, or 2 for the hi/lo split (3 MMAs per k-step)
   int k_elems_per_row;    // K elements per stage = per 128-byte K-major row: 32 (tf32) / 64 (bf16)
@@ -116,6 +119,30 @@ struct EpilogueOut {
              (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
                                  ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
   }
+  // split-K: alpha * acc of K range `split` (>= 1) into its [M, N] scratch plane
+  __device__ __forceinline__ void store_partial(const float (&acc)[kAccRegs], long long row,
+                                                long long n0, int nchunks, int split) const {
+    if (row >= p.M) return;
+    float* prow = p.partial + ((long long)(split - 1) * p.M + row) * p.N;
+    const bool vec = (p.N & 3) == 0;
+#pragma unroll
+    for (int c = 0; c < kAccRegs / 32; ++c) {
+      if (c < nchunks) {
+        const long long col0 = n0 + c * 32;
+        if (vec && col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(prow + col0 + j) =
+                make_float4(p.alpha * acc[c * 32 + j], p.alpha * acc[c * 32 + j + 1],
+                            p.alpha * acc[c * 32 + j + 2], p.alpha * acc[c * 32 + j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) prow[col0 + j] = p.alpha * acc[c * 32 + j];
+        }
+      }
+    }
+  }
   __device__ __forceinline__ void store(const float (&acc)[kAccRegs], long long row, long long n0,
                                         int nchunks) const {
     if (row >= p.M) return;
@@ -155,6 +182,14 @@ struct EpilogueOut {
   }
 };
 
+// work unit -> (tile, K range); consecutive units of a tile go to different CTAs
+#define AB_UNIT_DECODE                                                          \
+  const long long tile = unit / p.k_splits;                                     \
+  const int split = (int)(unit - tile * p.k_splits);                            \
+  const int kb_begin = split * p.kb_per_split;                                  \
+  const int kb_end = min(kb_begin + p.kb_per_split, num_k_blocks);              \
+  (void)split;
+
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
@@ -180,6 +215,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
   // consecutive so the CTAs resident at one time share A row panels and all of B in L2
   const long long tiles_n = (p.N + p.block_n - 1) / p.block_n;
   const long long num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * tiles_n;
+  const long long num_units = num_tiles * p.k_splits;
   const uint32_t tmem_cols = (uint32_t)(p.acc_stages * p.block_n);
 
   if (threadIdx.x == 0) {
@@ -214,10 +250,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b0)) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        AB_UNIT_DECODE
         const int m0 = (int)((tile / tiles_n) * BLOCK_M);
         const int n0 = (int)((tile % tiles_n) * p.block_n);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sbase = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
@@ -240,9 +277,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
       int stage = 0;
       uint32_t phase = 0;
       uint32_t sit = 0;  // accumulator segments issued by this CTA
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int kb0 = 0; kb0 < num_k_blocks; kb0 += p.seg_kblocks, ++sit) {
-          const int kb1 = min(kb0 + p.seg_kblocks, num_k_blocks);
+      for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        AB_UNIT_DECODE
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
+          const int kb1 = min(kb0 + p.seg_kblocks, kb_end);
           const uint32_t as = sit % (uint32_t)p.acc_stages;
           const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
           // wait until the epilogue has drained this accumulator stage
@@ -290,23 +328,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
     const EpilogueOut eo(p);
     float acc[kAccRegs];
     uint32_t sit = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        AB_UNIT_DECODE
       const long long m0 = (tile / tiles_n) * BLOCK_M;
       const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
-      for (int kb0 = 0; kb0 < num_k_blocks; kb0 += p.seg_kblocks, ++sit) {
+      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
         const uint32_t as = sit % (uint32_t)p.acc_stages;
         const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
         mbar_wait(&tmem_full_bar[as], aphase);
         tcgen05_fence_after();
         const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
                                ((uint32_t)(q * 32) << 16);
-        fold_segment(acc, t_acc, nchunks, kb0 == 0);
+        fold_segment(acc, t_acc, nchunks, kb0 == kb_begin);
         // the segment is in registers: hand the accumulator stage back to the MMA warp
         tcgen05_fence_before();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
                      : "memory");
       }
-      eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
+      if (split == 0) eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
+      else eo.store_partial(acc, m0 + q * 32 + lane, n0, nchunks, split);
     }
   }
   tcgen05_fence_before();
@@ -369,6 +409,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
   constexpr int TILE_M = 2 * BLOCK_M;
   const long long tiles_n = (p.N + p.block_n - 1) / p.block_n;
   const long long num_tiles = ((p.M + TILE_M - 1) / TILE_M) * tiles_n;
+  const long long num_units = num_tiles * p.k_splits;
   const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const uint32_t tmem_cols = (uint32_t)(p.acc_stages * p.block_n);
 
@@ -402,10 +443,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
+        AB_UNIT_DECODE
         const int m0 = (int)((tile / tiles_n) * TILE_M) + (int)rank * BLOCK_M;
         const int n0 = (int)((tile % tiles_n) * p.block_n) + (int)rank * (p.block_n / 2);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sbase = smem + (size_t)stage * stage_bytes;
           if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
@@ -429,9 +471,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
       int stage = 0;
       uint32_t phase = 0;
       uint32_t sit = 0;
-      for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters) {
-        for (int kb0 = 0; kb0 < num_k_blocks; kb0 += p.seg_kblocks, ++sit) {
-          const int kb1 = min(kb0 + p.seg_kblocks, num_k_blocks);
+      for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
+        AB_UNIT_DECODE
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
+          const int kb1 = min(kb0 + p.seg_kblocks, kb_end);
           const uint32_t as = sit % (uint32_t)p.acc_stages;
           const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
           mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
@@ -475,23 +518,25 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
     const EpilogueOut eo(p);
     float acc[kAccRegs];
     uint32_t sit = 0;
-    for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+    for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
+        AB_UNIT_DECODE
       const long long m0 = (tile / tiles_n) * TILE_M + (long long)rank * BLOCK_M;
       const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
-      for (int kb0 = 0; kb0 < num_k_blocks; kb0 += p.seg_kblocks, ++sit) {
+      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
         const uint32_t as = sit % (uint32_t)p.acc_stages;
         const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
         mbar_wait(&tmem_full_bar[as], aphase);
         tcgen05_fence_after();
         const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
                                ((uint32_t)(q * 32) << 16);
-        fold_segment(acc, t_acc, nchunks, kb0 == 0);
+        fold_segment(acc, t_acc, nchunks, kb0 == kb_begin);
         tcgen05_fence_before();
         asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(
                          smem_u32(&tmem_empty_bar[as]) & kPeerBitMask)
                      : "memory");
       }
-      eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
+      if (split == 0) eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
+      else eo.store_partial(acc, m0 + q * 32 + lane, n0, nchunks, split);
     }
   }
   tcgen05_fence_before();
@@ -508,6 +553,53 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
 // ------------------------------------------------------------------ operand packing
 // out planes are [R, pitch] row-major (K-major): out[r*pitch + c] = f(in[r*s_r + c*s_c]).
 // MODE 0: hi/lo tf32 split (two f32 planes), 1: f32 copy, 2: bf16.
+// Fast path of the operand pack: the source is contiguous along the plane's column index
+// (s_c == 1) with 16-byte aligned rows.  Each thread converts 8 consecutive elements
+// (two 128-bit loads -> one 128-bit bf16 store, or 128-bit stores to the hi/lo planes);
+// a pure streaming kernel instead of the 32 x 32 shared-memory transpose below, which ran
+// at half of the HBM bandwidth (489 us per GiB, profiles/r01_launches_mlp_bf16_v2.csv).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ in, long long R, long long Kc, long long s_r,
+                 void* __restrict__ out0, void* __restrict__ out1, long long pitch) {
+  const long long groups = Kc >> 3;  // groups of 8 columns per row (Kc % 8 == 0)
+  const long long total = R * groups;
+  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < total;
+       g += (long long)gridDim.x * 256) {
+    const long long r = g / groups, c = (g - r * groups) << 3;
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(in + r * s_r + c));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(in + r * s_r + c + 4));
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (MODE == 2) {
+      __nv_bfloat162 q[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out0) + r * pitch + c) =
+          *reinterpret_cast<const uint4*>(q);
+    } else if (MODE == 1) {
+      float* o = static_cast<float*>(out0) + r * pitch + c;
+      *reinterpret_cast<float4*>(o) = a;
+      *reinterpret_cast<float4*>(o + 4) = b;
+    } else {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t hb, lb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j]));
+        hi[j] = __uint_as_float(hb);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v[j] - hi[j]));
+        lo[j] = __uint_as_float(lb);
+      }
+      float* oh = static_cast<float*>(out0) + r * pitch + c;
+      float* ol = static_cast<float*>(out1) + r * pitch + c;
+      *reinterpret_cast<float4*>(oh) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(oh + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+      *reinterpret_cast<float4*>(ol) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<float4*>(ol + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 pack_kernel(const float* __restrict__ in, long long R, long long Kc, long long s_r, long long s_c,
@@ -676,6 +768,19 @@ int gemm_pack(int precision, const float* src, long long rows, long long k, long
   // plane rows/cols: K-major plane is [rows, k]; MN-major plane is [k, rows]
   const long long R = mn ? k : rows, Cc = mn ? rows : k;
   const long long sr = mn ? s_k : s_r, sc = mn ? s_r : s_k;
+  if (sc == 1 && Cc % 8 == 0 && sr % 4 == 0 && pitch % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const long long total = R * (Cc / 8);
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+    if (precision == 0) pack_rows_kernel<0><<<blocks, 256, 0, st>>>(src, R, Cc, sr, o0, o1, pitch);
+    else if (precision == 1) pack_rows_kernel<1><<<blocks, 256, 0, st>>>(src, R, Cc, sr, o0, o1, pitch);
+    else pack_rows_kernel<2><<<blocks, 256, 0, st>>>(src, R, Cc, sr, o0, o1, pitch);
+    g_launches++;
+    AB_CUDA(cudaGetLastError());
+    out->plane[0] = o0;
+    out->plane[1] = o1;
+    return AB_OK;
+  }
   dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((R + 31) / 32));
   if (grid.y > 65535) {
     // tall planes: fold the row-tile index into x instead (both are limited to 2^31-1 / 65535)
@@ -693,10 +798,90 @@ int gemm_pack(int precision, const float* src, long long rows, long long k, long
 
 bool gemm_tcgen05_eligible(long long M, long long N, long long K) { return eligible(M, N, K); }
 
+// ------------------------------------------------------------------------ split-K
+// The persistent grid has one CTA (pair) per SM (pair); a problem whose tile count is a
+// little above a multiple of that leaves most of the last wave idle (the cfg3 weight
+// gradients: 4096 x 4096 x 65536 = 256 tiles on 74 pairs = 3.46 waves -> 4).  When K is
+// long the K loop is cut into k_splits ranges, so the unit count fills the waves; range 0
+// writes C, ranges >= 1 write alpha * partial planes that splitk_reduce_kernel adds to C.
+bool use_two_cta(long long M, long long N) {
+  static const bool allow_2cta = getenv("AB_GEMM_1CTA") == nullptr;
+  return allow_2cta && M >= 256 && N >= 256 && (sm_count() % 2 == 0);
+}
+
+int plan_k_splits(int precision, long long M, long long N, long long K) {
+  static const char* env = getenv("AB_GEMM_SPLITK");  // 0/1 = off, n = force n ranges
+  const bool two = use_two_cta(M, N);
+  const long long block_n = two ? 256 : (N >= 256 ? 256 : (N >= 128 ? 128 : 64));
+  const long long tile_m = two ? 2 * BLOCK_M : BLOCK_M;
+  const long long tiles = ((M + tile_m - 1) / tile_m) * ((N + block_n - 1) / block_n);
+  const long long groups = two ? sm_count() / 2 : sm_count();
+  const long long k_elems = SW_BYTES / (precision == 2 ? 2 : 4);
+  const long long num_kb = (K + k_elems - 1) / k_elems;
+  if (env) {
+    const int f = atoi(env);
+    return (int)std::max<long long>(1, std::min<long long>(f, num_kb));
+  }
+  if (num_kb < 128 || (double)M * (double)N > 64.0 * 1024 * 1024) return 1;
+  auto eff = [&](long long s) {
+    const long long units = tiles * s;
+    return (double)units / (double)(((units + groups - 1) / groups) * groups);
+  };
+  int best = 1;
+  double best_score = eff(1);
+  for (int s = 2; s <= 4; ++s) {
+    if (num_kb / s < 64) break;
+    const double score = eff(s) * (1.0 - 0.01 * (s - 1));  // the partial planes are not free
+    if (score > best_score * 1.05) { best = s; best_score = score; }
+  }
+  return best;
+}
+
+size_t gemm_splitk_bytes(int precision, long long M, long long N, long long K) {
+  const int s = plan_k_splits(precision, M, N, K);
+  return s > 1 ? (size_t)(s - 1) * (size_t)M * (size_t)N * sizeof(float) + 256 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(float* __restrict__ C, long long c_rs, long long c_cs,
+                     const float* __restrict__ partial, long long M, long long N, int planes) {
+  const bool vec = c_cs == 1 && (N & 3) == 0 && (c_rs & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+  if (vec) {
+    const long long n4 = N >> 2, total = M * n4;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+      const long long r = i / n4, c = (i - r * n4) << 2;
+      float4 v = *reinterpret_cast<const float4*>(C + r * c_rs + c);
+      for (int s = 0; s < planes; ++s) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(partial + ((long long)s * M + r) * N + c));
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+      }
+      *reinterpret_cast<float4*>(C + r * c_rs + c) = v;
+    }
+  } else {
+    const long long total = M * N;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+      const long long r = i / N, c = i - r * N;
+      float v = C[r * c_rs + c * c_cs];
+      for (int s = 0; s < planes; ++s) v += partial[((long long)s * M + r) * N + c];
+      C[r * c_rs + c * c_cs] = v;
+    }
+  }
+}
+
+int splitk_finish(const GemmParams& p, cudaStream_t st) {
+  if (p.k_splits <= 1) return AB_OK;
+  const long long work = (p.M * p.N + 3) / 4;
+  const unsigned blocks = (unsigned)std::min<long long>((work + 255) / 256, (long long)sm_count() * 16);
+  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p.C, p.c_rs, p.c_cs, p.partial, p.M, p.N, p.k_splits - 1);
+  g_launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB_OK;
+}
+
 int gemm_run(int precision, long long M, long long N, long long K, float alpha,
              const PackedOperand& A, const PackedOperand& B, float beta, float* C, long long c_rs,
              long long c_cs, cudaStream_t st, const float* Cin = nullptr, long long cin_rs = 0,
-             long long cin_cs = 0) {
+             long long cin_cs = 0, void* splitk_ws = nullptr, size_t splitk_bytes = 0) {
   if (precision < 0 || precision > 2) return fail(AB_ERR_INVALID, "bad gemm precision %d", precision);
   if (A.precision != precision || B.precision != precision || A.rows != M || B.rows != N ||
       A.k != K || B.k != K)
@@ -723,8 +908,7 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   p.a_kstep = A.mn_major ? umma_k * SW_BYTES : 32;
   p.b_kstep = B.mn_major ? umma_k * SW_BYTES : 32;
   // 2-CTA mode (cta_group::2, 256 x 256 tile per CTA pair) for large problems
-  static const bool allow_2cta = getenv("AB_GEMM_1CTA") == nullptr;
-  const bool two_cta = allow_2cta && M >= 256 && N >= 256 && (sm_count() % 2 == 0);
+  const bool two_cta = use_two_cta(M, N);
   if (two_cta) {
     p.block_n = 256;
     p.b_tile_bytes = (p.block_n / 2) * SW_BYTES;  // this CTA's half of the B tile
@@ -739,9 +923,21 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     // mode; AB_GEMM_SEG_KB overrides (0 = never fold, the whole K loop stays in TMEM)
     static const char* seg_env = getenv("AB_GEMM_SEG_KB");
     const int num_kb = (int)((K + p.k_elems_per_row - 1) / p.k_elems_per_row);
-    int seg = precision == 0 ? 4 : num_kb;
-    if (seg_env) seg = atoi(seg_env) > 0 ? atoi(seg_env) : num_kb;
-    p.seg_kblocks = std::max(1, std::min(seg, std::max(1, num_kb)));
+    // split-K only with a scratch buffer from the caller (else one K range: still correct)
+    p.k_splits = 1;
+    const int want = plan_k_splits(precision, M, N, K);
+    if (want > 1 && splitk_ws && splitk_bytes >= (size_t)(want - 1) * (size_t)M * (size_t)N * sizeof(float) + 256)
+      p.k_splits = want;
+    p.kb_per_split = (num_kb + p.k_splits - 1) / p.k_splits;
+    int seg = precision == 0 ? 4 : p.kb_per_split;
+    if (seg_env) seg = atoi(seg_env) > 0 ? atoi(seg_env) : p.kb_per_split;
+    p.seg_kblocks = std::max(1, std::min(seg, std::max(1, p.kb_per_split)));
+    if (p.k_splits > 1) {
+      // whole segments per range, and no empty range
+      p.kb_per_split = (p.kb_per_split + p.seg_kblocks - 1) / p.seg_kblocks * p.seg_kblocks;
+      p.k_splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    }
+    p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(splitk_ws) + 255) & ~(uintptr_t)255);
   }
   // cute UMMA::InstrDescriptor: c_format F32=1 @[4,6), a/b format @[7,10)/[10,13)
   // (TF32=2, BF16=1), a_major @15, b_major @16 (1 = MN-major), N>>3 @[17,23), M>>4 @[24,29)
@@ -763,7 +959,7 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   if (parts == 1) { ma[1] = ma[0]; mb[1] = mb[0]; }
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   if (two_cta) {
-    const long long tiles2 = ((N + p.block_n - 1) / p.block_n) * ((M + tile_m - 1) / tile_m);
+    const long long tiles2 = ((N + p.block_n - 1) / p.block_n) * ((M + tile_m - 1) / tile_m) * p.k_splits;
     const long long clusters = std::min<long long>(tiles2, sm_count() / 2);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * clusters));
@@ -793,9 +989,9 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
       AB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<0>, ma[0], ma[1], mb[0], mb[1], p));
     }
     g_launches++;
-    return AB_OK;
+    return splitk_finish(p, st);
   }
-  const long long num_tiles = ((N + p.block_n - 1) / p.block_n) * ((M + BLOCK_M - 1) / BLOCK_M);
+  const long long num_tiles = ((N + p.block_n - 1) / p.block_n) * ((M + BLOCK_M - 1) / BLOCK_M) * p.k_splits;
   dim3 grid((unsigned)std::min<long long>(num_tiles, sm_count()));  // persistent: one CTA per SM
   if (bf16) {
     static bool attr1 = false;
@@ -814,7 +1010,7 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   }
   g_launches++;
   AB_CUDA(cudaGetLastError());
-  return AB_OK;
+  return splitk_finish(p, st);
 }
 
 size_t gemm_tcgen05_workspace(int precision, long long M, long long N, long long K, long long a_rs,
@@ -869,7 +1065,8 @@ extern "C" int ab_gemm_pack(int precision, const void* src, int64_t rows, int64_
 extern "C" int ab_gemm_packed(int precision, int64_t m, int64_t n, int64_t k, double alpha,
                               const ab_gemm_operand* A, const ab_gemm_operand* B, double beta,
                               const void* Cin, int64_t cin_rs, int64_t cin_cs, void* C,
-                              int64_t c_rs, int64_t c_cs, void* stream) {
+                              int64_t c_rs, int64_t c_cs, void* workspace, size_t workspace_bytes,
+                              void* stream) {
   if (!A || !B) return ab::fail(AB_ERR_INVALID, "null packed operand");
   if (!ab::gemm_tcgen05_eligible(m, n, k))
     return ab::fail(AB_ERR_UNSUPPORTED, "problem too small for the tensor-core path; use ab_gemm");
@@ -877,7 +1074,14 @@ extern "C" int ab_gemm_packed(int precision, int64_t m, int64_t n, int64_t k, do
   ab::PackedOperand pb{{B->plane0, B->plane1}, B->rows, B->k, B->pitch, B->mn_major, B->precision};
   return ab::gemm_run(precision, m, n, k, (float)alpha, pa, pb, (float)beta, static_cast<float*>(C),
                       c_rs, c_cs, ab::as_stream(stream), static_cast<const float*>(Cin), cin_rs,
-                      cin_cs);
+                      cin_cs, workspace, workspace_bytes);
+}
+
+extern "C" int ab_gemm_packed_workspace_bytes(int precision, int64_t m, int64_t n, int64_t k,
+                                              size_t* bytes) {
+  if (!bytes) return ab::fail(AB_ERR_INVALID, "null out pointer");
+  *bytes = ab::gemm_tcgen05_eligible(m, n, k) ? ab::gemm_splitk_bytes(precision, m, n, k) : 0;
+  return AB_OK;
 }
 
 extern "C" int ab_gemm_tensorcore_eligible(int64_t m, int64_t n, int64_t k) {

@@ -312,8 +312,12 @@ def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision
         opa = cache.operand(A, m, k, A.strides[0], A.strides[1], precision)
         opb = cache.operand(B, n, k, B.strides[1], B.strides[0], precision)
         cin_args = (None, 0, 0) if cin is None else (cin.ptr, cin.strides[0], cin.strides[1])
+        need = C.c_size_t()
+        _lib.check(lib.ab_gemm_packed_workspace_bytes(precision, m, n, k, C.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=A.owner.device) if need.value else None
         _lib.check(lib.ab_gemm_packed(precision, m, n, k, float(alpha), C.byref(opa), C.byref(opb),
                                       float(beta), *cin_args, C_.ptr, C_.strides[0], C_.strides[1],
+                                      ws.data_ptr() if ws is not None else None, need.value,
                                       stream_handle()))
         return
     if cin is not None:

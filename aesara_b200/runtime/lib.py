@@ -112,7 +112,11 @@ SIGNATURES = {
     "ab_gemm_packed": (
         C.c_int,
         [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_double,
-         C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p],
+         C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t,
+         C.c_void_p],
+    ),
+    "ab_gemm_packed_workspace_bytes": (
+        C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]
     ),
     "ab_gemm_tensorcore_eligible": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "ab_softmax": (

@@ -162,11 +162,15 @@ int ab_gemm_pack_bytes(int precision, int64_t rows, int64_t k, int64_t s_r, int6
 int ab_gemm_pack(int precision, const void* src, int64_t rows, int64_t k, int64_t s_r,
                  int64_t s_k, void* dst, size_t dst_bytes, ab_gemm_operand* out, void* stream);
 /* C <- beta*Cin + alpha*A@B.  Cin == NULL means in place (Cin = C); a separate Cin is
- * the Gemm{no_inplace} case (blas.py:1065-1093) without the copy of z. */
+ * the Gemm{no_inplace} case (blas.py:1065-1093) without the copy of z.  `workspace` is
+ * optional scratch for split-K (ab_gemm_packed_workspace_bytes; 0 bytes = not wanted):
+ * problems with few output tiles and a long K are cut along K so that every SM has work,
+ * and the partial products are summed into C by a second kernel. */
 int ab_gemm_packed(int precision, int64_t m, int64_t n, int64_t k, double alpha,
                    const ab_gemm_operand* A, const ab_gemm_operand* B, double beta,
                    const void* Cin, int64_t cin_rs, int64_t cin_cs, void* C, int64_t c_rs,
-                   int64_t c_cs, void* stream);
+                   int64_t c_cs, void* workspace, size_t workspace_bytes, void* stream);
+int ab_gemm_packed_workspace_bytes(int precision, int64_t m, int64_t n, int64_t k, size_t* bytes);
 int ab_gemm_tensorcore_eligible(int64_t m, int64_t n, int64_t k);
 
 /* ---- row ops ---------------------------------------------------

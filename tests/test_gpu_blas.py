@@ -79,6 +79,30 @@ def test_gemm_long_k_accuracy(K, m, n, k, layout):
     assert e_dev <= max(4.0 * e_cpu, 2e-6), f"K={k}: device {e_dev:.3g} vs fp32 CPU {e_cpu:.3g}"
 
 
+@pytest.mark.parametrize("precision,tol", [(0, 3e-6), (2, 2e-2)])
+@pytest.mark.parametrize("m,n,k", [(512, 768, 8192), (300, 520, 16384), (128, 256, 12288)])
+def test_gemm_split_k(K, m, n, k, precision, tol):
+    """Few output tiles and a long K: the K loop is split over several CTAs (pairs) and the
+    partial products are summed by a second kernel (alpha, beta and a separate C_in must
+    still be applied exactly once)."""
+    from aesara_b200.runtime import lib as _lib
+    import ctypes as C
+
+    need = C.c_size_t()
+    _lib.check(_lib.load().ab_gemm_packed_workspace_bytes(precision, m, n, k, C.byref(need)))
+    assert need.value > 0, "this shape is expected to take the split-K path"
+    rng = np.random.default_rng(k + n)
+    a = rng.standard_normal((m, k)).astype("float32")
+    b = rng.standard_normal((k, n)).astype("float32")
+    c0 = rng.standard_normal((m, n)).astype("float32")
+    out = _dev(np.zeros((m, n), "float32"))
+    K.gemm(out, 0.5, _dev(np.ascontiguousarray(a.T)).dimshuffle([1, 0]), _dev(b), -1.5, precision=precision,
+           cin=_dev(c0))
+    want = -1.5 * c0.astype(np.float64) + 0.5 * (a.astype(np.float64) @ b.astype(np.float64))
+    err = _normwise(out.to_numpy(), want)
+    assert err < tol, f"split-K gemm normwise error {err}"
+
+
 @pytest.mark.parametrize("precision,tol", [(1, 2e-3), (2, 2e-2)])
 def test_gemm_reduced_precision_policies(K, precision, tol):
     """TF32 / BF16 compute policies: stated looser tolerances."""
