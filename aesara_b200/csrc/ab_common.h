@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 
 #include "../../include/aesara_b200.h"
@@ -25,6 +26,7 @@ struct Module {
          RED_COLS, RED_COLS_P, RED_COLS_F, N_KERNELS };
   cudaKernel_t k[N_KERNELS] = {};
   bool tried[N_KERNELS] = {};
+  std::map<std::string, cudaKernel_t> named;  // kernels launched by name (ab_kernel_launch)
   int get(int which, cudaKernel_t* out);
 };
 

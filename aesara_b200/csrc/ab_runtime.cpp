@@ -207,6 +207,29 @@ int ab_module_load(const void* cubin, size_t cubin_size, ab_module** out) {
   return AB_OK;
 }
 
+int ab_kernel_launch(ab_module* mod, const char* name, unsigned grid_x, unsigned block_x,
+                     size_t smem_bytes, void** args, void* stream) {
+  Module* m = reinterpret_cast<Module*>(mod);
+  if (!m || !name || !args) return fail(AB_ERR_INVALID, "null argument");
+  if (grid_x == 0 || block_x == 0) return AB_OK;
+  cudaKernel_t kern = nullptr;
+  auto it = m->named.find(name);
+  if (it == m->named.end()) {
+    cudaError_t e = cudaLibraryGetKernel(&kern, m->lib, name);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(AB_ERR_INVALID, "module has no kernel %s", name);
+    }
+    m->named[name] = kern;
+  } else {
+    kern = it->second;
+  }
+  AB_CUDA(cudaLaunchKernel((const void*)kern, dim3(grid_x), dim3(block_x), args, smem_bytes,
+                           as_stream(stream)));
+  g_launches++;
+  return AB_OK;
+}
+
 int ab_module_unload(ab_module* mod) {
   Module* m = reinterpret_cast<Module*>(mod);
   if (!m) return AB_OK;

@@ -101,6 +101,10 @@ SIGNATURES = {
         [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
          C.c_int64, C.POINTER(C.c_size_t)],
     ),
+    "ab_kernel_launch": (
+        C.c_int,
+        [C.c_void_p, C.c_char_p, C.c_uint, C.c_uint, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p],
+    ),
     "ab_gemm_pack_bytes": (
         C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]
     ),

@@ -103,6 +103,20 @@ class ProgramExecutor:
             elif n.op == "Scan":
                 d = sorted({int(i) for v in n.params.get("destroy_map", {}).values() for i in v})
             self._destroys.append(d)
+        # row-region fusion (runtime/rowfuse.py): member nodes are skipped and the region runs
+        # as one kernel at the position of its last node; operands of skipped nodes must
+        # stay alive until then
+        from .rowfuse import RowFusion
+
+        self._fusions = RowFusion.detect(program)
+        self._fusion_of = {}
+        for f in self._fusions:
+            for i in f.members:
+                self._fusion_of[i] = f
+                if i != f.last:
+                    self._free_after[f.last].extend(self._free_after[i])
+                    self._free_after[i] = []
+        self.fused_regions_run = 0
         self.prepare()
 
     # ------------------------------------------------------------------
@@ -133,6 +147,8 @@ class ProgramExecutor:
             r = st.get("runner")
             if r is not None:
                 n += r.inner.compile_all()
+        for f in self._fusions:
+            n += f.compile_all()
         return n
 
     # ------------------------------------------------------------------
@@ -214,6 +230,29 @@ class ProgramExecutor:
                     ev = pending.pop(v, None)
                     if ev is not None:
                         torch.cuda.current_stream().wait_event(ev)
+            fusion = self._fusion_of.get(i)
+            if fusion is not None:
+                if i != fusion.last:
+                    continue  # deferred to the region's last node
+                if events is not None:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                try:
+                    done = fusion.run(self, env)
+                except Exception as exc:
+                    self.position_of_error = i
+                    raise NodeError(i, node, exc) from exc
+                if not done:
+                    self._run_nodes(fusion.members, env)
+                else:
+                    self.fused_regions_run += 1
+                if events is not None:
+                    e1.record()
+                    events.append((i, e0, e1))
+                for v in self._free_after[i]:
+                    env.pop(v, None)
+                continue
             if events is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
@@ -247,6 +286,28 @@ class ProgramExecutor:
         if self.host_outputs:
             outs = DeviceArray.download_all(outs)
         return outs
+
+    def _run_nodes(self, indices, env):
+        """Plain execution of the given nodes (a fused region whose operands did not fit)."""
+        nodes = self.program.nodes
+        for i in indices:
+            node = nodes[i]
+            try:
+                outs = self._steps[i](self, i, node, [env[v] for v in node.inputs])
+            except NodeError:
+                raise
+            except Exception as exc:
+                self.position_of_error = i
+                raise NodeError(i, node, exc) from exc
+            if len(node.outputs) == 1:
+                env[node.outputs[0]] = outs
+            else:
+                for vid, o in zip(node.outputs, outs):
+                    env[vid] = o
+            for pos in self._destroys[i]:
+                d = env.get(node.inputs[pos])
+                if isinstance(d, DeviceArray):
+                    self.pack_cache.invalidate(d.owner)
 
     def _copy_stream_for(self, cur):
         st = self._copy_streams.get(cur.device)

@@ -64,6 +64,9 @@ def workload_spec(name, args):
             desc=f"cfg5: logistic-regression cost+grad, {N} rows x {D} f32 per GPU",
             gemm_flops=0.0, n_gemm=0,
             elemwise_bytes=(2.0 * N * D + 12.0 * N) * 4,      # SURVEY §8d graph-as-optimised
+            # single-pass row-region fusion (runtime/rowfuse.py): X once, y read by `1 - y` and
+            # by the fused kernel, `1 - y` written and read back
+            fused_bytes=(1.0 * N * D + 4.0 * N) * 4,
         )
     if name == "readme":
         n = args.n or 1000
@@ -410,11 +413,17 @@ def main():
                             "peak": peaks["hbm"], "unit": "GB/s", "frac": ach_h / peaks["hbm"],
                             "peak_source": peaks["src"], "traffic": None, "ms_per_step": ms_step}
         else:
-            ach_h = spec["elemwise_bytes"] / (ms_step * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": "whole evaluation (CUDA-graph replay)",
+            single_pass = bool(spec.get("fused_bytes")) and ex.fused_regions_run > 0
+            nbytes = spec["fused_bytes"] if single_pass else spec["elemwise_bytes"]
+            ach_h = nbytes / (ms_step * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "whole evaluation (CUDA-graph replay)"
+                        + ("; ab_rowfused single pass over X" if single_pass else ""),
                         "achieved": ach_h, "peak": peaks["hbm"], "unit": "GB/s",
                         "frac": ach_h / peaks["hbm"], "peak_source": peaks["src"], "traffic": None,
-                        "ms_per_step": ms_step}
+                        "ms_per_step": ms_step,
+                        "algorithmic_bytes": nbytes,
+                        "bytes_model": ("single pass: N*D*4 + 16 N (SURVEY 8d: 'report which is implemented')"
+                                        if single_pass else "graph as optimised: 2*N*D*4 + 48 N (SURVEY 8d)")}
         gemm_ms = hbm_ms = other_ms = None
     elif spec["n_gemm"]:
         ach = spec["gemm_flops"] / (gemm_ms * 1e-3) / 1e12

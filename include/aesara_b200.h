@@ -93,6 +93,11 @@ void ab_buffer_free(void* p);
  * aesara/link/c/cmodule.py:ModuleCache). */
 int ab_module_load(const void* cubin, size_t cubin_size, ab_module** out);
 int ab_module_unload(ab_module* m);
+/* Launch a kernel of a loaded module by name with a 1-D grid (generated kernels whose
+ * parameter list is not one of the fixed Elemwise / CAReduce skeletons, e.g. the fused
+ * Gemv -> Elemwise -> Gemv^T row kernel).  args[i] points at the i-th kernel parameter. */
+int ab_kernel_launch(ab_module* m, const char* name, unsigned grid_x, unsigned block_x,
+                     size_t smem_bytes, void** args, void* stream);
 
 /* ---- Elemwise (aesara/tensor/elemwise.py:304, C thunk _c_all :835-1168) ---
  * Launch the fused scalar expression compiled in `m` over an ndim-dimensional

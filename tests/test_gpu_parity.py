@@ -240,6 +240,61 @@ def test_lstm_medium_size_vs_oracle_and_graph_replay(rt, T, B, H):
         np.testing.assert_array_equal(g.to_numpy(), e)
 
 
+@pytest.mark.parametrize("N,D,fused", [(1000, 48, True), (4099, 512, True), (257, 36, True), (3000, 1024, True),
+                                       (333, 128, True), (500, 1100, False), (500, 30, False)])
+def test_logreg_row_region_fusion(rt, N, D, fused):
+    """cfg5 graph: the Gemv -> Elemwise -> Sum / Gemv(X.T) region runs as one pass over X
+    (runtime/rowfuse.py) and matches both the node-by-node device execution and the
+    oracle; operands the fused kernel does not take (D > 1024, D % 4 != 0) fall back to the
+    node-by-node path."""
+    import os
+
+    from oracle.program_np import run_program
+
+    prog, _, _ = load_case("cfg5_logreg")
+    rng = np.random.default_rng(N + D)
+    ins = [rng.standard_normal((N, D)).astype("float32"), (rng.random(N) < 0.5).astype("float32"),
+           (rng.standard_normal(D) * 0.05).astype("float32"), np.float32(0.25)]
+    want = run_program(prog, [np.array(a) for a in ins])
+    ex = rt(prog)
+    assert len(ex._fusions) == 1
+    got = ex(*ins)
+    assert ex.fused_regions_run == (1 if fused else 0)
+    os.environ["AB_NO_ROWFUSE"] = "1"
+    try:
+        ex_plain = rt(prog)
+    finally:
+        del os.environ["AB_NO_ROWFUSE"]
+    assert not ex_plain._fusions
+    plain = ex_plain(*ins)
+    for k, (g, p, w) in enumerate(zip(got, plain, want)):
+        assert_matches(g, w, blas=True, what=f"fused logreg out {k} vs oracle")
+        assert_matches(g, p, blas=True, what=f"fused logreg out {k} vs node-by-node")
+
+
+def test_logreg_row_region_fusion_strided_and_device_scalars(rt):
+    """X as a column slice of a wider matrix (row stride > D), y as a strided view, the
+    bias as a 1-element device array."""
+    from aesara_b200.runtime.device import DeviceArray
+    from oracle.program_np import run_program
+
+    prog, _, _ = load_case("cfg5_logreg")
+    rng = np.random.default_rng(7)
+    N, D = 2000, 256
+    big = rng.standard_normal((N, D + 64)).astype("float32")
+    y2 = (rng.random(2 * N) < 0.5).astype("float32")
+    w = (rng.standard_normal(D) * 0.05).astype("float32")
+    b = np.float32(-0.5)
+    want = run_program(prog, [np.ascontiguousarray(big[:, 32 : 32 + D]), y2[::2].copy(), w, b])
+    Xd = DeviceArray.from_numpy(big).index((slice(None), slice(32, 32 + D)))
+    yd = DeviceArray.from_numpy(y2).index((slice(None, None, 2),))
+    ex = rt(prog)
+    got = ex(Xd, yd, DeviceArray.from_numpy(w), DeviceArray.from_numpy(np.asarray(b)))
+    assert ex.fused_regions_run == 1
+    for k, (g, wv) in enumerate(zip(got, want)):
+        assert_matches(g, wv, blas=True, what=f"strided fused logreg out {k}")
+
+
 def test_gemm_full_size_tile_independence(rt):
     """BASELINE-size GEMM property (no CPU truth at this size): rows of a
     [16384, 4096] x [4096, 4096] product equal the product of the row subset, for
