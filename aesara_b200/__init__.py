@@ -23,6 +23,14 @@ def __getattr__(name):
         from . import linker
 
         return getattr(linker, name)
+    if name in ("shared", "B200SharedVariable"):
+        from . import sharedvar
+
+        return getattr(sharedvar, name)
+    if name == "check_function":
+        from .debug import check_function
+
+        return check_function
     if name == "ProgramExecutor":
         from .runtime.vm import ProgramExecutor
 

@@ -62,33 +62,73 @@ class B200VM:
         self.thunks = [_NodeThunk(n, storage_map) for n in order]
         self.allow_gc = linker.allow_gc
         self.position_of_error = -1
-        self.time_thunks = False
         self.call_counts = [0] * len(order)
         self.call_times = [0.0] * len(order)
         upd = getattr(fgraph, "update_mapping", None) or {}
         self._updates = [(int(o), int(i)) for o, i in upd.items()]
+        # FunctionMaker appends the update expressions after the user's outputs
+        # (compile/function/types.py:1422-1432): those trailing outputs are never returned
+        n_out = len(output_storage)
+        self._updates_trail = sorted(o for o, _ in self._updates) == list(range(n_out - len(self._updates), n_out))
         self._host_out = not linker.device_outputs
+        self.time_thunks = bool(getattr(linker, "profile", None))
+        if self.time_thunks and hasattr(executor, "time_nodes"):
+            executor.time_nodes = True
 
     def __call__(self, output_subset=None):
-        from .runtime.device import DeviceArray
         from .runtime.vm import NodeError
+        from .sharedvar import is_device_value, owns_cell
 
         try:
             outs = self.executor(*[cell[0] for cell in self.input_storage])
         except NodeError as e:
             self.position_of_error = e.position
             raise e.original from None
+        finally:
+            self._collect_times()
+        dev_outs = list(outs)
         if self._host_out:
-            outs = [o.to_numpy() if isinstance(o, DeviceArray) else o for o in outs]
+            # a trailing update output that feeds a device-resident shared variable is
+            # never returned to the caller: do not download it
+            keep_dev = set()
+            if self._updates_trail:
+                keep_dev = {o for o, i in self._updates if owns_cell(self.input_storage[i])}
+            outs = [o if (k in keep_dev or not is_device_value(o)) else o.to_numpy()
+                    for k, o in enumerate(outs)]
         for cell, val in zip(self.output_storage, outs):
             cell[0] = val
         for out_idx, in_idx in self._updates:  # UpdatingVM.perform_updates, vm.py:326-335
-            self.input_storage[in_idx][0] = outs[out_idx]
+            cell = self.input_storage[in_idx]
+            if owns_cell(cell):
+                cell[0] = dev_outs[out_idx]       # stays on the device (sharedvar.py)
+            else:
+                v = outs[out_idx]
+                cell[0] = v.to_numpy() if (self._host_out and is_device_value(v)) else v
         return outs
 
+    # -- profiling (ProfileStats per-node times from CUDA events) ---------------------
+    def _collect_times(self):
+        if not self.time_thunks:
+            return
+        times = getattr(self.executor, "node_times_ms", None)
+        if times is None:
+            return
+        for i, _op, ms in times():
+            self.call_times[i] += ms * 1e-3
+            self.call_counts[i] += 1
+
     def update_profile(self, profile):
-        for i, node in enumerate(self.nodes):
-            profile.apply_callcount[node] = profile.apply_callcount.get(node, 0) + self.call_counts[i]
+        """``VM.update_profile`` (``link/vm.py:251-281``): per-Apply device time (CUDA events
+        recorded around every node) and call counts."""
+        for node, t, c in zip(self.nodes, self.call_times, self.call_counts):
+            profile.apply_time.setdefault((self.fgraph, node), 0.0)
+            profile.apply_time[(self.fgraph, node)] += t
+            profile.apply_callcount.setdefault((self.fgraph, node), 0)
+            profile.apply_callcount[(self.fgraph, node)] += c
+            profile.apply_cimpl[node] = True  # native kernels, not Python `perform`
+        for i in range(len(self.call_times)):
+            self.call_times[i] = 0.0
+            self.call_counts[i] = 0
 
 
 class B200Linker(LocalLinker):

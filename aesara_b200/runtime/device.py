@@ -275,6 +275,15 @@ class DeviceArray:
             host = t.cpu()
         return host.numpy().view(src.dtype).reshape(src.shape)
 
+    def copy(self):
+        """A C-contiguous device copy (the device analogue of ``ndarray.copy``)."""
+        from .kernels import contiguous_copy
+
+        return contiguous_copy(self)
+
+    def __deepcopy__(self, memo):
+        return self.copy()
+
     def __array__(self, dtype=None, copy=None):
         a = self.to_numpy()
         return a if dtype is None else a.astype(dtype)

@@ -84,6 +84,7 @@ class ProgramExecutor:
             if v not in keep and v not in self._const_host:
                 self._free_after[i].append(v)
         self.node_events = None
+        self.trace = None  # debug: {node index: [host copies of its outputs]} (aesara_b200/debug.py)
         self._first_use = {}
         for i, n in enumerate(program.nodes):
             for v in n.inputs:
@@ -276,6 +277,11 @@ class ProgramExecutor:
                 d = env.get(node.inputs[pos])
                 if isinstance(d, DeviceArray):
                     self.pack_cache.invalidate(d.owner)
+            if self.trace is not None:
+                vals = [env[v] for v in node.outputs]
+                self.trace[i] = [v.to_numpy() if isinstance(v, DeviceArray)
+                                 else (None if v is None or isinstance(v, slice) else np.array(v, copy=True))
+                                 for v in vals]
             for v in self._free_after[i]:
                 env.pop(v, None)
         self.node_events = events

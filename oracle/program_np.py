@@ -28,7 +28,7 @@ class OracleAssertionError(AssertionError):
     pass
 
 
-def run_program(prog, inputs, return_env=False):
+def run_program(prog, inputs, return_env=False, trace=None):
     """Evaluate ``prog`` on NumPy ``inputs`` (list in ``prog.inputs`` order)."""
     env = {}
     for vid, v in enumerate(prog.vars):
@@ -45,7 +45,7 @@ def run_program(prog, inputs, return_env=False):
         elif var.kind == "scalar":
             val = np.dtype(var.dtype).type(val)
         env[vid] = val
-    for node in prog.nodes:
+    for pos, node in enumerate(prog.nodes):
         args = [env[i] for i in node.inputs]
         outs = _H[node.op](node, args, prog)
         if not isinstance(outs, (list, tuple)):
@@ -57,6 +57,9 @@ def run_program(prog, inputs, return_env=False):
                 if o.dtype != np.dtype(var.dtype):
                     o = o.astype(var.dtype)
             env[vid] = o
+        if trace is not None:
+            trace[pos] = [None if env[v] is None or isinstance(env[v], slice) else np.array(env[v], copy=True)
+                          for v in node.outputs]
     outs = [env[v] for v in prog.outputs]
     if return_env:
         return outs, env

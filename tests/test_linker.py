@@ -22,16 +22,57 @@ def aes():
     return aesara, L
 
 
+class _FakeDeviceArray:
+    """Host-backed stand-in for runtime.device.DeviceArray (no GPU in this container):
+    what the VM / shared-variable logic needs to know is only "this value is on the device"."""
+
+    uploads = 0
+    downloads = 0
+
+    def __init__(self, a):
+        self._a = np.array(a, copy=True)
+        self.ptr = id(self._a)
+        self.dtype, self.shape = self._a.dtype, self._a.shape
+
+    def to_numpy(self):
+        type(self).downloads += 1
+        return self._a.copy()
+
+    def copy(self):
+        return _FakeDeviceArray(self._a)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.to_numpy() if dtype is None else self.to_numpy().astype(dtype)
+
+
 class _OracleExecutor:
     """Stand-in with the ProgramExecutor call signature (tests only)."""
 
+    device_results = False  # return _FakeDeviceArray outputs (as the real executor does)
+
     def __init__(self, program, **kw):
         self.program = program
+        self.trace = None
+        self.time_nodes = False
 
     def __call__(self, *inputs):
         from oracle.program_np import run_program
 
-        return run_program(self.program, [np.array(i) if isinstance(i, np.ndarray) else i for i in inputs])
+        host = []
+        for i in inputs:
+            if isinstance(i, _FakeDeviceArray):
+                host.append(i._a.copy())
+            else:
+                if isinstance(i, np.ndarray) and i.size > 64:
+                    _FakeDeviceArray.uploads += 1
+                host.append(np.array(i) if isinstance(i, np.ndarray) else i)
+        outs = run_program(self.program, host, trace=self.trace)
+        if self.device_results:
+            outs = [_FakeDeviceArray(o) if isinstance(o, np.ndarray) and o.ndim > 0 else o for o in outs]
+        return outs
+
+    def node_times_ms(self):
+        return [(i, n.op, 0.25) for i, n in enumerate(self.program.nodes)]
 
 
 def test_mode_and_linker_are_registered(aes):
@@ -112,3 +153,96 @@ def test_linker_copies_bind_to_one_graph(aes):
     b = a.accept(fg2)
     assert a is lk and b is not lk and b.fgraph is fg2
     assert lk.clone(allow_gc=False).allow_gc is False
+
+
+def test_device_resident_shared_variable_updates(aes, monkeypatch):
+    """weights in `aesara_b200.shared` stay on the device across calls —
+    the update result is written into the cell without a download and the next call does
+    not upload it; `get_value` still hands NumPy to the caller."""
+    aesara, L = aes
+    import aesara.tensor as at
+    import aesara_b200.runtime.vm as vm
+    from aesara_b200.sharedvar import B200SharedVariable, shared
+
+    monkeypatch.setattr(vm, "ProgramExecutor", _OracleExecutor)
+    monkeypatch.setattr(_OracleExecutor, "device_results", True)
+    _FakeDeviceArray.uploads = _FakeDeviceArray.downloads = 0
+    x = at.fvector("x")
+    W = shared(np.full(100, 0.5, "float32"), name="W")
+    assert isinstance(W, B200SharedVariable) and not W.is_on_device()
+    loss = ((W * x) ** 2).sum()
+    f = aesara.function([x], loss, updates=[(W, W - 0.1 * aesara.grad(loss, W))], mode=L.mode())
+    xv = np.linspace(-1, 1, 100).astype("float32")
+    ref_W = np.full(100, 0.5, "float32")
+    for step in range(3):
+        l = f(xv)
+        want = float(((ref_W * xv) ** 2).sum())
+        np.testing.assert_allclose(l, want, rtol=1e-5)
+        ref_W = ref_W - 0.1 * (2 * ref_W * xv * xv)
+        assert W.is_on_device()
+    # one upload of W (first call) + x each call; W's update was never downloaded
+    assert _FakeDeviceArray.uploads == 1 + 3
+    assert _FakeDeviceArray.downloads == 0
+    np.testing.assert_allclose(W.get_value(), ref_W, rtol=1e-5)
+    assert _FakeDeviceArray.downloads == 1
+    internal = W.get_value(borrow=True, return_internal_type=True)
+    assert isinstance(internal, _FakeDeviceArray)
+    W.set_value(np.zeros(100, "float32"))
+    assert not W.is_on_device()
+    np.testing.assert_allclose(f(xv), 0.0)
+    W.set_value(_FakeDeviceArray(np.ones(100, "float32")))
+    np.testing.assert_allclose(f(xv), float((xv ** 2).sum()), rtol=1e-5)
+    with pytest.raises(TypeError):
+        W.set_value(_FakeDeviceArray(np.ones((2, 2), "float32")))
+    # an ordinary aesara.shared keeps host semantics (its update IS downloaded)
+    acc = aesara.shared(np.zeros(100, "float32"), name="acc")
+    g = aesara.function([x], [], updates=[(acc, acc + x)], mode=L.mode())
+    g(xv)
+    assert isinstance(acc.container.storage[0], np.ndarray)
+    np.testing.assert_allclose(acc.get_value(), xv)
+
+
+def test_profile_receives_per_node_times(aes, monkeypatch):
+    """`aesara.function(..., profile=True)`: the VM feeds ProfileStats per-Apply times and
+    call counts (link/vm.py:251-281) — on the device these come from CUDA events."""
+    aesara, L = aes
+    import aesara.tensor as at
+    import aesara_b200.runtime.vm as vm
+
+    monkeypatch.setattr(vm, "ProgramExecutor", _OracleExecutor)
+    x = at.fvector("x")
+    f = aesara.function([x], at.tanh(x).sum(), mode=L.mode(), profile=True)
+    for _ in range(3):
+        f(np.ones(7, "float32"))
+    prof = f.profile
+    assert prof.fct_callcount == 3
+    assert len(prof.apply_time) == len(f.maker.fgraph.apply_nodes)
+    assert all(abs(t - 3 * 0.25e-3) < 1e-9 for t in prof.apply_time.values())
+    assert all(c == 3 for c in prof.apply_callcount.values())
+
+
+def test_dual_run_checker(aes, monkeypatch):
+    """DualLinker-style harness: every node of the B200 run is compared with the reference
+    thunk of the same Apply; a corrupted node is located."""
+    aesara, L = aes
+    import aesara.tensor as at
+    import aesara_b200.runtime.vm as vm
+    from aesara_b200.debug import DualRunMismatch, check_function
+
+    monkeypatch.setattr(vm, "ProgramExecutor", _OracleExecutor)
+    X, w = at.fmatrix("X"), at.fvector("w")
+    out = [at.tanh(X @ w).sum(), at.exp(X).max(axis=0)]
+    vals = [np.random.default_rng(0).standard_normal((9, 5)).astype("float32"),
+            np.random.default_rng(1).standard_normal(5).astype("float32")]
+    report = check_function([X, w], out, vals)
+    assert len(report) >= 3 and all(isinstance(r[2], float) for r in report)
+    report_c = check_function([X, w], out, vals, reference_linker="c")
+    assert len(report_c) == len(report)
+
+    import oracle.program_np as O
+
+    orig = O._H["CAReduce"]
+    monkeypatch.setitem(O._H, "CAReduce", lambda node, args, prog: orig(node, args, prog) * 1.001)
+    with pytest.raises(DualRunMismatch) as ei:
+        check_function([X, w], out, vals)
+    assert "CAReduce" in str(ei.value.node.op.__class__.__mro__) or "Sum" in str(ei.value.node) or "Max" in str(ei.value.node)
