@@ -484,7 +484,15 @@ def main():
 
     if rank == 0:
         cb = None if args.no_cpu else cpu_baseline(spec)
-        par = "single" if world == 1 else f"dp{world} (batch rows sharded, one NCCL all-gather of outputs)"
+        if world == 1:
+            par = "single"
+        else:
+            from aesara_b200.shard import exchange_plan
+
+            how = exchange_plan(combiner.layout.total, world) if combiner.layout is not None else "allgather"
+            par = (f"dp{world} (batch rows sharded; outputs combined by one NCCL "
+                   + ("all-reduce of the pre-weighted packed outputs)" if how == "allreduce"
+                      else "all-gather of the packed outputs + local weighted sum)"))
         line = {
             "metric": "graph-evals/s", "value": value, "unit": "graph-evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,

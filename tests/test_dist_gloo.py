@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from aesara_b200.shard import combine_weights, pack_layout, row_block
+from aesara_b200.shard import ALLREDUCE_MIN_ELEMS, combine_weights, exchange_plan, pack_layout, row_block
 
 
 def test_row_blocks_cover_and_balance():
@@ -26,6 +26,13 @@ def test_row_blocks_cover_and_balance():
 def test_pack_layout_alignment():
     L = pack_layout([(), (5,), (3, 3)])
     assert L.offsets == [0, 4, 12] and L.total == 24
+
+
+def test_exchange_plan_by_payload():
+    assert exchange_plan(514, 8) == "allgather"                   # cfg5: (D+2) floats
+    assert exchange_plan(2 * 4096 * 4096 + 2 * 4096 + 4, 8) == "allreduce"   # cfg3 gradients
+    assert exchange_plan(ALLREDUCE_MIN_ELEMS, 2) == "allreduce"
+    assert exchange_plan(1 << 30, 1) == "allgather"               # nothing to exchange
 
 
 def _free_port():
@@ -60,6 +67,10 @@ def _worker(rank, world, port, n_rows, q):
     rows = [row_block(n_rows, world, r) for r in range(world)]
     wts = combine_weights("mean", [e - s for s, e in rows])
     comb = sum(wt * g for wt, g in zip(wts, gathered)).numpy()
+    # the large-payload plan: weight the local buffer, one all_reduce (shard.exchange_plan)
+    reduced = flat * wts[rank]
+    dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
+    np.testing.assert_allclose(reduced.numpy(), comb, rtol=1e-6, atol=1e-7)
     if rank == 0:
         full = run_program(prog, [X, y, w, np.float32(0.1)])
         res = []

@@ -159,6 +159,11 @@ def test_output_combiner_device_path_single_rank(rt):
         got = comb([DeviceArray.from_numpy(o) for o in outs])
         for g, w in zip(got, outs):
             np.testing.assert_allclose(g.to_numpy(), w, rtol=1e-6)
+        # the large-payload plan: weight the local buffer, one in-place all_reduce
+        comb2 = OutputCombiner(1, mode="mean", plan="allreduce")
+        got2 = comb2([DeviceArray.from_numpy(o) for o in outs])
+        for g, w in zip(got2, outs):
+            np.testing.assert_allclose(g.to_numpy(), w, rtol=1e-6)
     finally:
         dist.destroy_process_group()
 
