@@ -48,8 +48,27 @@ __device__ __forceinline__ T ab_floordiv_uint(T x, T y) { return y == 0 ? (T)0 :
 template <typename T>
 __device__ __forceinline__ T ab_mod_uint(T x, T y) { return y == 0 ? (T)0 : x % y; }
 
-__device__ __forceinline__ float ab_floordiv_f(float x, float y) { return floorf(x / y); }
-__device__ __forceinline__ double ab_floordiv_f(double x, double y) { return floor(x / y); }
+// IntDiv on floats is NOT floor(x / y) in the reference: the C code (basic.py:2083-2121)
+// divides magnitudes and corrects with fmod, which differs for infinite divisors
+// (0.5 // -inf = -1) and when |x| / |y| rounds up to an integer.
+__device__ __forceinline__ float ab_floordiv_f(float x, float y) {
+  if (y == 0.0f) return floorf(x / y);
+  if (y < 0.0f) {
+    if (x < 0.0f) return floorf((-x) / (-y));
+    return -floorf(x / (-y)) - ((fmodf(x, -y) == 0.0f) ? 0.0f : 1.0f);
+  }
+  if (x < 0.0f) return -floorf((-x) / y) - ((fmodf(-x, y) == 0.0f) ? 0.0f : 1.0f);
+  return floorf(x / y);
+}
+__device__ __forceinline__ double ab_floordiv_f(double x, double y) {
+  if (y == 0.0) return floor(x / y);
+  if (y < 0.0) {
+    if (x < 0.0) return floor((-x) / (-y));
+    return -floor(x / (-y)) - ((fmod(x, -y) == 0.0) ? 0.0 : 1.0);
+  }
+  if (x < 0.0) return -floor((-x) / y) - ((fmod(-x, y) == 0.0) ? 0.0 : 1.0);
+  return floor(x / y);
+}
 // Python-sign floating modulo (basic.py:2207-2236)
 __device__ __forceinline__ float ab_mod_f(float x, float y) {
   if (y == 0.0f) return fmodf(x, y);

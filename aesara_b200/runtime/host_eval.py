@@ -79,7 +79,14 @@ def _fold(args, fn):
 
 
 def supports(expr):
-    return all(st["op"] in _OPS for st in expr["stmts"])
+    for st in expr["stmts"]:
+        if st["op"] not in _OPS:
+            return False
+        # float IntDiv / Mod follow branchy C formulas in the reference (basic.py:2083-2121,
+        # :2207-2236) that only the device bodies reproduce: never evaluate them here
+        if st["op"] in ("int_div", "mod") and np.dtype(st["dtype"]).kind not in "biu":
+            return False
+    return True
 
 
 def eval_expr(expr, inputs):

@@ -83,7 +83,19 @@ def _int_div(x, y):  # basic.py:2055-2127: floor division
         if np.issubdtype(rt, np.integer) or rt == np.bool_:
             y_safe = np.where(y == 0, 1, y)
             return np.where(y == 0, 0, np.floor_divide(x, y_safe))
-        return np.floor(np.asarray(x) / np.asarray(y))
+        # floats: the reference divides magnitudes and corrects with fmod (basic.py:2083-2121);
+        # this is not floor(x / y) for infinite divisors or when |x|/|y| rounds up to an integer
+        x = np.asarray(x, dtype=rt)
+        y = np.asarray(y, dtype=rt)
+        x, y = np.broadcast_arrays(x, y)
+        one = rt.type(1)
+        pp = np.floor(x / y)
+        mm = np.floor((-x) / (-y))
+        pm = -np.floor(x / (-y)) - np.where(np.fmod(x, -y) == 0, 0, one)
+        mp = -np.floor((-x) / y) - np.where(np.fmod(-x, y) == 0, 0, one)
+        neg_y = np.where(x < 0, mm, pm)
+        pos_y = np.where(x < 0, mp, pp)
+        return np.where(y == 0, pp, np.where(y < 0, neg_y, pos_y)).astype(rt)
 
 
 def _sgn(x):  # basic.py:2614-2630

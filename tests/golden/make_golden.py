@@ -272,6 +272,78 @@ def _():
     return [A, x, y], [at.dot(A, x) * 2 + y, at.dot(A.T, y)], [rnd((77, 50), "float64"), rnd(50, "float64"), rnd(77, "float64")]
 
 
+# ---------------------------------------------------------------- views / layout edge cases
+@case("views_negative_steps")
+def _():
+    x = at.fmatrix("x")
+    v = at.fvector("v")
+    t = at.ftensor3("t")
+    outs = [x[::-1] * 2, x[5:1:-2, ::3] + 1, x[:, -1], x[-2], x[1:-1, 2:-2].sum(axis=0),
+            at.dot(x[::-1], v), at.dot(x[:, ::-1], v[::-1]), at.dot(x[::2].T, x[::2]),
+            t[::-1, :, ::-2].sum(axis=1), t[1][::-1].T + 0.5, v[::-3].max(), at.exp(v[None, :] + v[:, None])[::4, 1::5],
+            x[2:2].sum(), x[:, 3:1].shape[1] + x[:0].sum(axis=0)]
+    return [x, v, t], outs, [rnd((12, 10)), rnd(10), rnd((4, 5, 6))]
+
+
+@case("incsubtensor_variants")
+def _():
+    x = at.fmatrix("x")
+    v = at.fvector("v")
+    s = at.fscalar("s")
+    outs = [at.set_subtensor(x[1:4], 0.5), at.inc_subtensor(x[::2, 1::3], s), at.set_subtensor(x[:, 2], v[:x.shape[0]]),
+            at.inc_subtensor(x[-1], v[:x.shape[1]] * 2), at.set_subtensor(x[2:5, 1:3], x[0:3, 4:6] + 1),
+            at.inc_subtensor(v[::-1][:3], 10.0), at.set_subtensor(x[3, 4], s * s), at.inc_subtensor(x[1:1], 7.0)]
+    return [x, v, s], outs, [rnd((7, 9)), rnd(9), np.float32(1.25)]
+
+
+@case("reshape_flatten_noncontig")
+def _():
+    x = at.fmatrix("x")
+    t = at.ftensor3("t")
+    n = at.lscalar("n")
+    outs = [x.T.reshape((-1,)), x.reshape((n, -1)) * 2, t.dimshuffle(2, 0, 1).reshape((6, -1)).sum(axis=1),
+            x.flatten() + 1, t.flatten(2), x[::2].reshape((3, 2, -1)).max(axis=2), x.T.flatten()[::5],
+            at.shape_padleft(x.sum(axis=0), 2) + t[:1, :1, :1].reshape((1, 1, 1)),
+            x.reshape((1, -1))[0, 3:9], at.reshape(x.sum(), ())]
+    return [x, t, n], outs, [rnd((6, 10)), rnd((4, 5, 6)), np.int64(4)]
+
+
+@case("nan_inf_semantics_f32")
+def _():
+    x, y = at.fvector("x"), at.fvector("y")
+    outs = [at.maximum(x, y), at.minimum(x, y), at.lt(x, y), at.ge(x, y), at.eq(x, x), at.neq(x, y),
+            at.switch(at.isnan(x), y, x), x / y, x // y, x % y, at.sqrt(x), at.log(abs(x)), at.exp(x * 40),
+            at.isinf(x / y), at.sgn(x), abs(x), at.clip(x, y, y + 2), at.floor(x), at.tanh(x * 1e6),
+            at.sigmoid(x * 200), at.softplus(x * 200), at.log1p(x), at.true_div(1.0, x) * 0.0, at.pow(x, y)]
+    xv = np.array([0.0, -0.0, 1.5, -2.5, np.nan, np.inf, -np.inf, 3.0, -3.0, 1e-30, 7.25, -7.25, 0.5, 2.0, -1.0, 9.0], "float32")
+    yv = np.array([0.0, 2.0, -2.0, 0.0, 1.0, np.inf, 2.0, np.nan, -0.0, 1e30, 2.0, 2.0, -np.inf, 0.5, 0.5, -3.0], "float32")
+    return [x, y], outs, [xv, yv]
+
+
+@case("alloc_and_shape_ops")
+def _():
+    x = at.fmatrix("x")
+    v = at.fvector("v")
+    n = at.lscalar("n")
+    outs = [at.zeros((n, 3)) + v[:3], at.ones_like(x) * v[:x.shape[1]], at.alloc(v, n, v.shape[0]) * 2,
+            at.fill(x, 2.5) + x, x.shape[0] * 2 + x.shape[1], at.zeros_like(x, dtype="int32") + n,
+            at.alloc(np.float32(1.5), n), at.prod(x.shape) + at.cast(n, "int64"),
+            at.tile(v[:2], (3, 2)), at.repeat(v[:3], 2), at.stack([v, v * 2]).T.sum(axis=1),
+            at.full_like(x, 4.0)[1:, :2] - x[1:, :2]]
+    return [x, v, n], outs, [rnd((4, 6)), rnd(6), np.int64(5)]
+
+
+@case("blas_edge_shapes")
+def _():
+    a, b, c = at.fmatrix("a"), at.fmatrix("b"), at.fmatrix("c")
+    v = at.fvector("v")
+    z = at.fmatrix("z")
+    outs = [at.dot(a[:1], b), at.dot(a, b[:, :1]), at.dot(a[:, :1], b[:1]), at.dot(a[:0], b), at.dot(a, b[:, :0]),
+            at.dot(a[:1], v[:a.shape[1]]), at.dot(v[:a.shape[0]], a), z + 0.5 * at.dot(a, b), at.dot(c, c.T) - at.dot(c.T, c)[:4, :4].sum(),
+            at.dot(a, b).T + at.dot(b.T, a.T), at.outer(v, v)[:3] + 1, at.dot(v, v) * v]
+    return [a, b, c, v, z], outs, [rnd((5, 7)), rnd((7, 6)), rnd((4, 9)), rnd(8), rnd((5, 6))]
+
+
 # ---------------------------------------------------------------- Scan
 @case("scan_cumsum_allsteps")
 def _():
