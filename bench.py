@@ -201,6 +201,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(summary, kernel_substr):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel from
+    a committed ``ncu --set full`` summary under profiles/ (None if it is not there)."""
+    path = os.path.join(ROOT, "profiles", summary)
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, inside, seen = 0.0, False, 0
+    for line in open(path):
+        if line.startswith("kernel:"):
+            if inside and seen == 2:
+                break
+            inside, total, seen = kernel_substr in line, 0.0, 0
+        elif inside and ("dram__bytes_read.sum " in line or "dram__bytes_write.sum " in line):
+            parts = line.split()
+            total += float(parts[1]) * unit.get(parts[2], 1.0)
+            seen += 1
+    return total if seen == 2 else None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -444,6 +464,19 @@ def main():
                     "frac": ach_h / peaks["hbm"], "peak_source": peaks["src"], "traffic": None,
                     "ms_per_step": hbm_ms}
         roofline_hbm = None
+
+    # DRAM traffic of the dominant kernel, per launch, from the committed ncu --set full summary
+    # of the same command (profiles/; cold-cache, serialised capture)
+    tsrc = None
+    if spec["name"] == "mlp" and args.precision == "bf16":
+        tsrc = ("r01_gemm_bf16_v4_8warp_epilogue.txt", "gemm_tcgen05_2cta_kernel")
+    elif spec["name"] == "logreg" and ex.fused_regions_run > 0:
+        tsrc = ("r01_rowfused_logreg.txt", "ab_rowfused")
+    elif spec["name"] == "elemwise":
+        tsrc = ("r01_elemwise_cfg2_v2_unroll1.txt", "ab_ew_flat_vec")
+    if tsrc is not None:
+        roofline["traffic"] = ncu_traffic(*tsrc)
+        roofline["traffic_source"] = f"profiles/{tsrc[0]} ({tsrc[1]}, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
 
     # end to end through the host API: pinned host inputs, H2D + eval + D2H of every output
     e2e = None
