@@ -41,154 +41,7 @@ namespace {
 
 using namespace ab::tc;
 
-struct GemmParams {
-  long long M, N, K;      // K in elements of the packed type
-  float alpha, beta;
-  float* C;
-  long long c_rs, c_cs;
-  const float* Cin;       // beta term source (== C for the in-place Gemm, another buffer otherwise)
-  long long cin_rs, cin_cs;
-  int block_n;            // 64 / 128 / 256
-  int acc_stages;         // TMEM accumulator stages (2 -> epilogue overlaps the next segment)
-  int seg_kblocks;        // k-blocks accumulated inside the tensor core before the epilogue
-                          // folds the partial sum into its FP32 registers (see "segments")
-  int k_splits;           // split-K: work unit = (tile, K range); unit u -> tile u / k_splits
-  int kb_per_split;       // k-blocks per K range
-  float* partial;         // [k_splits - 1][M][N] alpha * (A@B over K range s), s >= 1
-  int stages;
-  int nparts;             // 1, or 2 for the hi/lo split (3 MMAs per k-step)
-  int k_elems_per_row;    // K elements per stage = per 128-byte K-major row: 32 (tf32) / 64 (bf16)
-  int a_tile_bytes, b_tile_bytes;
-  int a_mn, b_mn;         // operand is MN-major
-  int a_chunks, b_chunks; // MN-major: 128-byte MN chunks per tile (tile_rows * elem_size / 128)
-  int chunk_bytes;        // MN-major: k_elems_per_row rows * 128 B
-  int mn_per_chunk;       // MN-major: elements per chunk (128 / elem_size)
-  int a_kstep, b_kstep;   // descriptor advance per MMA K-step: 32 B (K-major) or umma_k rows * 128 B
-  uint32_t idesc;
-};
-
-// one operand tile -> shared memory.  K-major: a single box {128 B of K, tile rows};
-// MN-major: one box {128 B of MN, BLOCK_K rows} per chunk.
-__device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
-                                          int kc, int mn0, int mn_major, int chunks,
-                                          const GemmParams& p) {
-  if (!mn_major) {
-    tma_load_2d(dst, map, bar, kc, mn0);
-  } else {
-    for (int c = 0; c < chunks; ++c)
-      tma_load_2d(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
-  }
-}
-
-// ---------------------------------------------------------------------- segments
-// The tensor core adds each MMA's products into the FP32 accumulator with truncation
-// (round toward zero), a bias that grows linearly with the number of accumulation steps:
-// measured on B200, an unsegmented 3xTF32 K = 4096 product is ~3e-5 from the FP64 result
-// where a true-fp32 sgemm is ~4e-7 (tests/test_gpu_blas.py::test_gemm_long_k_accuracy).
-// So the K loop is cut into segments of seg_kblocks k-blocks: each segment starts a fresh
-// TMEM accumulator, and the epilogue warps add the finished segment into FP32 registers
-// with round-to-nearest while the tensor core works on the next segment in the other
-// TMEM stage.  For precision 0 a segment is 128 K elements (48 truncating steps); the
-// tf32 / bf16 policies keep the whole K loop in one segment.
-constexpr int kAccRegs = 128;  // accumulator columns per epilogue thread (BLOCK_N 256 / 2)
-
-__device__ __forceinline__ void fold_segment(float (&acc)[kAccRegs], uint32_t t_acc, int nchunks,
-                                             bool first) {
-#pragma unroll
-  for (int c = 0; c < kAccRegs / 32; ++c) {
-    if (c < nchunks) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
-      if (first) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __uint_as_float(r[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
-      }
-    }
-  }
-}
-
-// C[row, n0 + ...] = alpha * acc + beta * Cin for one thread's row and column range
-struct EpilogueOut {
-  const GemmParams& p;
-  bool vec_ok;
-  __device__ explicit EpilogueOut(const GemmParams& p_) : p(p_) {
-    vec_ok = (p.c_cs == 1) && ((p.c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-             (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
-                                 ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
-  }
-  // split-K: alpha * acc of K range `split` (>= 1) into its [M, N] scratch plane
-  __device__ __forceinline__ void store_partial(const float (&acc)[kAccRegs], long long row,
-                                                long long n0, int nchunks, int split) const {
-    if (row >= p.M) return;
-    float* prow = p.partial + ((long long)(split - 1) * p.M + row) * p.N;
-    const bool vec = (p.N & 3) == 0;
-#pragma unroll
-    for (int c = 0; c < kAccRegs / 32; ++c) {
-      if (c < nchunks) {
-        const long long col0 = n0 + c * 32;
-        if (vec && col0 + 32 <= p.N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(prow + col0 + j) =
-                make_float4(p.alpha * acc[c * 32 + j], p.alpha * acc[c * 32 + j + 1],
-                            p.alpha * acc[c * 32 + j + 2], p.alpha * acc[c * 32 + j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) prow[col0 + j] = p.alpha * acc[c * 32 + j];
-        }
-      }
-    }
-  }
-  __device__ __forceinline__ void store(const float (&acc)[kAccRegs], long long row, long long n0,
-                                        int nchunks) const {
-    if (row >= p.M) return;
-    float* crow = p.C + row * p.c_rs;
-    const float* irow = p.Cin + row * p.cin_rs;
-#pragma unroll
-    for (int c = 0; c < kAccRegs / 32; ++c) {
-      if (c < nchunks) {
-        const long long col0 = n0 + c * 32;
-        if (vec_ok && col0 + 32 <= p.N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v;
-            v.x = p.alpha * acc[c * 32 + j];
-            v.y = p.alpha * acc[c * 32 + j + 1];
-            v.z = p.alpha * acc[c * 32 + j + 2];
-            v.w = p.alpha * acc[c * 32 + j + 3];
-            if (p.beta != 0.0f) {
-              const float4 o = *reinterpret_cast<const float4*>(irow + col0 + j);
-              v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
-            }
-            *reinterpret_cast<float4*>(crow + col0 + j) = v;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long col = col0 + j;
-            if (col < p.N) {
-              float v = p.alpha * acc[c * 32 + j];
-              if (p.beta != 0.0f) v += p.beta * irow[col * p.cin_cs];
-              crow[col * p.c_cs] = v;
-            }
-          }
-        }
-      }
-    }
-  }
-};
-
-// work unit -> (tile, K range); consecutive units of a tile go to different CTAs
-#define AB_UNIT_DECODE                                                          \
-  const long long tile = unit / p.k_splits;                                     \
-  const int split = (int)(unit - tile * p.k_splits);                            \
-  const int kb_begin = split * p.kb_per_split;                                  \
-  const int kb_end = min(kb_begin + p.kb_per_split, num_k_blocks);              \
-  (void)split;
+#include "ab_gemm_tcgen05_kernel.cuh"
 
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -197,193 +50,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
                     const __grid_constant__ CUtensorMap map_b0,
                     const __grid_constant__ CUtensorMap map_b1,
                     const __grid_constant__ GemmParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 for SWIZZLE_128B
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  __shared__ __align__(8) uint64_t full_bar[8];
-  __shared__ __align__(8) uint64_t empty_bar[8];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ uint32_t tmem_base_slot;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int stage_bytes = p.nparts * (p.a_tile_bytes + p.b_tile_bytes);
-  const int num_k_blocks = (int)((p.K + p.k_elems_per_row - 1) / p.k_elems_per_row);
-  // persistent tile scheduler: CTA b handles tiles b, b + gridDim.x, ...; N-tiles are
-  // consecutive so the CTAs resident at one time share A row panels and all of B in L2
-  const long long tiles_n = (p.N + p.block_n - 1) / p.block_n;
-  const long long num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * tiles_n;
-  const long long num_units = num_tiles * p.k_splits;
-  const uint32_t tmem_cols = (uint32_t)(p.acc_stages * p.block_n);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], kThreads - 64);  // every epilogue thread arrives
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    // allocate the accumulator columns (power of two >= 32): acc_stages x block_n
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(&tmem_base_slot)),
-                 "r"(tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a0)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b0)) : "memory");
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        AB_UNIT_DECODE
-        const int m0 = (int)((tile / tiles_n) * BLOCK_M);
-        const int n0 = (int)((tile % tiles_n) * p.block_n);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sbase = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          const int kc = kb * p.k_elems_per_row;
-          load_tile(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
-          load_tile(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0, p.b_mn,
-                    p.b_chunks, p);
-          if (p.nparts == 2) {
-            load_tile(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
-            load_tile(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc, n0,
-                      p.b_mn, p.b_chunks, p);
-          }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t sit = 0;  // accumulator segments issued by this CTA
-      for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        AB_UNIT_DECODE
-        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
-          const int kb1 = min(kb0 + p.seg_kblocks, kb_end);
-          const uint32_t as = sit % (uint32_t)p.acc_stages;
-          const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
-          // wait until the epilogue has drained this accumulator stage
-          mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-          tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tcgen05_fence_after();
-            const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t a_hi = sbase;
-            const uint32_t a_lo = sbase + p.a_tile_bytes;
-            const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
-            const uint32_t b_lo = b_hi + p.b_tile_bytes;
-            const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
-            const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
-#pragma unroll
-            for (int k = 0; k < SW_BYTES / 32; ++k) {  // 32 bytes of K per instruction
-              const uint32_t ka = k * (uint32_t)p.a_kstep, kb_off = k * (uint32_t)p.b_kstep;
-              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-              if (p.nparts == 2) {
-                // small cross terms first, the dominant hi*hi term last
-                umma<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
-                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kb_off, b_lbo), p.idesc, 1u);
-                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, 1u);
-              } else {
-                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
-              }
-            }
-            tcgen05_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
-          tcgen05_commit(&tmem_full_bar[as]);  // segment complete
-        }
-      }
-    }
-  } else {
-    // ================= epilogue (warps 2..9) =================
-    // Two warps share each TMEM lane quarter; each owns half of the tile's columns and
-    // keeps them as FP32 register accumulators across the K segments.
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;    // which half of the columns
-    const int half_n = p.block_n >> 1;
-    const int nchunks = half_n >> 5;     // 32-column chunks: 1, 2 or 4
-    const EpilogueOut eo(p);
-    float acc[kAccRegs];
-    uint32_t sit = 0;
-    for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        AB_UNIT_DECODE
-      const long long m0 = (tile / tiles_n) * BLOCK_M;
-      const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
-      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
-        const uint32_t as = sit % (uint32_t)p.acc_stages;
-        const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
-        mbar_wait(&tmem_full_bar[as], aphase);
-        tcgen05_fence_after();
-        const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
-                               ((uint32_t)(q * 32) << 16);
-        fold_segment(acc, t_acc, nchunks, kb0 == kb_begin);
-        // the segment is in registers: hand the accumulator stage back to the MMA warp
-        tcgen05_fence_before();
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
-                     : "memory");
-      }
-      if (split == 0) eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
-      else eo.store_partial(acc, m0 + q * 32 + lane, n0, nchunks, split);
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(tmem_cols)
-                 : "memory");
-  }
+  gemm_1cta_body<KIND>(map_a0, map_a1, map_b0, map_b1, p);
 }
 
-// ------------------------------------------------------------------ 2-CTA variant
-// cta_group::2: a cluster of two CTAs (same TPC) computes one 256 x 256 tile.  Each
-// CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), the
-// leader CTA issues tcgen05.mma.cta_group::2 (M = 256) that reads both CTAs' shared
-// memory, and each CTA's TMEM receives its 128 accumulator rows.  Per CTA and k-block
-// that is 32 KB from L2 instead of 48 KB: the 1-CTA kernel is L2->SM bandwidth bound
-// (profiles/r01_gemm_bf16_v2_persistent.txt: lts2xbar 13.7 TB/s, tensor pipe 72 %).
-//   * full barriers live in the leader; both CTAs' TMA loads complete_tx on them
-//     (cp.async.bulk.tensor...cta_group::2 with the peer bit of the barrier address
-//     cleared), the leader arms expect_tx for the bytes of both;
-//   * tcgen05.commit.cta_group::2 ... multicast::cluster arrives on the empty /
-//     tmem_full barriers of both CTAs;
-//   * all 256 epilogue threads arrive on the leader's tmem_empty barrier.
-__device__ __forceinline__ void load_tile_2sm(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
-                                              int kc, int mn0, int mn_major, int chunks,
-                                              const GemmParams& p) {
-  if (!mn_major) {
-    tma_load_2d_2sm(dst, map, bar, kc, mn0);
-  } else {
-    for (int c = 0; c < chunks; ++c)
-      tma_load_2d_2sm(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
-  }
-}
-// GemmParams here: block_n = 256 (the pair's N tile), b_tile_bytes = 128 rows * 128 B
-// (this CTA's half), b_chunks = chunks of the half, idesc encodes M = 256, N = 256.
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
@@ -391,165 +60,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
                          const __grid_constant__ CUtensorMap map_b0,
                          const __grid_constant__ CUtensorMap map_b1,
                          const __grid_constant__ GemmParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  __shared__ __align__(8) uint64_t full_bar[8];
-  __shared__ __align__(8) uint64_t empty_bar[8];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ uint32_t tmem_base_slot;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int stage_bytes = p.nparts * (p.a_tile_bytes + p.b_tile_bytes);
-  const int num_k_blocks = (int)((p.K + p.k_elems_per_row - 1) / p.k_elems_per_row);
-  constexpr int TILE_M = 2 * BLOCK_M;
-  const long long tiles_n = (p.N + p.block_n - 1) / p.block_n;
-  const long long num_tiles = ((p.M + TILE_M - 1) / TILE_M) * tiles_n;
-  const long long num_units = num_tiles * p.k_splits;
-  const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const uint32_t tmem_cols = (uint32_t)(p.acc_stages * p.block_n);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 2 * (kThreads - 64));  // the epilogue threads of both CTAs
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(&tmem_base_slot)),
-                 "r"(tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // barriers of both CTAs are initialised before any remote signal
-  tcgen05_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-
-  if (warp == 0) {
-    // ================= TMA producer (one per CTA) =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
-        AB_UNIT_DECODE
-        const int m0 = (int)((tile / tiles_n) * TILE_M) + (int)rank * BLOCK_M;
-        const int n0 = (int)((tile % tiles_n) * p.block_n) + (int)rank * (p.block_n / 2);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sbase = smem + (size_t)stage * stage_bytes;
-          if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
-          const int kc = kb * p.k_elems_per_row;
-          load_tile_2sm(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
-          load_tile_2sm(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0,
-                        p.b_mn, p.b_chunks, p);
-          if (p.nparts == 2) {
-            load_tile_2sm(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn,
-                          p.a_chunks, p);
-            load_tile_2sm(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc,
-                          n0, p.b_mn, p.b_chunks, p);
-          }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer (leader CTA only) =================
-    if (leader && lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t sit = 0;
-      for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
-        AB_UNIT_DECODE
-        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
-          const int kb1 = min(kb0 + p.seg_kblocks, kb_end);
-          const uint32_t as = sit % (uint32_t)p.acc_stages;
-          const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
-          mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-          tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tcgen05_fence_after();
-            const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t a_hi = sbase;
-            const uint32_t a_lo = sbase + p.a_tile_bytes;
-            const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
-            const uint32_t b_lo = b_hi + p.b_tile_bytes;
-            const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
-            const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
-#pragma unroll
-            for (int k = 0; k < SW_BYTES / 32; ++k) {
-              const uint32_t ka = k * (uint32_t)p.a_kstep, kbo = k * (uint32_t)p.b_kstep;
-              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-              if (p.nparts == 2) {
-                umma_2sm<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
-                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kbo, b_lbo), p.idesc, 1u);
-                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, 1u);
-              } else {
-                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
-              }
-            }
-            tcgen05_commit_2sm(&empty_bar[stage]);  // frees the stage in both CTAs
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
-          tcgen05_commit_2sm(&tmem_full_bar[as]);  // both CTAs' epilogues may fold the segment
-        }
-      }
-    }
-  } else {
-    // ================= epilogue (warps 2..9 of both CTAs) =================
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int half_n = p.block_n >> 1;
-    const int nchunks = half_n >> 5;
-    const EpilogueOut eo(p);
-    float acc[kAccRegs];
-    uint32_t sit = 0;
-    for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
-        AB_UNIT_DECODE
-      const long long m0 = (tile / tiles_n) * TILE_M + (long long)rank * BLOCK_M;
-      const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
-      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
-        const uint32_t as = sit % (uint32_t)p.acc_stages;
-        const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
-        mbar_wait(&tmem_full_bar[as], aphase);
-        tcgen05_fence_after();
-        const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
-                               ((uint32_t)(q * 32) << 16);
-        fold_segment(acc, t_acc, nchunks, kb0 == kb_begin);
-        tcgen05_fence_before();
-        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(
-                         smem_u32(&tmem_empty_bar[as]) & kPeerBitMask)
-                     : "memory");
-      }
-      if (split == 0) eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
-      else eo.store_partial(acc, m0 + q * 32 + lane, n0, nchunks, split);
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // nobody signals the peer's barriers / reads its smem after this
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(tmem_cols)
-                 : "memory");
-  }
+  gemm_2cta_body<KIND>(map_a0, map_a1, map_b0, map_b1, p);
 }
-
 // ------------------------------------------------------------------ operand packing
 // out planes are [R, pitch] row-major (K-major): out[r*pitch + c] = f(in[r*s_r + c*s_c]).
 // MODE 0: hi/lo tf32 split (two f32 planes), 1: f32 copy, 2: bf16.
@@ -868,6 +380,36 @@ splitk_reduce_kernel(float* __restrict__ C, long long c_rs, long long c_cs,
   }
 }
 
+// Fused consumer (see ab_gemm_tcgen05_kernel.cuh / codegen/gemm_epilogue.py): the NVRTC
+// module holding the AB_EPILOGUE build of the kernels, its memory operands and the
+// optional bf16 shadow plane.
+struct EpilogueSpec {
+  Module* module = nullptr;
+  int nops = 0;
+  const float* ptr[4] = {};
+  long long rs[4] = {}, cs[4] = {};
+  void* shadow = nullptr;
+  long long shadow_pitch = 0;
+};
+
+int fused_kernel(Module* m, const char* name, cudaKernel_t* out) {
+  auto it = m->named.find(name);
+  if (it != m->named.end()) { *out = it->second; return AB_OK; }
+  cudaKernel_t kern = nullptr;
+  if (cudaLibraryGetKernel(&kern, m->lib, name) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(AB_ERR_INVALID, "fused GEMM module has no kernel %s", name);
+  }
+  cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(AB_ERR_CUDA, "cannot raise the dynamic shared memory limit of %s: %s", name, cudaGetErrorString(e));
+  }
+  m->named[name] = kern;
+  *out = kern;
+  return AB_OK;
+}
+
 int splitk_finish(const GemmParams& p, cudaStream_t st) {
   if (p.k_splits <= 1) return AB_OK;
   const long long work = (p.M * p.N + 3) / 4;
@@ -881,7 +423,8 @@ int splitk_finish(const GemmParams& p, cudaStream_t st) {
 int gemm_run(int precision, long long M, long long N, long long K, float alpha,
              const PackedOperand& A, const PackedOperand& B, float beta, float* C, long long c_rs,
              long long c_cs, cudaStream_t st, const float* Cin = nullptr, long long cin_rs = 0,
-             long long cin_cs = 0, void* splitk_ws = nullptr, size_t splitk_bytes = 0) {
+             long long cin_cs = 0, void* splitk_ws = nullptr, size_t splitk_bytes = 0,
+             const EpilogueSpec* ep = nullptr) {
   if (precision < 0 || precision > 2) return fail(AB_ERR_INVALID, "bad gemm precision %d", precision);
   if (A.precision != precision || B.precision != precision || A.rows != M || B.rows != N ||
       A.k != K || B.k != K)
@@ -925,7 +468,7 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     const int num_kb = (int)((K + p.k_elems_per_row - 1) / p.k_elems_per_row);
     // split-K only with a scratch buffer from the caller (else one K range: still correct)
     p.k_splits = 1;
-    const int want = plan_k_splits(precision, M, N, K);
+    const int want = ep ? 1 : plan_k_splits(precision, M, N, K);  // partial sums cannot be post-processed
     if (want > 1 && splitk_ws && splitk_bytes >= (size_t)(want - 1) * (size_t)M * (size_t)N * sizeof(float) + 256)
       p.k_splits = want;
     p.kb_per_split = (num_kb + p.k_splits - 1) / p.k_splits;
@@ -946,6 +489,18 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
             ((uint32_t)(B.mn_major ? 1 : 0) << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
             ((uint32_t)(tile_m >> 4) << 24);
 
+  if (ep) {
+    if (ep->nops < 0 || ep->nops > 4) return fail(AB_ERR_INVALID, "fused epilogue takes at most 4 operands");
+    for (int k = 0; k < ep->nops; ++k) {
+      if (!ep->ptr[k]) return fail(AB_ERR_INVALID, "null fused-epilogue operand");
+      if (ep->cs[k] == 1 && ((reinterpret_cast<uintptr_t>(ep->ptr[k]) & 15) || (ep->rs[k] & 3)))
+        return fail(AB_ERR_UNSUPPORTED, "fused-epilogue operand %d is not 16-byte aligned", k);
+      p.ep_ptr[k] = ep->ptr[k]; p.ep_rs[k] = ep->rs[k]; p.ep_cs[k] = ep->cs[k];
+    }
+    if (ep->shadow && ((reinterpret_cast<uintptr_t>(ep->shadow) & 7) || (ep->shadow_pitch & 3)))
+      return fail(AB_ERR_UNSUPPORTED, "bf16 shadow plane is not 8-byte aligned");
+    p.shadow = ep->shadow; p.shadow_pitch = ep->shadow_pitch;
+  }
   CUtensorMap ma[2], mb[2];
   int rc;
   for (int i = 0; i < parts; ++i) {
@@ -973,6 +528,14 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (ep) {
+      cudaKernel_t kern;
+      if ((rc = fused_kernel(ep->module, bf16 ? "ab_gemm_ep_2cta_f16" : "ab_gemm_ep_2cta_tf32", &kern))) return rc;
+      void* args[] = {&ma[0], &ma[1], &mb[0], &mb[1], &p};
+      AB_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kern, args));
+      g_launches++;
+      return AB_OK;
+    }
     if (bf16) {
       static bool a1 = false;
       if (!a1) {
@@ -993,6 +556,14 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   }
   const long long num_tiles = ((N + p.block_n - 1) / p.block_n) * ((M + BLOCK_M - 1) / BLOCK_M) * p.k_splits;
   dim3 grid((unsigned)std::min<long long>(num_tiles, sm_count()));  // persistent: one CTA per SM
+  if (ep) {
+    cudaKernel_t kern;
+    if ((rc = fused_kernel(ep->module, bf16 ? "ab_gemm_ep_1cta_f16" : "ab_gemm_ep_1cta_tf32", &kern))) return rc;
+    void* args[] = {&ma[0], &ma[1], &mb[0], &mb[1], &p};
+    AB_CUDA(cudaLaunchKernel((const void*)kern, grid, dim3(kThreads), args, smem, st));
+    g_launches++;
+    return AB_OK;
+  }
   if (bf16) {
     static bool attr1 = false;
     if (!attr1) {
@@ -1075,6 +646,31 @@ extern "C" int ab_gemm_packed(int precision, int64_t m, int64_t n, int64_t k, do
   return ab::gemm_run(precision, m, n, k, (float)alpha, pa, pb, (float)beta, static_cast<float*>(C),
                       c_rs, c_cs, ab::as_stream(stream), static_cast<const float*>(Cin), cin_rs,
                       cin_cs, workspace, workspace_bytes);
+}
+
+extern "C" int ab_gemm_packed_fused(int precision, int64_t m, int64_t n, int64_t k, double alpha,
+                                    const ab_gemm_operand* A, const ab_gemm_operand* B, double beta,
+                                    const void* Cin, int64_t cin_rs, int64_t cin_cs, void* C,
+                                    int64_t c_rs, int64_t c_cs, const ab_gemm_epilogue* ep,
+                                    void* stream) {
+  if (!A || !B || !ep || !ep->module) return ab::fail(AB_ERR_INVALID, "null argument");
+  if (!ab::gemm_tcgen05_eligible(m, n, k))
+    return ab::fail(AB_ERR_UNSUPPORTED, "problem too small for the tensor-core path");
+  ab::PackedOperand pa{{A->plane0, A->plane1}, A->rows, A->k, A->pitch, A->mn_major, A->precision};
+  ab::PackedOperand pb{{B->plane0, B->plane1}, B->rows, B->k, B->pitch, B->mn_major, B->precision};
+  ab::EpilogueSpec spec;
+  spec.module = reinterpret_cast<ab::Module*>(ep->module);
+  spec.nops = ep->n_operands;
+  for (int i = 0; i < 4; ++i) {
+    spec.ptr[i] = static_cast<const float*>(ep->ptr[i]);
+    spec.rs[i] = ep->rs[i];
+    spec.cs[i] = ep->cs[i];
+  }
+  spec.shadow = ep->shadow_bf16;
+  spec.shadow_pitch = ep->shadow_pitch;
+  return ab::gemm_run(precision, m, n, k, (float)alpha, pa, pb, (float)beta, static_cast<float*>(C),
+                      c_rs, c_cs, ab::as_stream(stream), static_cast<const float*>(Cin), cin_rs,
+                      cin_cs, nullptr, 0, &spec);
 }
 
 extern "C" int ab_gemm_packed_workspace_bytes(int precision, int64_t m, int64_t n, int64_t k,

@@ -1,0 +1,575 @@
+// ab_gemm_tcgen05_kernel.cuh — device code of the tcgen05 GEMM (parameters, TMA producer /
+// MMA issuer / epilogue warps, 1-CTA and 2-CTA bodies).  Included by ab_gemm_tcgen05.cu
+// (ahead-of-time kernels with the plain alpha/beta epilogue) and, with AB_EPILOGUE
+// defined, concatenated behind a generated `ab_ep_body` and compiled by NVRTC
+// (codegen/gemm_epilogue.py): the Elemwise node that consumes a Gemm/Dot22 result is then
+// applied to the accumulator registers before the only store.
+#pragma once
+
+struct GemmParams {
+  long long M, N, K;      // K in elements of the packed type
+  float alpha, beta;
+  float* C;
+  long long c_rs, c_cs;
+  const float* Cin;       // beta term source (== C for the in-place Gemm, another buffer otherwise)
+  long long cin_rs, cin_cs;
+  int block_n;            // 64 / 128 / 256
+  int acc_stages;         // TMEM accumulator stages (2 -> epilogue overlaps the next segment)
+  int seg_kblocks;        // k-blocks accumulated inside the tensor core before the epilogue
+                          // folds the partial sum into its FP32 registers (see "segments")
+  int k_splits;           // split-K: work unit = (tile, K range); unit u -> tile u / k_splits
+  int kb_per_split;       // k-blocks per K range
+  float* partial;         // [k_splits - 1][M][N] alpha * (A@B over K range s), s >= 1
+  int stages;
+  int nparts;             // 1, or 2 for the hi/lo split (3 MMAs per k-step)
+  int k_elems_per_row;    // K elements per stage = per 128-byte K-major row: 32 (tf32) / 64 (bf16)
+  int a_tile_bytes, b_tile_bytes;
+  int a_mn, b_mn;         // operand is MN-major
+  int a_chunks, b_chunks; // MN-major: 128-byte MN chunks per tile (tile_rows * elem_size / 128)
+  int chunk_bytes;        // MN-major: k_elems_per_row rows * 128 B
+  int mn_per_chunk;       // MN-major: elements per chunk (128 / elem_size)
+  int a_kstep, b_kstep;   // descriptor advance per MMA K-step: 32 B (K-major) or umma_k rows * 128 B
+  uint32_t idesc;
+  // fused consumer (AB_EPILOGUE builds only; zero otherwise): out = ab_ep_body(v, e0..e3)
+  // with v = alpha*acc + beta*Cin and e_k = ep_ptr[k][row * ep_rs[k] + col * ep_cs[k]]
+  // (stride 0 = broadcast); `shadow` receives the bf16 copy of out as a [M, shadow_pitch]
+  // K-major operand plane for the GEMM that consumes it next
+  const float* ep_ptr[4];
+  long long ep_rs[4], ep_cs[4];
+  void* shadow;
+  long long shadow_pitch;
+};
+
+// one operand tile -> shared memory.  K-major: a single box {128 B of K, tile rows};
+// MN-major: one box {128 B of MN, BLOCK_K rows} per chunk.
+__device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
+                                          int kc, int mn0, int mn_major, int chunks,
+                                          const GemmParams& p) {
+  if (!mn_major) {
+    tma_load_2d(dst, map, bar, kc, mn0);
+  } else {
+    for (int c = 0; c < chunks; ++c)
+      tma_load_2d(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
+  }
+}
+
+// ---------------------------------------------------------------------- segments
+// The tensor core adds each MMA's products into the FP32 accumulator with truncation
+// (round toward zero), a bias that grows linearly with the number of accumulation steps:
+// measured on B200, an unsegmented 3xTF32 K = 4096 product is ~3e-5 from the FP64 result
+// where a true-fp32 sgemm is ~4e-7 (tests/test_gpu_blas.py::test_gemm_long_k_accuracy).
+// So the K loop is cut into segments of seg_kblocks k-blocks: each segment starts a fresh
+// TMEM accumulator, and the epilogue warps add the finished segment into FP32 registers
+// with round-to-nearest while the tensor core works on the next segment in the other
+// TMEM stage.  For precision 0 a segment is 128 K elements (48 truncating steps); the
+// tf32 / bf16 policies keep the whole K loop in one segment.
+constexpr int kAccRegs = 128;  // accumulator columns per epilogue thread (BLOCK_N 256 / 2)
+
+__device__ __forceinline__ void fold_segment(float (&acc)[kAccRegs], uint32_t t_acc, int nchunks,
+                                             bool first) {
+#pragma unroll
+  for (int c = 0; c < kAccRegs / 32; ++c) {
+    if (c < nchunks) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
+      if (first) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __uint_as_float(r[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+      }
+    }
+  }
+}
+
+// C[row, n0 + ...] = alpha * acc + beta * Cin for one thread's row and column range
+struct EpilogueOut {
+  const GemmParams& p;
+  bool vec_ok;
+  __device__ explicit EpilogueOut(const GemmParams& p_) : p(p_) {
+    vec_ok = (p.c_cs == 1) && ((p.c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+             (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
+                                 ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
+  }
+  // split-K: alpha * acc of K range `split` (>= 1) into its [M, N] scratch plane
+  __device__ __forceinline__ void store_partial(const float (&acc)[kAccRegs], long long row,
+                                                long long n0, int nchunks, int split) const {
+    if (row >= p.M) return;
+    float* prow = p.partial + ((long long)(split - 1) * p.M + row) * p.N;
+    const bool vec = (p.N & 3) == 0;
+#pragma unroll
+    for (int c = 0; c < kAccRegs / 32; ++c) {
+      if (c < nchunks) {
+        const long long col0 = n0 + c * 32;
+        if (vec && col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(prow + col0 + j) =
+                make_float4(p.alpha * acc[c * 32 + j], p.alpha * acc[c * 32 + j + 1],
+                            p.alpha * acc[c * 32 + j + 2], p.alpha * acc[c * 32 + j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) prow[col0 + j] = p.alpha * acc[c * 32 + j];
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void store(const float (&acc)[kAccRegs], long long row, long long n0,
+                                        int nchunks) const {
+    if (row >= p.M) return;
+    float* crow = p.C + row * p.c_rs;
+    const float* irow = p.Cin + row * p.cin_rs;
+#pragma unroll
+    for (int c = 0; c < kAccRegs / 32; ++c) {
+      if (c < nchunks) {
+        const long long col0 = n0 + c * 32;
+        if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v;
+            v.x = p.alpha * acc[c * 32 + j];
+            v.y = p.alpha * acc[c * 32 + j + 1];
+            v.z = p.alpha * acc[c * 32 + j + 2];
+            v.w = p.alpha * acc[c * 32 + j + 3];
+            if (p.beta != 0.0f) {
+              const float4 o = *reinterpret_cast<const float4*>(irow + col0 + j);
+              v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
+            }
+#ifdef AB_EPILOGUE
+            {
+              float e[4][4];
+#pragma unroll
+              for (int k = 0; k < AB_EP_NOPS; ++k) {
+                const float* q = p.ep_ptr[k] + row * p.ep_rs[k] + (col0 + j) * p.ep_cs[k];
+                if (p.ep_cs[k] == 1) {
+                  const float4 t = *reinterpret_cast<const float4*>(q);
+                  e[k][0] = t.x; e[k][1] = t.y; e[k][2] = t.z; e[k][3] = t.w;
+                } else {
+                  e[k][0] = q[0]; e[k][1] = q[p.ep_cs[k]]; e[k][2] = q[2 * p.ep_cs[k]]; e[k][3] = q[3 * p.ep_cs[k]];
+                }
+              }
+              v.x = AB_EP_CALL(v.x, 0); v.y = AB_EP_CALL(v.y, 1); v.z = AB_EP_CALL(v.z, 2); v.w = AB_EP_CALL(v.w, 3);
+              if (p.shadow) {
+                uint32_t lo2, hi2;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(v.y), "f"(v.x));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(v.w), "f"(v.z));
+                *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.shadow) + row * p.shadow_pitch + col0 + j) =
+                    make_uint2(lo2, hi2);
+              }
+            }
+#endif
+            *reinterpret_cast<float4*>(crow + col0 + j) = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long col = col0 + j;
+            if (col < p.N) {
+              float v = p.alpha * acc[c * 32 + j];
+              if (p.beta != 0.0f) v += p.beta * irow[col * p.cin_cs];
+#ifdef AB_EPILOGUE
+              {
+                float e[4][1];
+#pragma unroll
+                for (int k = 0; k < AB_EP_NOPS; ++k) e[k][0] = p.ep_ptr[k][row * p.ep_rs[k] + col * p.ep_cs[k]];
+                v = AB_EP_CALL(v, 0);
+                if (p.shadow) {
+                  uint32_t b2;
+                  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b2) : "f"(0.0f), "f"(v));
+                  static_cast<uint16_t*>(p.shadow)[row * p.shadow_pitch + col] = (uint16_t)(b2 & 0xFFFFu);
+                }
+              }
+#endif
+              crow[col * p.c_cs] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+};
+
+// work unit -> (tile, K range); consecutive units of a tile go to different CTAs
+#define AB_UNIT_DECODE                                                          \
+  const long long tile = unit / p.k_splits;                                     \
+  const int split = (int)(unit - tile * p.k_splits);                            \
+  const int kb_begin = split * p.kb_per_split;                                  \
+  const int kb_end = min(kb_begin + p.kb_per_split, num_k_blocks);              \
+  (void)split;
+
+template <int KIND>
+__device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1,
+                                               const CUtensorMap& map_b0, const CUtensorMap& map_b1,
+                                               const GemmParams& p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 for SWIZZLE_128B
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stage_bytes = p.nparts * (p.a_tile_bytes + p.b_tile_bytes);
+  const int num_k_blocks = (int)((p.K + p.k_elems_per_row - 1) / p.k_elems_per_row);
+  // persistent tile scheduler: CTA b handles tiles b, b + gridDim.x, ...; N-tiles are
+  // consecutive so the CTAs resident at one time share A row panels and all of B in L2
+  const long long tiles_n = (p.N + p.block_n - 1) / p.block_n;
+  const long long num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * tiles_n;
+  const long long num_units = num_tiles * p.k_splits;
+  const uint32_t tmem_cols = (uint32_t)(p.acc_stages * p.block_n);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], kThreads - 64);  // every epilogue thread arrives
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    // allocate the accumulator columns (power of two >= 32): acc_stages x block_n
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a0)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b0)) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        AB_UNIT_DECODE
+        const int m0 = (int)((tile / tiles_n) * BLOCK_M);
+        const int n0 = (int)((tile % tiles_n) * p.block_n);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sbase = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          const int kc = kb * p.k_elems_per_row;
+          load_tile(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
+          load_tile(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0, p.b_mn,
+                    p.b_chunks, p);
+          if (p.nparts == 2) {
+            load_tile(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
+            load_tile(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc, n0,
+                      p.b_mn, p.b_chunks, p);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t sit = 0;  // accumulator segments issued by this CTA
+      for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        AB_UNIT_DECODE
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
+          const int kb1 = min(kb0 + p.seg_kblocks, kb_end);
+          const uint32_t as = sit % (uint32_t)p.acc_stages;
+          const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+          // wait until the epilogue has drained this accumulator stage
+          mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t a_hi = sbase;
+            const uint32_t a_lo = sbase + p.a_tile_bytes;
+            const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
+            const uint32_t b_lo = b_hi + p.b_tile_bytes;
+            const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
+            const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
+#pragma unroll
+            for (int k = 0; k < SW_BYTES / 32; ++k) {  // 32 bytes of K per instruction
+              const uint32_t ka = k * (uint32_t)p.a_kstep, kb_off = k * (uint32_t)p.b_kstep;
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (p.nparts == 2) {
+                // small cross terms first, the dominant hi*hi term last
+                umma<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
+                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kb_off, b_lbo), p.idesc, 1u);
+                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, 1u);
+              } else {
+                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
+              }
+            }
+            tcgen05_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          tcgen05_commit(&tmem_full_bar[as]);  // segment complete
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..9) =================
+    // Two warps share each TMEM lane quarter; each owns half of the tile's columns and
+    // keeps them as FP32 register accumulators across the K segments.
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the columns
+    const int half_n = p.block_n >> 1;
+    const int nchunks = half_n >> 5;     // 32-column chunks: 1, 2 or 4
+    const EpilogueOut eo(p);
+    float acc[kAccRegs];
+    uint32_t sit = 0;
+    for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        AB_UNIT_DECODE
+      const long long m0 = (tile / tiles_n) * BLOCK_M;
+      const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
+      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
+        const uint32_t as = sit % (uint32_t)p.acc_stages;
+        const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tcgen05_fence_after();
+        const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
+                               ((uint32_t)(q * 32) << 16);
+        fold_segment(acc, t_acc, nchunks, kb0 == kb_begin);
+        // the segment is in registers: hand the accumulator stage back to the MMA warp
+        tcgen05_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
+                     : "memory");
+      }
+      if (split == 0) eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
+      else eo.store_partial(acc, m0 + q * 32 + lane, n0, nchunks, split);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ 2-CTA variant
+// cta_group::2: a cluster of two CTAs (same TPC) computes one 256 x 256 tile.  Each
+// CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), the
+// leader CTA issues tcgen05.mma.cta_group::2 (M = 256) that reads both CTAs' shared
+// memory, and each CTA's TMEM receives its 128 accumulator rows.  Per CTA and k-block
+// that is 32 KB from L2 instead of 48 KB: the 1-CTA kernel is L2->SM bandwidth bound
+// (profiles/r01_gemm_bf16_v2_persistent.txt: lts2xbar 13.7 TB/s, tensor pipe 72 %).
+//   * full barriers live in the leader; both CTAs' TMA loads complete_tx on them
+//     (cp.async.bulk.tensor...cta_group::2 with the peer bit of the barrier address
+//     cleared), the leader arms expect_tx for the bytes of both;
+//   * tcgen05.commit.cta_group::2 ... multicast::cluster arrives on the empty /
+//     tmem_full barriers of both CTAs;
+//   * all 256 epilogue threads arrive on the leader's tmem_empty barrier.
+__device__ __forceinline__ void load_tile_2sm(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
+                                              int kc, int mn0, int mn_major, int chunks,
+                                              const GemmParams& p) {
+  if (!mn_major) {
+    tma_load_2d_2sm(dst, map, bar, kc, mn0);
+  } else {
+    for (int c = 0; c < chunks; ++c)
+      tma_load_2d_2sm(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
+  }
+}
+// GemmParams here: block_n = 256 (the pair's N tile), b_tile_bytes = 128 rows * 128 B
+// (this CTA's half), b_chunks = chunks of the half, idesc encodes M = 256, N = 256.
+template <int KIND>
+__device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1,
+                                               const CUtensorMap& map_b0, const CUtensorMap& map_b1,
+                                               const GemmParams& p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int stage_bytes = p.nparts * (p.a_tile_bytes + p.b_tile_bytes);
+  const int num_k_blocks = (int)((p.K + p.k_elems_per_row - 1) / p.k_elems_per_row);
+  constexpr int TILE_M = 2 * BLOCK_M;
+  const long long tiles_n = (p.N + p.block_n - 1) / p.block_n;
+  const long long num_tiles = ((p.M + TILE_M - 1) / TILE_M) * tiles_n;
+  const long long num_units = num_tiles * p.k_splits;
+  const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const uint32_t tmem_cols = (uint32_t)(p.acc_stages * p.block_n);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * (kThreads - 64));  // the epilogue threads of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote signal
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (one per CTA) =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
+        AB_UNIT_DECODE
+        const int m0 = (int)((tile / tiles_n) * TILE_M) + (int)rank * BLOCK_M;
+        const int n0 = (int)((tile % tiles_n) * p.block_n) + (int)rank * (p.block_n / 2);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sbase = smem + (size_t)stage * stage_bytes;
+          if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
+          const int kc = kb * p.k_elems_per_row;
+          load_tile_2sm(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
+          load_tile_2sm(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0,
+                        p.b_mn, p.b_chunks, p);
+          if (p.nparts == 2) {
+            load_tile_2sm(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn,
+                          p.a_chunks, p);
+            load_tile_2sm(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc,
+                          n0, p.b_mn, p.b_chunks, p);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t sit = 0;
+      for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
+        AB_UNIT_DECODE
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
+          const int kb1 = min(kb0 + p.seg_kblocks, kb_end);
+          const uint32_t as = sit % (uint32_t)p.acc_stages;
+          const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+          mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t a_hi = sbase;
+            const uint32_t a_lo = sbase + p.a_tile_bytes;
+            const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
+            const uint32_t b_lo = b_hi + p.b_tile_bytes;
+            const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
+            const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
+#pragma unroll
+            for (int k = 0; k < SW_BYTES / 32; ++k) {
+              const uint32_t ka = k * (uint32_t)p.a_kstep, kbo = k * (uint32_t)p.b_kstep;
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (p.nparts == 2) {
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kbo, b_lbo), p.idesc, 1u);
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, 1u);
+              } else {
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
+              }
+            }
+            tcgen05_commit_2sm(&empty_bar[stage]);  // frees the stage in both CTAs
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          tcgen05_commit_2sm(&tmem_full_bar[as]);  // both CTAs' epilogues may fold the segment
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..9 of both CTAs) =================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int half_n = p.block_n >> 1;
+    const int nchunks = half_n >> 5;
+    const EpilogueOut eo(p);
+    float acc[kAccRegs];
+    uint32_t sit = 0;
+    for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
+        AB_UNIT_DECODE
+      const long long m0 = (tile / tiles_n) * TILE_M + (long long)rank * BLOCK_M;
+      const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
+      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
+        const uint32_t as = sit % (uint32_t)p.acc_stages;
+        const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tcgen05_fence_after();
+        const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
+                               ((uint32_t)(q * 32) << 16);
+        fold_segment(acc, t_acc, nchunks, kb0 == kb_begin);
+        tcgen05_fence_before();
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(
+                         smem_u32(&tmem_empty_bar[as]) & kPeerBitMask)
+                     : "memory");
+      }
+      if (split == 0) eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
+      else eo.store_partial(acc, m0 + q * 32 + lane, n0, nchunks, split);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody signals the peer's barriers / reads its smem after this
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(tmem_cols)
+                 : "memory");
+  }
+}
+
+
+#ifdef AB_EPILOGUE
+// NVRTC build: C-linkage entry points (the module is loaded by name from gemm_run)
+extern "C" __global__ void __launch_bounds__(kThreads, 1)
+ab_gemm_ep_1cta_tf32(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
+                     const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
+                     const __grid_constant__ GemmParams p) { gemm_1cta_body<0>(a0, a1, b0, b1, p); }
+extern "C" __global__ void __launch_bounds__(kThreads, 1)
+ab_gemm_ep_1cta_f16(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
+                    const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
+                    const __grid_constant__ GemmParams p) { gemm_1cta_body<1>(a0, a1, b0, b1, p); }
+extern "C" __global__ void __launch_bounds__(kThreads, 1)
+ab_gemm_ep_2cta_tf32(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
+                     const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
+                     const __grid_constant__ GemmParams p) { gemm_2cta_body<0>(a0, a1, b0, b1, p); }
+extern "C" __global__ void __launch_bounds__(kThreads, 1)
+ab_gemm_ep_2cta_f16(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
+                    const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
+                    const __grid_constant__ GemmParams p) { gemm_2cta_body<1>(a0, a1, b0, b1, p); }
+#endif

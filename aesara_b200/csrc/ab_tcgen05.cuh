@@ -2,8 +2,19 @@
 // (ab_gemm_tcgen05.cu, ab_scan_lstm.cu): mbarrier, TMA (cp.async.bulk.tensor),
 // tcgen05.mma / commit / ld, fences, and the SWIZZLE_128B shared-memory descriptor.
 #pragma once
+#ifdef __CUDACC_RTC__
+// NVRTC build (fused-epilogue GEMM, codegen/gemm_epilogue.py): no system headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+struct alignas(64) CUtensorMap_st { unsigned long long opaque[16]; };
+typedef CUtensorMap_st CUtensorMap;
+#else
 #include <cuda.h>
 #include <stdint.h>
+#endif
 
 namespace ab {
 namespace tc {

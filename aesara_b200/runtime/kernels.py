@@ -266,6 +266,19 @@ class PackCache:
             for k in dead:
                 del self._e[k]
 
+    def adopt(self, arr: DeviceArray, buf, pitch):
+        """Register a bf16 plane written by a fused GEMM epilogue as the pack of ``arr``
+        ([rows, k] float32, K-contiguous): the next product reads it without a pack pass."""
+        import weakref
+
+        rows, k = arr.shape
+        key = (arr.ptr, rows, k, arr.strides[0], 0, 2)
+        try:
+            ref = weakref.ref(arr.owner)
+        except TypeError:
+            ref = (lambda o: (lambda: o))(arr.owner)
+        self._e[key] = (ref, buf.data_ptr(), None, pitch, buf)
+
     def operand(self, arr: DeviceArray, rows, k, s_r, s_k, precision):
         import weakref
 
@@ -301,8 +314,10 @@ class PackCache:
 
 
 def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision=0, cache=None,
-         cin: DeviceArray = None):
-    """C <- beta*Cin + alpha*A@B (Cin = C, i.e. in place, unless ``cin`` is given)."""
+         cin: DeviceArray = None, epilogue=None):
+    """C <- beta*Cin + alpha*A@B (Cin = C, i.e. in place, unless ``cin`` is given).
+    ``epilogue`` (a ``gemmfuse.EpilogueRequest``) asks for the fused variant: C <- f(that,
+    operands); it is marked ``applied`` only if the tensor-core path took it."""
     lib = _lib.load()
     m, k = A.shape
     k2, n = B.shape
@@ -312,6 +327,26 @@ def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision
         opa = cache.operand(A, m, k, A.strides[0], A.strides[1], precision)
         opb = cache.operand(B, n, k, B.strides[1], B.strides[0], precision)
         cin_args = (None, 0, 0) if cin is None else (cin.ptr, cin.strides[0], cin.strides[1])
+        if epilogue is not None:
+            ep = _lib.GemmEpilogue()
+            ep.module = epilogue.fusion.handle()
+            ep.n_operands = len(epilogue.operands)
+            for i, a in enumerate(epilogue.operands):
+                ep.ptr[i] = a.ptr
+                ep.rs[i] = 0 if a.shape[0] == 1 else a.strides[0]
+                ep.cs[i] = 0 if a.shape[1] == 1 else a.strides[1]
+            shadow = None
+            if epilogue.want_shadow and C_.strides == (n, 1):
+                shadow = torch.empty(m * n * 2, dtype=torch.uint8, device=A.owner.device)
+                ep.shadow_bf16 = shadow.data_ptr()
+                ep.shadow_pitch = n
+            _lib.check(lib.ab_gemm_packed_fused(precision, m, n, k, float(alpha), C.byref(opa), C.byref(opb),
+                                                float(beta), *cin_args, C_.ptr, C_.strides[0],
+                                                C_.strides[1], C.byref(ep), stream_handle()))
+            epilogue.applied = True
+            if shadow is not None:
+                epilogue.shadow = (shadow, n)
+            return
         need = C.c_size_t()
         _lib.check(lib.ab_gemm_packed_workspace_bytes(precision, m, n, k, C.byref(need)))
         ws = torch.empty(need.value, dtype=torch.uint8, device=A.owner.device) if need.value else None

@@ -119,6 +119,11 @@ SIGNATURES = {
          C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t,
          C.c_void_p],
     ),
+    "ab_gemm_packed_fused": (
+        C.c_int,
+        [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_double,
+         C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p],
+    ),
     "ab_gemm_packed_workspace_bytes": (
         C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]
     ),
@@ -163,6 +168,18 @@ class GemmOperand(C.Structure):
         ("pitch", C.c_int64),
         ("mn_major", C.c_int32),
         ("precision", C.c_int32),
+    ]
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [
+        ("module", C.c_void_p),
+        ("n_operands", C.c_int32),
+        ("ptr", C.c_void_p * 4),
+        ("rs", C.c_int64 * 4),
+        ("cs", C.c_int64 * 4),
+        ("shadow_bf16", C.c_void_p),
+        ("shadow_pitch", C.c_int64),
     ]
 
 

@@ -109,7 +109,12 @@ class ProgramExecutor:
         # stay alive until then
         from .rowfuse import RowFusion
 
+        from .gemmfuse import GemmEpilogueFusion
+
         self._fusions = RowFusion.detect(program)
+        taken = {i for f in self._fusions for i in f.members}
+        self._fusions += GemmEpilogueFusion.detect(program, self._destroys, taken)
+        self._gemm_epilogue = None
         self._fusion_of = {}
         for f in self._fusions:
             for i in f.members:
@@ -504,7 +509,7 @@ def _dot22(ex, i, node, args):
         raise ValueError(f"Shape mismatch: x has {x.shape[1]} cols (and {x.shape[0]} rows) but y has "
                          f"{y.shape[0]} rows (and {y.shape[1]} cols)")
     z = DeviceArray.empty((x.shape[0], y.shape[1]), x.dtype)
-    K.gemm(z, 1.0, x, y, 0.0, ex.precision, cache=ex.pack_cache)
+    K.gemm(z, 1.0, x, y, 0.0, ex.precision, cache=ex.pack_cache, epilogue=ex._gemm_epilogue)
     return z
 
 
@@ -515,7 +520,7 @@ def _dot22scalar(ex, i, node, args):
     if x.shape[1] != y.shape[0]:
         raise ValueError("Shape mismatch in Dot22Scalar")
     z = DeviceArray.empty((x.shape[0], y.shape[1]), x.dtype)
-    K.gemm(z, a, x, y, 0.0, ex.precision, cache=ex.pack_cache)
+    K.gemm(z, a, x, y, 0.0, ex.precision, cache=ex.pack_cache, epilogue=ex._gemm_epilogue)
     return z
 
 
@@ -539,9 +544,9 @@ def _gemm(ex, i, node, args):
         # Gemm{no_inplace}: out = b*z + a*x.y without first copying z (blas.py:1065-1093
         # copies z into the output and calls BLAS with beta): the epilogue reads z directly
         out = DeviceArray.empty((m, n), z.dtype)
-        K.gemm(out, a, x, y, b, ex.precision, cache=ex.pack_cache, cin=z)
+        K.gemm(out, a, x, y, b, ex.precision, cache=ex.pack_cache, cin=z, epilogue=ex._gemm_epilogue)
         return out
-    K.gemm(z, a, x, y, b, ex.precision, cache=ex.pack_cache)
+    K.gemm(z, a, x, y, b, ex.precision, cache=ex.pack_cache, epilogue=ex._gemm_epilogue)
     return z
 
 
@@ -596,7 +601,7 @@ def _dot(ex, i, node, args):
         return out
     if x.ndim == 2 and y.ndim == 2:
         z = DeviceArray.empty((x.shape[0], y.shape[1]), x.dtype)
-        K.gemm(z, 1.0, x, y, 0.0, ex.precision, cache=ex.pack_cache)
+        K.gemm(z, 1.0, x, y, 0.0, ex.precision, cache=ex.pack_cache, epilogue=ex._gemm_epilogue)
         return z
     raise NotImplementedError("Dot with ndim > 2")
 

@@ -407,8 +407,10 @@ def main():
 
     # per-kind device time (average per step) from the per-node CUDA events
     gemm_ms, hbm_ms, other_ms = 0.0, 0.0, 0.0
+    fused_gemm = {f.last for f in ex._fusions if type(f).__name__ == "GemmEpilogueFusion"}
     for i, lst in node_ms.items():
-        op = prog.nodes[i].op
+        # a fused Gemm -> Elemwise region is timed at its last node: it is tensor-pipe work
+        op = "Gemm" if i in fused_gemm else prog.nodes[i].op
         t = float(np.mean(lst))
         if op in ("Dot22", "Gemm", "Dot22Scalar", "Scan"):
             gemm_ms += t
@@ -448,12 +450,16 @@ def main():
     elif spec["n_gemm"]:
         ach = spec["gemm_flops"] / (gemm_ms * 1e-3) / 1e12
         peak = peaks["bf16"] if args.precision == "bf16" else peaks["bf16"] / 2.0
-        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (+operand pack) per Gemm/Dot22 node",
+        n_fused = sum(1 for f in ex._fusions if type(f).__name__ == "GemmEpilogueFusion" and not f.broken)
+        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (+operand pack) per Gemm/Dot22 node"
+                    + (f"; {n_fused} of them with the consuming Elemwise node fused into the epilogue" if n_fused else ""),
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "peak_source": peaks["src"] + ("" if args.precision == "bf16" else "; tf32 = bf16/2 (nominal ratio)"),
                     "traffic": None, "ms_per_step": gemm_ms}
         ach_h = spec["elemwise_bytes"] / (hbm_ms * 1e-3) / 1e9 if hbm_ms else None
-        roofline_hbm = {"bound": "hbm", "kernel": "fused Elemwise + CAReduce nodes",
+        roofline_hbm = {"bound": "hbm", "kernel": "fused Elemwise + CAReduce nodes"
+                        + (f" (the algorithmic bytes of all of them over the time of those not absorbed into a GEMM "
+                           f"epilogue: may exceed the peak, SURVEY 8d)" if n_fused else ""),
                         "achieved": ach_h, "peak": peaks["hbm"], "unit": "GB/s",
                         "frac": ach_h / peaks["hbm"] if ach_h else None,
                         "peak_source": peaks["src"], "traffic": None, "ms_per_step": hbm_ms}

@@ -176,6 +176,25 @@ int ab_gemm_packed(int precision, int64_t m, int64_t n, int64_t k, double alpha,
                    const void* Cin, int64_t cin_rs, int64_t cin_cs, void* C, int64_t c_rs,
                    int64_t c_cs, void* workspace, size_t workspace_bytes, void* stream);
 int ab_gemm_packed_workspace_bytes(int precision, int64_t m, int64_t n, int64_t k, size_t* bytes);
+
+/* Gemm/Dot22 followed by the Elemwise node that consumes it, in one kernel: `module` is
+ * the NVRTC build of the tcgen05 kernels with that node's scalar expression as the
+ * epilogue (aesara_b200/codegen/gemm_epilogue.py); C <- f(beta*Cin + alpha*A@B, e0..e3)
+ * with e_i read at ptr[i][row*rs[i] + col*cs[i]] (stride 0 broadcasts).  `shadow_bf16`
+ * (optional) receives the bf16 copy of the result as a [m, shadow_pitch] plane: the
+ * packed operand of the next product (replaces ab_gemm_pack for that matrix). */
+typedef struct {
+  ab_module* module;
+  int32_t n_operands;
+  const void* ptr[4];
+  int64_t rs[4], cs[4];
+  void* shadow_bf16;
+  int64_t shadow_pitch;
+} ab_gemm_epilogue;
+int ab_gemm_packed_fused(int precision, int64_t m, int64_t n, int64_t k, double alpha,
+                         const ab_gemm_operand* A, const ab_gemm_operand* B, double beta,
+                         const void* Cin, int64_t cin_rs, int64_t cin_cs, void* C, int64_t c_rs,
+                         int64_t c_cs, const ab_gemm_epilogue* ep, void* stream);
 int ab_gemm_tensorcore_eligible(int64_t m, int64_t n, int64_t k);
 
 /* ---- row ops ---------------------------------------------------

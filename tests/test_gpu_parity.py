@@ -241,6 +241,37 @@ def test_mlp_medium_size_fp32_faithful_vs_oracle(rt):
         assert nerr(g, t) < 2e-2, f"bf16 policy out {k}"
 
 
+@pytest.mark.parametrize("precision", [0, 2])
+def test_mlp_gemm_epilogue_fusion_matches_node_by_node(rt, precision):
+    """cfg3 graph, B=1024, H=512: the three Gemm/Dot22 -> Elemwise pairs run as fused
+    tcgen05 kernels (runtime/gemmfuse.py) and give the node-by-node result (the epilogue
+    evaluates the same scalar expression on the same fp32 values; the bf16 shadow plane it
+    writes equals the separate pack, so even the bf16 policy is bit-identical)."""
+    import os
+
+    prog, _, _ = load_case("cfg3_mlp")
+    rng = np.random.default_rng(21)
+    B, H = 1024, 512
+    ins = [rng.standard_normal((B, H)).astype("float32"), rng.standard_normal((B, H)).astype("float32"),
+           (rng.standard_normal((H, H)) / np.sqrt(H)).astype("float32"), (rng.standard_normal(H) * 0.1).astype("float32"),
+           (rng.standard_normal((H, H)) / np.sqrt(H)).astype("float32"), (rng.standard_normal(H) * 0.1).astype("float32")]
+    ex = rt(prog, precision=precision)
+    n_gemm_fusions = sum(type(f).__name__ == "GemmEpilogueFusion" for f in ex._fusions)
+    assert n_gemm_fusions == 3
+    fused = ex(*ins)
+    assert ex.fused_regions_run == 3
+    assert not any(f.broken for f in ex._fusions)
+    os.environ["AB_NO_GEMM_FUSE"] = "1"
+    try:
+        ex_plain = rt(prog, precision=precision)
+    finally:
+        del os.environ["AB_NO_GEMM_FUSE"]
+    assert not ex_plain._fusions
+    plain = ex_plain(*ins)
+    for k, (a, b) in enumerate(zip(fused, plain)):
+        np.testing.assert_array_equal(a, b, err_msg=f"precision {precision} output {k}: fused vs node-by-node")
+
+
 @pytest.mark.parametrize("T,B,H", [(12, 256, 128), (5, 384, 192), (4, 200, 64)])
 def test_lstm_medium_size_vs_oracle_and_graph_replay(rt, T, B, H):
     """cfg4 graph at medium sizes (a full 2-CTA tile, a ragged second 2-CTA tile, and a
