@@ -84,13 +84,52 @@ __device__ __forceinline__ void fold_segment(float (&acc)[kAccRegs], uint32_t t_
 }
 
 // C[row, n0 + ...] = alpha * acc + beta * Cin for one thread's row and column range
+// 8 consecutive floats: one 256-bit access (sm_100 LDG/STG.256) when 32-byte aligned, else
+// two 128-bit ones (16-byte alignment is the caller's precondition)
+// (PTX ISA 8.8 = CUDA 12.9; an older NVRTC, e.g. the 12.8 one bundled with PyTorch that wins
+// the SONAME race in a Python process, only knows 128-bit vectors)
+#if defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ >= 1209)
+#define AB_HAS_V8 1
+#else
+#define AB_HAS_V8 0
+#endif
+__device__ __forceinline__ void ld8(const float* q, float (&o)[8], bool wide) {
+#if AB_HAS_V8
+  if (wide) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+                 : "l"(q));
+  } else
+#endif
+  {
+    const float4 a = *reinterpret_cast<const float4*>(q);
+    const float4 b = *reinterpret_cast<const float4*>(q + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+}
+__device__ __forceinline__ void st8(float* q, const float (&v)[8], bool wide) {
+#if AB_HAS_V8
+  if (wide) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(q), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+  } else
+#endif
+  {
+    *reinterpret_cast<float4*>(q) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(q + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 struct EpilogueOut {
   const GemmParams& p;
-  bool vec_ok;
+  bool vec_ok, wide_out, wide_in;
   __device__ explicit EpilogueOut(const GemmParams& p_) : p(p_) {
     vec_ok = (p.c_cs == 1) && ((p.c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
              (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
                                  ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
+    wide_out = ((p.c_rs & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0);
+    wide_in = ((p.cin_rs & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.Cin) & 31) == 0);
   }
   // split-K: alpha * acc of K range `split` (>= 1) into its [M, N] scratch plane
   __device__ __forceinline__ void store_partial(const float (&acc)[kAccRegs], long long row,
@@ -126,41 +165,50 @@ struct EpilogueOut {
       if (c < nchunks) {
         const long long col0 = n0 + c * 32;
         if (vec_ok && col0 + 32 <= p.N) {
+          // 8 columns per step: one 256-bit access per 32-byte sector where the rows are
+          // 32-byte aligned (each L2 sector is touched by one request instead of two)
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v;
-            v.x = p.alpha * acc[c * 32 + j];
-            v.y = p.alpha * acc[c * 32 + j + 1];
-            v.z = p.alpha * acc[c * 32 + j + 2];
-            v.w = p.alpha * acc[c * 32 + j + 3];
+          for (int j = 0; j < 32; j += 8) {
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = p.alpha * acc[c * 32 + j + t];
             if (p.beta != 0.0f) {
-              const float4 o = *reinterpret_cast<const float4*>(irow + col0 + j);
-              v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
+              float o[8];
+              ld8(irow + col0 + j, o, wide_in);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[t] += p.beta * o[t];
             }
 #ifdef AB_EPILOGUE
             {
-              float e[4][4];
+              float e[4][8];
 #pragma unroll
               for (int k = 0; k < AB_EP_NOPS; ++k) {
                 const float* q = p.ep_ptr[k] + row * p.ep_rs[k] + (col0 + j) * p.ep_cs[k];
                 if (p.ep_cs[k] == 1) {
-                  const float4 t = *reinterpret_cast<const float4*>(q);
-                  e[k][0] = t.x; e[k][1] = t.y; e[k][2] = t.z; e[k][3] = t.w;
+                  ld8(q, e[k], ((reinterpret_cast<uintptr_t>(p.ep_ptr[k]) & 31) == 0) && ((p.ep_rs[k] & 7) == 0));
                 } else {
-                  e[k][0] = q[0]; e[k][1] = q[p.ep_cs[k]]; e[k][2] = q[2 * p.ep_cs[k]]; e[k][3] = q[3 * p.ep_cs[k]];
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) e[k][t] = q[t * p.ep_cs[k]];
                 }
               }
-              v.x = AB_EP_CALL(v.x, 0); v.y = AB_EP_CALL(v.y, 1); v.z = AB_EP_CALL(v.z, 2); v.w = AB_EP_CALL(v.w, 3);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[t] = AB_EP_CALL(v[t], t);
               if (p.shadow) {
-                uint32_t lo2, hi2;
-                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(v.y), "f"(v.x));
-                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(v.w), "f"(v.z));
-                *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.shadow) + row * p.shadow_pitch + col0 + j) =
-                    make_uint2(lo2, hi2);
+                uint32_t h[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[t]) : "f"(v[2 * t + 1]), "f"(v[2 * t]));
+                uint16_t* sp = static_cast<uint16_t*>(p.shadow) + row * p.shadow_pitch + col0 + j;
+                if (((reinterpret_cast<uintptr_t>(p.shadow) & 15) == 0) && ((p.shadow_pitch & 7) == 0)) {
+                  *reinterpret_cast<uint4*>(sp) = make_uint4(h[0], h[1], h[2], h[3]);
+                } else {
+                  *reinterpret_cast<uint2*>(sp) = make_uint2(h[0], h[1]);
+                  *reinterpret_cast<uint2*>(sp + 4) = make_uint2(h[2], h[3]);
+                }
               }
             }
 #endif
-            *reinterpret_cast<float4*>(crow + col0 + j) = v;
+            st8(crow + col0 + j, v, wide_out);
           }
         } else {
 #pragma unroll
