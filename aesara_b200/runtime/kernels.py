@@ -176,17 +176,20 @@ def add_into(dst: DeviceArray, src: DeviceArray):
 class CAReduceKernel:
     _by_key = {}
 
-    def __init__(self, scalar_op, in_dtype, acc_dtype, out_dtype):
-        self.src, self.meta = careduce_source(scalar_op, in_dtype, acc_dtype, out_dtype)
+    def __init__(self, scalar_op, in_dtype, acc_dtype, out_dtype, pre_expr=None):
+        self.src, self.meta = careduce_source(scalar_op, in_dtype, acc_dtype, out_dtype, pre_expr=pre_expr)
         self.out_dtype = np.dtype(out_dtype)
         self._handle = None
 
     @classmethod
-    def get(cls, scalar_op, in_dtype, acc_dtype, out_dtype):
-        key = (scalar_op, str(in_dtype), str(acc_dtype), str(out_dtype))
+    def get(cls, scalar_op, in_dtype, acc_dtype, out_dtype, pre_expr=None):
+        import json
+
+        key = (scalar_op, str(in_dtype), str(acc_dtype), str(out_dtype),
+               json.dumps(pre_expr, sort_keys=True, default=str) if pre_expr is not None else None)
         k = cls._by_key.get(key)
         if k is None:
-            k = cls._by_key[key] = cls(*key)
+            k = cls._by_key[key] = cls(scalar_op, str(in_dtype), str(acc_dtype), str(out_dtype), pre_expr)
         return k
 
     def compile(self):

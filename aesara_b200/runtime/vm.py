@@ -114,6 +114,10 @@ class ProgramExecutor:
         self._fusions = RowFusion.detect(program)
         taken = {i for f in self._fusions for i in f.members}
         self._fusions += GemmEpilogueFusion.detect(program, self._destroys, taken)
+        from .redfuse import ReducePreFusion
+
+        taken = {i for f in self._fusions for i in f.members}
+        self._fusions += ReducePreFusion.detect(program, self._destroys, taken)
         self._gemm_epilogue = None
         self._fusion_of = {}
         for f in self._fusions:

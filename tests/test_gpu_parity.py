@@ -258,14 +258,15 @@ def test_mlp_gemm_epilogue_fusion_matches_node_by_node(rt, precision):
     ex = rt(prog, precision=precision)
     n_gemm_fusions = sum(type(f).__name__ == "GemmEpilogueFusion" for f in ex._fusions)
     assert n_gemm_fusions == 3
+    assert sum(type(f).__name__ == "ReducePreFusion" for f in ex._fusions) == 1  # Sqr -> Sum (the loss)
     fused = ex(*ins)
-    assert ex.fused_regions_run == 3
+    assert ex.fused_regions_run == 4
     assert not any(f.broken for f in ex._fusions)
-    os.environ["AB_NO_GEMM_FUSE"] = "1"
+    os.environ["AB_NO_GEMM_FUSE"] = os.environ["AB_NO_RED_FUSE"] = "1"
     try:
         ex_plain = rt(prog, precision=precision)
     finally:
-        del os.environ["AB_NO_GEMM_FUSE"]
+        del os.environ["AB_NO_GEMM_FUSE"], os.environ["AB_NO_RED_FUSE"]
     assert not ex_plain._fusions
     plain = ex_plain(*ins)
     for k, (a, b) in enumerate(zip(fused, plain)):
