@@ -369,6 +369,77 @@ def test_logreg_row_region_fusion_strided_and_device_scalars(rt):
         assert_matches(g, wv, blas=True, what=f"strided fused logreg out {k}")
 
 
+def test_mlp_full_size_fused_equals_node_by_node(rt):
+    """BASELINE cfg3 size (B=65536, H=4096; no CPU truth at this size): the fused
+    execution (3 GEMM epilogues + Sqr->Sum) is bit-identical to node-by-node execution
+    under the bf16 policy, and row-permuting the batch leaves loss and gradients unchanged
+    up to summation order."""
+    import os
+
+    import torch
+
+    from aesara_b200.runtime.device import DeviceArray
+
+    prog, _, _ = load_case("cfg3_mlp")
+    B, H = 65536, 4096
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.randn(B, H, device="cuda", generator=g)
+    Y = torch.randn(B, H, device="cuda", generator=g)
+    W1 = torch.randn(H, H, device="cuda", generator=g) / H ** 0.5
+    W2 = torch.randn(H, H, device="cuda", generator=g) / H ** 0.5
+    b1 = torch.randn(H, device="cuda", generator=g) * 0.1
+    b2 = torch.randn(H, device="cuda", generator=g) * 0.1
+
+    def run(ex, Xt, Yt):
+        outs = ex(*[DeviceArray.from_torch(t) for t in (Xt, Yt, W1, b1, W2, b2)])
+        return [np.asarray(o) for o in outs]
+
+    ex = rt(prog, precision=2, host_outputs=False)
+    fused = run(ex, X, Y)
+    assert ex.fused_regions_run == 4
+    os.environ["AB_NO_GEMM_FUSE"] = os.environ["AB_NO_RED_FUSE"] = "1"
+    try:
+        plain = run(rt(prog, precision=2, host_outputs=False), X, Y)
+    finally:
+        del os.environ["AB_NO_GEMM_FUSE"], os.environ["AB_NO_RED_FUSE"]
+    for k, (a, b) in enumerate(zip(fused, plain)):
+        np.testing.assert_array_equal(a, b, err_msg=f"full-size MLP output {k}: fused vs node-by-node")
+    perm = torch.randperm(B, device="cuda", generator=g)
+    shuffled = run(ex, X[perm].contiguous(), Y[perm].contiguous())
+    for k, (a, b) in enumerate(zip(shuffled, fused)):
+        assert_matches(a, b, blas=True, rtol=2e-5, what=f"full-size MLP output {k} under a batch permutation")
+
+
+def test_lstm_full_size_fast_path_vs_general_loop(rt):
+    """BASELINE cfg4 size (T=128, B=8192, H=1024): the persistent kernel and the general
+    per-step device loop agree on h_T, c_T (both fp32-faithful; different summation order)."""
+    import os
+
+    import torch
+
+    from aesara_b200.runtime.device import DeviceArray
+
+    prog, _, _ = load_case("cfg4_lstm")
+    T, B, H = 128, 8192, 1024
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(T, B, 4 * H, device="cuda", generator=g)
+    U = torch.randn(H, 4 * H, device="cuda", generator=g) / H ** 0.5
+    z = torch.zeros(B, H, device="cuda")
+    ins = [DeviceArray.from_torch(t) for t in (x, z, z.clone(), U)]
+    ex = rt(prog, host_outputs=False)
+    fast = [np.asarray(o) for o in ex(*ins)]
+    scan_idx = [i for i, n in enumerate(prog.nodes) if n.op == "Scan"][0]
+    assert ex._state[scan_idx]["runner"].used_fast_path
+    os.environ["AB_SCAN_NO_FAST"] = "1"
+    try:
+        general = [np.asarray(o) for o in rt(prog, host_outputs=False)(*ins)]
+    finally:
+        del os.environ["AB_SCAN_NO_FAST"]
+    for k, (a, b) in enumerate(zip(fast, general)):
+        assert np.isfinite(a).all()
+        assert_matches(a, b, blas=True, rtol=2e-5, what=f"full-size LSTM output {k}: persistent kernel vs general loop")
+
+
 def test_gemm_full_size_tile_independence(rt):
     """BASELINE-size GEMM property (no CPU truth at this size): rows of a
     [16384, 4096] x [4096, 4096] product equal the product of the row subset, for
