@@ -124,3 +124,61 @@ def test_lstm_fast_path_matcher_rejects_other_recurrences():
                 if s["op"] == "tanh":
                     s["op"] = "sigmoid"
     assert r.lstm.match(256, 128) is False
+
+
+# ---------------------------------------------------------------- executor-level regions
+def test_fusion_regions_detected_on_the_committed_programs():
+    """Region detection is host logic over the lowered program: cfg5 has one row region
+    (Gemv -> 3 Elemwise -> 2 Sum + Gemv(X.T)), cfg3 three Gemm->Elemwise pairs and one
+    Sqr->Sum; graphs whose GEMM result has several consumers are left alone."""
+    from aesara_b200.runtime.vm import ProgramExecutor
+    from tests._cases import load_case
+
+    prog, _, _ = load_case("cfg5_logreg")
+    ex = ProgramExecutor(prog)
+    (f,) = ex._fusions
+    assert type(f).__name__ == "RowFusion"
+    ops = [prog.nodes[i].op for i in f.members]
+    assert ops.count("Gemv") == 2 and ops.count("CAReduce") == 2 and ops.count("Elemwise") == 3
+    assert f.last == max(f.members) and f.alpha1 == 1.0 and f.alpha2 == 1.0
+    assert all(not ex._free_after[i] for i in f.members if i != f.last)  # operands stay alive
+
+    prog, _, _ = load_case("cfg3_mlp")
+    ex = ProgramExecutor(prog)
+    kinds = sorted(type(f).__name__ for f in ex._fusions)
+    assert kinds == ["GemmEpilogueFusion"] * 3 + ["ReducePreFusion"]
+    for f in ex._fusions:
+        if type(f).__name__ == "GemmEpilogueFusion":
+            g, e = f.members
+            assert prog.nodes[g].op in ("Dot22", "Gemm") and prog.nodes[e].op == "Elemwise"
+            assert prog.nodes[e].inputs[f.acc_input] == prog.nodes[g].outputs[0]
+    shadows = [f.shadow_consumer for f in ex._fusions if type(f).__name__ == "GemmEpilogueFusion"]
+    assert shadows.count(True) == 2  # h and dpre feed later products; (h@W2 - Y) + b2 does not
+
+    for name in ("softmax_classifier", "blas_dot22_layouts", "cfg4_lstm", "cfg1_readme"):
+        prog, _, _ = load_case(name)
+        assert not [f for f in ProgramExecutor(prog)._fusions if type(f).__name__ == "RowFusion"]
+
+
+def test_fused_kernel_sources_compile_for_sm100a():
+    """NVRTC (no GPU needed): the row-region kernel, the tcgen05 GEMM with a generated
+    epilogue, and the reduction with a fused pre-map."""
+    from aesara_b200.runtime.vm import ProgramExecutor
+    from tests._cases import load_case
+
+    for name in ("cfg5_logreg", "cfg3_mlp", "careduce_big_1d"):
+        prog, _, _ = load_case(name)
+        ex = ProgramExecutor(prog)
+        assert ex._fusions
+        for f in ex._fusions:
+            assert f.compile_all() == 1
+
+
+def test_regions_can_be_switched_off(monkeypatch):
+    from aesara_b200.runtime.vm import ProgramExecutor
+    from tests._cases import load_case
+
+    prog, _, _ = load_case("cfg3_mlp")
+    for var in ("AB_NO_GEMM_FUSE", "AB_NO_RED_FUSE", "AB_NO_ROWFUSE"):
+        monkeypatch.setenv(var, "1")
+    assert not ProgramExecutor(prog)._fusions
