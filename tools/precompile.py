@@ -18,9 +18,11 @@ def main():
     kerns = list(K.ElemwiseKernel._by_key.values()) + list(K.CAReduceKernel._by_key.values())
     for dt in ("float32", "float64", "int64", "int32", "int8", "bool"):
         kerns.append(K._identity_kernel(dt))
+    fusions = [f for ex in exs for f in ex._fusions]  # row-region / GEMM-epilogue / map-reduce kernels
     with ThreadPoolExecutor(8) as pool:
         list(pool.map(lambda k: k.compile(), kerns))
-    print(f"compiled {len(kerns)} modules in {time.time() - t:.1f}s")
+        list(pool.map(lambda f: f.compile_all(), fusions))
+    print(f"compiled {len(kerns)} modules + {len(fusions)} fused regions in {time.time() - t:.1f}s")
 
 
 if __name__ == "__main__":
