@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpu_trip_multi2.sh N   (run under gpurun --gpus N): benches only, short
+# usage: gpu_scaling.sh N   (run under gpurun --gpus N): benches only, short
 set -u
 N=${1:-2}
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
