@@ -475,7 +475,9 @@ def main():
     # of the same command (profiles/; cold-cache, serialised capture)
     tsrc = None
     if spec["name"] == "mlp" and args.precision == "bf16":
-        tsrc = ("r01_gemm_bf16_v4_8warp_epilogue.txt", "gemm_tcgen05_2cta_kernel")
+        fused = any(type(f).__name__ == "GemmEpilogueFusion" and not f.broken for f in ex._fusions)
+        tsrc = (("r01_gemm_fused_epilogue.txt", "ab_gemm_ep_2cta_f16") if fused
+                else ("r01_gemm_bf16_v4_8warp_epilogue.txt", "gemm_tcgen05_2cta_kernel"))
     elif spec["name"] == "logreg" and ex.fused_regions_run > 0:
         tsrc = ("r01_rowfused_logreg.txt", "ab_rowfused")
     elif spec["name"] == "elemwise":
