@@ -193,6 +193,71 @@ def _():
     return [a, b, x], [a * x + a, at.exp(b) * b, a + b, x.sum() * a], [np.float32(1.5), np.float64(-0.25), rnd(33)]
 
 
+# ---------------------------------------------------------------- random Elemwise graphs
+# Seeded random compositions over mixed dtypes: the reference's type promotion, fusion and
+# in-place passes decide the Composite bodies; values stay in domains where C and CUDA are
+# both defined (non-zero integer divisors, bounded float -> int casts).
+def _fuzz_graph(seed, n_outs=7, n_elems=193):
+    r = np.random.default_rng(seed)
+    f32, f64 = at.fvector("f32"), at.dvector("f64")
+    i32, i64, i8, u8 = at.ivector("i32"), at.lvector("i64"), at.bvector("i8"), at.vector("u8", dtype="uint8")
+    bo = at.vector("bo", dtype="bool")
+    floats, ints = [f32, f64], [i32, i64, i8, u8]
+    pool_f, pool_i, pool_b = list(floats), list(ints), [bo]
+
+    def pick(pool):
+        return pool[int(r.integers(len(pool)))]
+
+    unary_f = [at.tanh, at.sigmoid, abs, at.neg, at.sqr, at.floor, at.ceil, lambda t: at.exp(at.tanh(t)),
+               lambda t: at.log(abs(t) + 1), lambda t: at.sqrt(abs(t)), at.sgn, lambda t: at.softplus(t),
+               lambda t: at.log1p(abs(t)), lambda t: at.expm1(at.tanh(t)), at.sin, at.cos, at.arctan,
+               lambda t: at.round(t)]
+    binary_f = [lambda a, b: a + b, lambda a, b: a - b, lambda a, b: a * b, lambda a, b: a / (abs(b) + 0.5),
+                at.maximum, at.minimum, lambda a, b: a // (abs(b) + 1), lambda a, b: a % (abs(b) + 1),
+                lambda a, b: at.switch(at.gt(a, b), a, b * 2), lambda a, b: at.arctan2(a, abs(b) + 0.1),
+                lambda a, b: abs(a) ** at.tanh(b)]
+    binary_i = [lambda a, b: a + b, lambda a, b: a - b, lambda a, b: a * b, lambda a, b: a // (abs(b) + 1),
+                lambda a, b: a % (abs(b) + 1), lambda a, b: a & b, lambda a, b: a | b, lambda a, b: a ^ b,
+                at.maximum, at.minimum, lambda a, b: at.switch(at.lt(a, b), a, b)]
+    unary_i = [abs, at.neg, lambda t: ~t, at.sgn, lambda t: at.cast(t, "int8"), lambda t: at.cast(t, "int64"),
+               lambda t: at.cast(t, "uint8"), lambda t: at.cast(t, "int16"), lambda t: at.cast(t, "float32")]
+    cmp_ops = [at.lt, at.gt, at.le, at.ge, at.eq, at.neq]
+    for _ in range(int(r.integers(14, 22))):
+        kind = r.random()
+        if kind < 0.40:
+            a = pick(pool_f)
+            b = pick(pool_f + pool_i) if r.random() < 0.4 else pick(pool_f)
+            pool_f.append(pick(binary_f)(a, b))
+        elif kind < 0.58:
+            pool_f.append(pick(unary_f)(pick(pool_f)))
+        elif kind < 0.74:
+            pool_i.append(pick(binary_i)(pick(pool_i), pick(pool_i)))
+        elif kind < 0.84:
+            v = pick(unary_i)(pick(pool_i))
+            (pool_f if "float" in v.dtype else pool_i).append(v)
+        elif kind < 0.92:
+            a, b = (pick(pool_f), pick(pool_f)) if r.random() < 0.5 else (pick(pool_i), pick(pool_i))
+            pool_b.append(pick(cmp_ops)(a, b))
+        elif kind < 0.96:
+            pool_b.append(pick([lambda a, b: a & b, lambda a, b: a | b, lambda a, b: a ^ b])(pick(pool_b), pick(pool_b)))
+        else:
+            # bounded float -> int cast, then back into the integer pool
+            pool_i.append(at.cast(at.floor(at.tanh(pick(pool_f)) * 100), pick(["int32", "int64", "int16"])))
+    cands = pool_f[2:] + pool_i[4:] + pool_b[1:]
+    idx = r.permutation(len(cands))[:n_outs]
+    outs = [cands[int(k)] for k in idx]
+    vals = [rnd(n_elems, "float32"), rnd(n_elems, "float64"), rnd(n_elems, "int32"), rnd(n_elems, "int64"),
+            rnd(n_elems, "int8"), rnd(n_elems, "uint8"), rnd(n_elems, "bool")]
+    return [f32, f64, i32, i64, i8, u8, bo], outs, vals
+
+
+for _seed in range(8):
+    def _make(seed=_seed):
+        return _fuzz_graph(1000 + seed)
+
+    CASES[f"ew_fuzz_{_seed}"] = _make
+
+
 # ---------------------------------------------------------------- CAReduce tables
 # axes table of tests/tensor/test_elemwise.py:412-428 (TestCAReduce)
 @case("careduce_sum_axes")
