@@ -225,3 +225,80 @@ extern "C" int ab_scatter_rows(int dtype, int idx_dtype, int set_instead_of_inc,
   if (rc) return rc;
   return check ? read_and_clear_flag(flag, st, "AdvancedIncSubtensor1") : AB_OK;
 }
+
+
+// ---- several index vectors -> one flat row index (AdvancedSubtensor, subtensor.py:2577) ----
+// flat[r] = ravel(idx_0[r], ..., idx_{k-1}[r]) over dims d_0..d_{k-1}; negative indices wrap,
+// an out-of-range index sets the error flag (flat = 0 keeps the following gather in bounds).
+namespace {
+struct RavelParams {
+  const long long* idx[4];
+  long long stride[4];   // element strides (0 = a length-1 index vector broadcast over r)
+  long long dims[4];
+  int k;
+  long long n;
+};
+__global__ void __launch_bounds__(256)
+ravel_index_kernel(const __grid_constant__ RavelParams p, long long* __restrict__ out, int* flag) {
+  const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (r >= p.n) return;
+  long long flat = 0;
+  bool ok = true;
+  for (int j = 0; j < p.k; ++j) {
+    long long v = p.idx[j][r * p.stride[j]];
+    if (v < 0) v += p.dims[j];
+    ok = ok && v >= 0 && v < p.dims[j];
+    flat = flat * p.dims[j] + v;
+  }
+  if (!ok) { *flag = 1; flat = 0; }
+  out[r] = flat;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+arange_kernel(T start, T step, long long n, T* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = (T)(start + (T)i * step);
+}
+}  // namespace
+
+extern "C" int ab_ravel_index(int k, const void* const* idx, const int64_t* idx_stride,
+                              const int64_t* dims, int64_t n, void* out, int check, void* stream) {
+  if (k < 1 || k > 4) return fail(AB_ERR_UNSUPPORTED, "ab_ravel_index takes 1..4 index vectors, got %d", k);
+  if (n <= 0) return AB_OK;
+  cudaStream_t st = as_stream(stream);
+  int* flag = error_flag();
+  if (!flag) return fail(AB_ERR_CUDA, "cannot allocate the index-error flag");
+  RavelParams p{};
+  p.k = k;
+  p.n = n;
+  for (int j = 0; j < k; ++j) {
+    p.idx[j] = static_cast<const long long*>(idx[j]);
+    p.stride[j] = idx_stride[j];
+    p.dims[j] = dims[j];
+  }
+  ravel_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, static_cast<long long*>(out), flag);
+  g_launches++;
+  AB_CUDA(cudaGetLastError());
+  return check ? read_and_clear_flag(flag, st, "AdvancedSubtensor") : AB_OK;
+}
+
+// ARange (tensor/basic.py:3011): out[i] = start + i * step, evaluated in the output dtype
+extern "C" int ab_arange(int dtype, double start, double step, int64_t start_i, int64_t step_i,
+                         int64_t n, void* out, void* stream) {
+  if (n <= 0) return AB_OK;
+  cudaStream_t st = as_stream(stream);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  switch (dtype) {
+    case AB_F32: arange_kernel<float><<<blocks, 256, 0, st>>>((float)start, (float)step, n, static_cast<float*>(out)); break;
+    case AB_F64: arange_kernel<double><<<blocks, 256, 0, st>>>(start, step, n, static_cast<double*>(out)); break;
+    case AB_I64: arange_kernel<long long><<<blocks, 256, 0, st>>>(start_i, step_i, n, static_cast<long long*>(out)); break;
+    case AB_I32: arange_kernel<int><<<blocks, 256, 0, st>>>((int)start_i, (int)step_i, n, static_cast<int*>(out)); break;
+    case AB_I16: arange_kernel<short><<<blocks, 256, 0, st>>>((short)start_i, (short)step_i, n, static_cast<short*>(out)); break;
+    case AB_I8: arange_kernel<signed char><<<blocks, 256, 0, st>>>((signed char)start_i, (signed char)step_i, n, static_cast<signed char*>(out)); break;
+    case AB_U8: arange_kernel<unsigned char><<<blocks, 256, 0, st>>>((unsigned char)start_i, (unsigned char)step_i, n, static_cast<unsigned char*>(out)); break;
+    default: return fail(AB_ERR_UNSUPPORTED, "ARange: dtype code %d", dtype);
+  }
+  g_launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB_OK;
+}

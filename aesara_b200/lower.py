@@ -459,6 +459,36 @@ def _l_advincsub1(op, apply):
     return "AdvancedIncSubtensor1", {"inplace": bool(op.inplace), "set": bool(op.set_instead_of_inc)}
 
 
+def _int_vector_indices(apply, first):
+    """AdvancedSubtensor / AdvancedIncSubtensor are lowered for the integer-array form only:
+    one integer vector (or 0-d integer) per leading dimension of x, no slices / newaxis /
+    boolean masks (subtensor.py:2577-2805)."""
+    for v in apply.inputs[first:]:
+        t = v.type
+        if not hasattr(t, "dtype") or not hasattr(t, "ndim") or str(t.dtype)[:3] not in ("int", "uin") or t.ndim > 1:
+            raise UnsupportedOp(
+                f"B200 backend: {apply.op} is implemented for integer index vectors only "
+                f"(got an index of type {t}); there is no CPU fallback for tensor work")
+    return len(apply.inputs) - first
+
+
+@lowers("AdvancedSubtensor")
+def _l_advsub(op, apply):
+    return "AdvancedSubtensor", {"n_idx": _int_vector_indices(apply, 1)}
+
+
+@lowers("AdvancedIncSubtensor")
+def _l_advincsub(op, apply):
+    return "AdvancedIncSubtensor", {"n_idx": _int_vector_indices(apply, 2), "inplace": bool(op.inplace),
+                                    "set": bool(op.set_instead_of_inc),
+                                    "ignore_duplicates": bool(getattr(op, "ignore_duplicates", False))}
+
+
+@lowers("ARange")
+def _l_arange(op, apply):
+    return "ARange", {"dtype": str(op.dtype)}
+
+
 @lowers("Join")
 def _l_join(op, apply):
     return "Join", {}

@@ -101,6 +101,15 @@ SIGNATURES = {
         [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
          C.c_int64, C.POINTER(C.c_size_t)],
     ),
+    "ab_ravel_index": (
+        C.c_int,
+        [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64,
+         C.c_void_p, C.c_int, C.c_void_p],
+    ),
+    "ab_arange": (
+        C.c_int,
+        [C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p],
+    ),
     "ab_kernel_launch": (
         C.c_int,
         [C.c_void_p, C.c_char_p, C.c_uint, C.c_uint, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p],

@@ -812,6 +812,104 @@ def _advsub1(ex, i, node, args):
     return out
 
 
+def _ravel_indices(ex, i, node, x, idx_args):
+    """k integer index vectors over the k leading dims of x -> (flat int64 row index on the
+    device, x viewed as [prod(dims), *rest]) (``ab_ravel_index``)."""
+    import ctypes as C
+
+    from . import lib as _lib
+    from .device import stream_handle
+
+    k = len(idx_args)
+    if k > x.ndim:
+        raise IndexError(f"too many indices for array: array is {x.ndim}-dimensional, but {k} were indexed")
+    idxs = []
+    for a in idx_args:
+        a = a if isinstance(a, DeviceArray) else ex.dev(np.atleast_1d(np.asarray(a)))
+        if a.ndim == 0:
+            a = a.reshape_view((1,))
+        if a.ndim != 1 or a.dtype.kind not in "iu":
+            raise IndexError("arrays used as indices must be integer vectors")
+        if a.dtype != np.int64:
+            a64 = DeviceArray.empty(a.shape, "int64")
+            K.copy_into(a64, a)
+            a = a64
+        idxs.append(a)
+    n = max(a.shape[0] for a in idxs)
+    for a in idxs:
+        if a.shape[0] not in (1, n):
+            raise IndexError("shape mismatch: indexing arrays could not be broadcast together")
+    dims = x.shape[:k]
+    flat = DeviceArray.empty((n,), "int64")
+    ptrs = (C.c_void_p * k)(*[a.ptr for a in idxs])
+    strides = (C.c_int64 * k)(*[0 if a.shape[0] == 1 and n != 1 else a.strides[0] for a in idxs])
+    cd = (C.c_int64 * k)(*dims)
+    try:
+        _lib.check(_lib.load().ab_ravel_index(k, ptrs, strides, cd, n, flat.ptr, 1, stream_handle()))
+    except _lib.AbError as e:
+        if e.code == 4:
+            raise IndexError(str(e)) from None
+        raise
+    rows = 1
+    for d in dims:
+        rows *= d
+    return flat, rows, n
+
+
+@_op("AdvancedSubtensor")
+def _advsub(ex, i, node, args):
+    x, *idx = args
+    if is_host(x) and all(is_host(a) for a in idx):
+        return np.asarray(x)[tuple(np.asarray(a) for a in idx)]
+    (x,) = _as_dev_inputs(ex, i, Node("AdvancedSubtensor", [node.inputs[0]], []), [x])
+    k = len(idx)
+    xc = _as_c_contiguous(x)
+    flat, rows, n = _ravel_indices(ex, i, node, xc, idx)
+    rest = xc.shape[k:]
+    x2 = xc.reshape_view((rows,) + rest)
+    out = _EXEC["AdvancedSubtensor1"](ex, i, Node("AdvancedSubtensor1", node.inputs[:2], node.outputs), [x2, flat])
+    return out
+
+
+@_op("AdvancedIncSubtensor")
+def _advincsub(ex, i, node, args):
+    p = node.params
+    xa, ya, *idx = args
+    x, y = _as_dev_inputs(ex, i, Node("AdvancedIncSubtensor", node.inputs[:2], []), [xa, ya])
+    k = len(idx)
+    if not p["inplace"] or is_host(xa) or not x.is_c_contiguous():
+        x = K.contiguous_copy(x)
+    flat, rows, n = _ravel_indices(ex, i, node, x, idx)
+    rest = x.shape[k:]
+    x2 = x.reshape_view((rows,) + rest)
+    sub = Node("AdvancedIncSubtensor1", node.inputs[:3], node.outputs,
+               {"inplace": True, "set": p["set"]})
+    _EXEC["AdvancedIncSubtensor1"](ex, i, sub, [x2, y, flat])
+    return x
+
+
+@_op("ARange")
+def _arange(ex, i, node, args):
+    from ..ir import DTYPE_CODE
+    from . import lib as _lib
+    from .device import stream_handle
+
+    vals = []
+    for a in args:
+        vals.append(np.asarray(a.to_numpy() if isinstance(a, DeviceArray) else a).item())
+    start, stop, step = vals
+    dt = np.dtype(node.params["dtype"])
+    host = np.arange(start, stop, step, dtype=dt) if (abs(stop - start) / max(abs(step), 1e-300)) <= host_eval.MAX_HOST_ELEMS else None
+    if host is not None:
+        return host
+    n = len(range(int(start), int(stop), int(step))) if dt.kind in "iu" else int(np.ceil((stop - start) / step))
+    n = max(n, 0)
+    out = DeviceArray.empty((n,), dt)
+    _lib.check(_lib.load().ab_arange(DTYPE_CODE[dt.name], float(start), float(step), int(start), int(step),
+                                     n, out.ptr, stream_handle()))
+    return out
+
+
 @_op("AdvancedIncSubtensor1")
 def _advincsub1(ex, i, node, args):
     from ..ir import DTYPE_CODE

@@ -224,6 +224,18 @@ int ab_scatter_rows(int dtype, int idx_dtype, int set_instead_of_inc, void* x,
                     int64_t idx_stride, int64_t n_idx, const void* y, int64_t y_row_stride,
                     int64_t y_col_stride, int check, void* stream);
 
+/* AdvancedSubtensor / AdvancedIncSubtensor with one integer vector per leading dimension
+ * (x[i, j], aesara/tensor/subtensor.py:2577/2727): ab_ravel_index folds the k int64 index
+ * vectors (element strides idx_stride, 0 broadcasts a length-1 vector) over dims[0..k) into
+ * one flat int64 row index, wrapping negative values; the gather / scatter is then
+ * ab_take_rows / ab_scatter_rows over x viewed as [prod(dims), inner]. */
+int ab_ravel_index(int k, const void* const* idx, const int64_t* idx_stride, const int64_t* dims,
+                   int64_t n, void* out, int check, void* stream);
+/* ARange (aesara/tensor/basic.py:3011): out[i] = start + i*step in dtype (floats use
+ * start/step, integers start_i/step_i). */
+int ab_arange(int dtype, double start, double step, int64_t start_i, int64_t step_i, int64_t n,
+              void* out, void* stream);
+
 /* ---- Scan fast path: LSTM-cell recurrence as one persistent kernel -----------------
  * (aesara/scan/op.py:637; inner graph of SURVEY App. A.4).  For t in [0,T):
  *   pre = x[t] + h_{t-1} @ U;  c_t = sigmoid(pre_f)*c_{t-1} + sigmoid(pre_i)*tanh(pre_g);

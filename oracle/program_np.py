@@ -270,6 +270,32 @@ def _alloc(node, args, prog):  # aesara/tensor/basic.py:1389 (perform :1468)
     return np.array(np.broadcast_to(v, shape))
 
 
+@_h("AdvancedSubtensor")
+def _advsub(node, args, prog):  # aesara/tensor/subtensor.py:2577 (perform :2641)
+    x, *idx = args
+    return np.asarray(x)[tuple(np.asarray(i) for i in idx)]
+
+
+@_h("AdvancedIncSubtensor")
+def _advincsub(node, args, prog):  # aesara/tensor/subtensor.py:2727 (perform :2768)
+    x, y, *idx = args
+    out = np.array(x, copy=True)
+    idx = tuple(np.asarray(i) for i in idx)
+    if node.params["set"]:
+        out[idx] = y
+    elif node.params.get("ignore_duplicates"):
+        out[idx] += y
+    else:
+        np.add.at(out, idx, y)
+    return out
+
+
+@_h("ARange")
+def _arange(node, args, prog):  # aesara/tensor/basic.py:2867 (perform :2937)
+    start, stop, step = (np.asarray(a).item() for a in args)
+    return np.arange(start, stop, step, dtype=node.params["dtype"])
+
+
 @_h("BroadcastTo")
 def _broadcast_to(node, args, prog):  # aesara/tensor/extra_ops.py:1613 (perform :1652)
     v, *shape = args

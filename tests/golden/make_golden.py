@@ -550,6 +550,39 @@ def _():
                                          rnd((10, 3, 5)), rnd(12, "int64")]
 
 
+@case("classifier_int_labels")
+def _():
+    from aesara.tensor.special import log_softmax
+
+    x, W = at.fmatrix("x"), at.fmatrix("W")
+    y = at.lvector("y")
+    logits = x @ W
+    lp = log_softmax(logits, axis=1)
+    loss = -at.mean(lp[at.arange(y.shape[0]), y])          # ARange + AdvancedSubtensor
+    g = aesara.grad(loss, W)                               # AdvancedIncSubtensor in the backward pass
+    acc = at.mean(at.eq(at.argmax(logits, axis=1), y))
+    return [x, W, y], [loss, g, acc], [rnd((200, 48)), rnd((48, 10), "float32", -0.5, 0.5),
+                                       RNG.integers(0, 10, size=200).astype("int64")]
+
+
+@case("adv_index_pairs")
+def _():
+    x = at.fmatrix("x")
+    t = at.ftensor3("t")
+    i, j = at.lvector("i"), at.lvector("j")
+    k32 = at.ivector("k32")
+    v = at.fvector("v")
+    n = at.lscalar("n")
+    outs = [x[i, j], t[i, j], t[i, j][:, ::2] * 2, at.inc_subtensor(x[i, j], v), at.set_subtensor(x[i, j], 0.5),
+            at.inc_subtensor(t[i, j], 1.0), at.inc_subtensor(x[k32, k32], v[:k32.shape[0]] * 2),
+            at.arange(n) * 2, at.arange(2, n, 3), at.arange(0, n, 1, dtype="float32") / 4, at.arange(n)[::-1] + i[:1],
+            x[at.arange(x.shape[0]), at.argmax(x, axis=1)], at.arange(300, dtype="int32").sum() + n]
+    iv = np.array([0, 3, 3, -1, 2, 0, 3], "int64")
+    jv = np.array([1, 4, 4, -2, 0, 1, 4], "int64")
+    return [x, t, i, j, k32, v, n], outs, [rnd((4, 5)), rnd((4, 5, 6)), iv, jv, np.array([1, 1, 2], "int32"),
+                                           rnd(7), np.int64(11)]
+
+
 @case("join_split_reshape")
 def _():
     a, b, c = at.fmatrix("a"), at.fmatrix("b"), at.fmatrix("c")
@@ -562,7 +595,7 @@ def _():
     return [a, b, c, v], outs, [rnd((4, 6)), rnd((3, 6)), rnd((4, 1)), rnd(5, "int64")]
 
 
-PY_LINKER_CASES = {"indexing_embedding"}
+PY_LINKER_CASES = {"indexing_embedding", "adv_index_pairs", "classifier_int_labels"}
 
 
 def main(names):
