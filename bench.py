@@ -471,6 +471,13 @@ def main():
                     "ms_per_step": hbm_ms}
         roofline_hbm = None
 
+    if roofline.get("bound") == "tensor" and args.precision == "fp32":
+        # fp32-faithful products issue three TF32 MMAs each: the pipe-level ceiling for the
+        # algorithmic flops is a third of the TF32 peak
+        roofline["mma_per_product"] = 3
+        roofline["ceiling_3xtf32"] = roofline["peak"] / 3.0
+        roofline["frac_of_3xtf32_ceiling"] = roofline["achieved"] / (roofline["peak"] / 3.0)
+
     # DRAM traffic of the dominant kernel, per launch, from the committed ncu --set full summary
     # of the same command (profiles/; cold-cache, serialised capture)
     tsrc = None
