@@ -260,6 +260,13 @@ class ProgramExecutor:
                 if events is not None:
                     e1.record()
                     events.append((i, e0, e1))
+                if self.trace is not None:
+                    # values a fused region does not materialise are simply absent
+                    for m in fusion.members:
+                        vals = [env.get(v) for v in nodes[m].outputs]
+                        if all(v is not None for v in vals):
+                            self.trace[m] = [v.to_numpy() if isinstance(v, DeviceArray) else np.array(v, copy=True)
+                                             for v in vals]
                 for v in self._free_after[i]:
                     env.pop(v, None)
                 continue
