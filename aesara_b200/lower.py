@@ -484,6 +484,29 @@ def _l_advincsub(op, apply):
                                     "ignore_duplicates": bool(getattr(op, "ignore_duplicates", False))}
 
 
+@lowers("ExtractDiag")
+def _l_extract_diag(op, apply):
+    # tensor/basic.py:3480 ExtractDiag: ndarray.diagonal(offset, axis1, axis2) — a view of the
+    # input when op.view, else a copy
+    return "ExtractDiag", {"offset": int(op.offset), "axis1": int(op.axis1), "axis2": int(op.axis2),
+                           "view": bool(op.view)}
+
+
+@lowers("AllocDiag")
+def _l_alloc_diag(op, apply):
+    # tensor/basic.py:3600 AllocDiag (the gradient of ExtractDiag): a zero matrix with the
+    # input vector on its `offset` diagonal; lowered for vector inputs
+    if apply.inputs[0].type.ndim != 1 or (int(op.axis1), int(op.axis2)) != (0, 1):
+        raise UnsupportedOp("B200 backend: AllocDiag is implemented for vector inputs only; "
+                            "there is no CPU fallback for tensor work")
+    return "AllocDiag", {"offset": int(op.offset)}
+
+
+@lowers("Eye")
+def _l_eye(op, apply):
+    return "Eye", {"dtype": str(op.dtype)}
+
+
 @lowers("ARange")
 def _l_arange(op, apply):
     return "ARange", {"dtype": str(op.dtype)}

@@ -210,6 +210,25 @@ class DeviceArray:
                 raise ValueError(f"broadcast_to: cannot broadcast {self.shape} to {shape}")
         return self.view(shape, strides)
 
+    def diagonal(self, offset=0, axis1=0, axis2=1):
+        """``ndarray.diagonal`` as a view: the two axes collapse into one (stride s1 + s2)
+        that becomes the LAST axis, like NumPy."""
+        nd = self.ndim
+        axis1 %= nd
+        axis2 %= nd
+        if axis1 == axis2:
+            raise ValueError("axis1 and axis2 cannot be the same")
+        n1, n2 = self.shape[axis1], self.shape[axis2]
+        s1, s2 = self.strides[axis1], self.strides[axis2]
+        if offset >= 0:
+            length, off = max(0, min(n1, n2 - offset)), offset * s2
+        else:
+            length, off = max(0, min(n1 + offset, n2)), -offset * s1
+        keep = [d for d in range(nd) if d not in (axis1, axis2)]
+        shape = [self.shape[d] for d in keep] + [length]
+        strides = [self.strides[d] for d in keep] + [s1 + s2]
+        return self.view(shape, strides, off if length > 0 else 0)
+
     def index(self, idx):
         """Basic NumPy indexing (ints and slices) -> view."""
         idx = tuple(idx) + (slice(None),) * (self.ndim - len(idx))

@@ -895,6 +895,44 @@ def _advincsub(ex, i, node, args):
     return x
 
 
+@_op("ExtractDiag")
+def _extract_diag(ex, i, node, args):
+    (x,) = args
+    p = node.params
+    if is_host(x):
+        return np.array(np.asarray(x).diagonal(p["offset"], p["axis1"], p["axis2"]), copy=True)
+    d = x.diagonal(p["offset"], p["axis1"], p["axis2"])
+    return d if p["view"] else K.contiguous_copy(d)
+
+
+@_op("AllocDiag")
+def _alloc_diag(ex, i, node, args):
+    (v,) = args
+    k = node.params["offset"]
+    if is_host(v):
+        return np.diag(np.asarray(v), k)
+    n = v.shape[0] + abs(k)
+    out = DeviceArray.empty((n, n), v.dtype)
+    K.copy_into(out, ex.dev(np.zeros((1, 1), v.dtype), key=(i, "zero")))
+    if v.shape[0]:
+        K.copy_into(out.diagonal(k), v)
+    return out
+
+
+@_op("Eye")
+def _eye(ex, i, node, args):
+    n, m, k = (int(np.asarray(a.to_numpy() if isinstance(a, DeviceArray) else a).item()) for a in args)
+    dt = np.dtype(node.params["dtype"])
+    if n * m <= host_eval.MAX_HOST_ELEMS:
+        return np.eye(n, m, k, dtype=dt)
+    out = DeviceArray.empty((n, m), dt)
+    K.copy_into(out, ex.dev(np.zeros((1, 1), dt), key=(i, "zero")))
+    diag = out.diagonal(k)
+    if diag.size:
+        K.copy_into(diag, ex.dev(np.ones((1,), dt), key=(i, "one")))
+    return out
+
+
 @_op("ARange")
 def _arange(ex, i, node, args):
     from ..ir import DTYPE_CODE

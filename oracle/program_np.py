@@ -290,6 +290,23 @@ def _advincsub(node, args, prog):  # aesara/tensor/subtensor.py:2727 (perform :2
     return out
 
 
+@_h("ExtractDiag")
+def _extract_diag(node, args, prog):  # aesara/tensor/basic.py:3480 (perform :3557)
+    p = node.params
+    return np.array(np.asarray(args[0]).diagonal(p["offset"], p["axis1"], p["axis2"]), copy=True)
+
+
+@_h("AllocDiag")
+def _alloc_diag(node, args, prog):  # aesara/tensor/basic.py:3600 (perform :3640), vector input
+    return np.diag(np.asarray(args[0]), node.params["offset"])
+
+
+@_h("Eye")
+def _eye(node, args, prog):  # aesara/tensor/basic.py:1318 (perform :1339)
+    n, m, k = (int(np.asarray(a).item()) for a in args)
+    return np.eye(n, m, k, dtype=node.params["dtype"])
+
+
 @_h("ARange")
 def _arange(node, args, prog):  # aesara/tensor/basic.py:2867 (perform :2937)
     start, stop, step = (np.asarray(a).item() for a in args)
