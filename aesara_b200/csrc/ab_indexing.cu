@@ -302,3 +302,113 @@ extern "C" int ab_arange(int dtype, double start, double step, int64_t start_i, 
   AB_CUDA(cudaGetLastError());
   return AB_OK;
 }
+
+
+// ---- CumOp (cumsum / cumprod along one axis; aesara/tensor/extra_ops.py:253) --------------
+// x viewed as [outer, L, inner] (C-contiguous).  inner > 1: one thread per (outer, inner)
+// line, consecutive threads on consecutive `inner` (coalesced), sequential over L.
+// inner == 1: one CTA per line — chunks of 256 x 8 elements, thread-local scan, warp-shuffle
+// scan of the thread totals, carry from chunk to chunk.  Output dtype = input dtype (the
+// reference's C implementation, extra_ops.py:325-375, accumulates in that type too).
+namespace {
+template <typename T, bool MUL>
+__device__ __forceinline__ T cum_op(T a, T b) { return MUL ? (T)(a * b) : (T)(a + b); }
+
+template <typename T, bool MUL>
+__global__ void __launch_bounds__(256)
+cum_lines_kernel(const T* __restrict__ x, T* __restrict__ out, long long outer, long long L, long long inner) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= outer * inner) return;
+  const long long o = t / inner, i = t - o * inner;
+  const T* p = x + o * L * inner + i;
+  T* q = out + o * L * inner + i;
+  T acc = MUL ? (T)1 : (T)0;
+  for (long long l = 0; l < L; ++l) {
+    acc = cum_op<T, MUL>(acc, p[l * inner]);
+    q[l * inner] = acc;
+  }
+}
+
+template <typename T, bool MUL>
+__global__ void __launch_bounds__(256)
+cum_block_kernel(const T* __restrict__ x, T* __restrict__ out, long long L) {
+  constexpr int ITEMS = 8;
+  __shared__ T warp_tot[8];
+  __shared__ T carry_s;
+  const T ident = MUL ? (T)1 : (T)0;
+  const T* p = x + (long long)blockIdx.x * L;
+  T* q = out + (long long)blockIdx.x * L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = ident;
+  __syncthreads();
+  for (long long base = 0; base < L; base += 256 * ITEMS) {
+    T v[ITEMS];
+    const long long s0 = base + (long long)threadIdx.x * ITEMS;
+    T run = ident;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const T e = (s0 + k < L) ? p[s0 + k] : ident;
+      run = cum_op<T, MUL>(run, e);
+      v[k] = run;
+    }
+    // inclusive scan of the thread totals inside the warp
+    T incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const T up = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl = cum_op<T, MUL>(up, incl);
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    T prefix = carry_s;                       // everything before this chunk
+    for (int w = 0; w < warp; ++w) prefix = cum_op<T, MUL>(prefix, warp_tot[w]);
+    T excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = ident;
+    prefix = cum_op<T, MUL>(prefix, excl);     // everything before this thread's items
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k)
+      if (s0 + k < L) q[s0 + k] = cum_op<T, MUL>(prefix, v[k]);
+    __syncthreads();
+    if (threadIdx.x == 255) carry_s = cum_op<T, MUL>(prefix, run);
+    __syncthreads();
+  }
+}
+
+template <typename T>
+int cum_dispatch(bool mul, const void* x, void* out, long long outer, long long L, long long inner,
+                 cudaStream_t st) {
+  const T* xi = static_cast<const T*>(x);
+  T* oo = static_cast<T*>(out);
+  if (inner == 1) {
+    if (mul) cum_block_kernel<T, true><<<(unsigned)outer, 256, 0, st>>>(xi, oo, L);
+    else cum_block_kernel<T, false><<<(unsigned)outer, 256, 0, st>>>(xi, oo, L);
+  } else {
+    const unsigned blocks = (unsigned)((outer * inner + 255) / 256);
+    if (mul) cum_lines_kernel<T, true><<<blocks, 256, 0, st>>>(xi, oo, outer, L, inner);
+    else cum_lines_kernel<T, false><<<blocks, 256, 0, st>>>(xi, oo, outer, L, inner);
+  }
+  g_launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB_OK;
+}
+}  // namespace
+
+extern "C" int ab_cumulative(int dtype, int mul, const void* x, void* out, int64_t outer, int64_t len,
+                             int64_t inner, void* stream) {
+  if (outer <= 0 || len <= 0 || inner <= 0) return AB_OK;
+  if (outer > 0x7fffffffLL) return fail(AB_ERR_UNSUPPORTED, "CumOp over more than 2^31 lines");
+  cudaStream_t st = as_stream(stream);
+  switch (dtype) {
+    case AB_F32: return cum_dispatch<float>(mul != 0, x, out, outer, len, inner, st);
+    case AB_F64: return cum_dispatch<double>(mul != 0, x, out, outer, len, inner, st);
+    case AB_I64: return cum_dispatch<long long>(mul != 0, x, out, outer, len, inner, st);
+    case AB_I32: return cum_dispatch<int>(mul != 0, x, out, outer, len, inner, st);
+    case AB_I16: return cum_dispatch<short>(mul != 0, x, out, outer, len, inner, st);
+    case AB_I8: return cum_dispatch<signed char>(mul != 0, x, out, outer, len, inner, st);
+    case AB_U8: return cum_dispatch<unsigned char>(mul != 0, x, out, outer, len, inner, st);
+    case AB_U16: return cum_dispatch<unsigned short>(mul != 0, x, out, outer, len, inner, st);
+    case AB_U32: return cum_dispatch<unsigned int>(mul != 0, x, out, outer, len, inner, st);
+    case AB_U64: return cum_dispatch<unsigned long long>(mul != 0, x, out, outer, len, inner, st);
+    default: return fail(AB_ERR_UNSUPPORTED, "CumOp: dtype code %d", dtype);
+  }
+}

@@ -484,6 +484,11 @@ def _l_advincsub(op, apply):
                                     "ignore_duplicates": bool(getattr(op, "ignore_duplicates", False))}
 
 
+@lowers("CumOp")
+def _l_cumop(op, apply):
+    return "CumOp", {"axis": None if op.axis is None else int(op.axis), "mode": str(op.mode)}
+
+
 @lowers("ExtractDiag")
 def _l_extract_diag(op, apply):
     # tensor/basic.py:3480 ExtractDiag: ndarray.diagonal(offset, axis1, axis2) — a view of the

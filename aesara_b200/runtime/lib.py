@@ -106,6 +106,10 @@ SIGNATURES = {
         [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64,
          C.c_void_p, C.c_int, C.c_void_p],
     ),
+    "ab_cumulative": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p],
+    ),
     "ab_arange": (
         C.c_int,
         [C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p],

@@ -895,6 +895,36 @@ def _advincsub(ex, i, node, args):
     return x
 
 
+@_op("CumOp")
+def _cumop(ex, i, node, args):
+    from ..ir import DTYPE_CODE
+    from . import lib as _lib
+    from .device import stream_handle
+
+    (x,) = args
+    p = node.params
+    if is_host(x):
+        xa = np.asarray(x)
+        f = np.cumsum if p["mode"] == "add" else np.cumprod
+        return f(xa, axis=p["axis"], dtype=xa.dtype)
+    x = _as_c_contiguous(x)
+    axis = p["axis"]
+    if axis is None:
+        shape, outer, L, inner = (x.size,), 1, x.size, 1
+    else:
+        axis %= x.ndim
+        shape = x.shape
+        outer = int(np.prod(shape[:axis], dtype=np.int64)) if axis else 1
+        L = shape[axis]
+        inner = int(np.prod(shape[axis + 1:], dtype=np.int64)) if axis + 1 < x.ndim else 1
+    out = DeviceArray.empty(shape, x.dtype)
+    if x.dtype == np.bool_:
+        raise TypeError("CumOp on bool arrays is not implemented on the device")
+    _lib.check(_lib.load().ab_cumulative(DTYPE_CODE[x.dtype.name], 1 if p["mode"] == "mul" else 0, x.ptr,
+                                         out.ptr, outer, L, inner, stream_handle()))
+    return out
+
+
 @_op("ExtractDiag")
 def _extract_diag(ex, i, node, args):
     (x,) = args

@@ -236,6 +236,11 @@ int ab_ravel_index(int k, const void* const* idx, const int64_t* idx_stride, con
 int ab_arange(int dtype, double start, double step, int64_t start_i, int64_t step_i, int64_t n,
               void* out, void* stream);
 
+/* CumOp (aesara/tensor/extra_ops.py:253): running sum (mul = 0) / product (mul = 1) along the
+ * middle axis of x viewed as C-contiguous [outer, len, inner]; out has the dtype of x. */
+int ab_cumulative(int dtype, int mul, const void* x, void* out, int64_t outer, int64_t len,
+                  int64_t inner, void* stream);
+
 /* ---- Scan fast path: LSTM-cell recurrence as one persistent kernel -----------------
  * (aesara/scan/op.py:637; inner graph of SURVEY App. A.4).  For t in [0,T):
  *   pre = x[t] + h_{t-1} @ U;  c_t = sigmoid(pre_f)*c_{t-1} + sigmoid(pre_i)*tanh(pre_g);

@@ -290,6 +290,13 @@ def _advincsub(node, args, prog):  # aesara/tensor/subtensor.py:2727 (perform :2
     return out
 
 
+@_h("CumOp")
+def _cumop(node, args, prog):  # aesara/tensor/extra_ops.py:253 (C code :325-375: accumulates in x's dtype)
+    x = np.asarray(args[0])
+    f = np.cumsum if node.params["mode"] == "add" else np.cumprod
+    return f(x, axis=node.params["axis"], dtype=x.dtype)
+
+
 @_h("ExtractDiag")
 def _extract_diag(node, args, prog):  # aesara/tensor/basic.py:3480 (perform :3557)
     p = node.params

@@ -583,6 +583,18 @@ def _():
                                            rnd(7), np.int64(11)]
 
 
+@case("cumsum_cumprod")
+def _():
+    x = at.fmatrix("x")
+    t = at.dtensor3("t")
+    v = at.fvector("v")
+    iv = at.lvector("iv")
+    outs = [at.cumsum(x, axis=0), at.cumsum(x, axis=1), at.cumsum(x), at.cumprod(t * 0.5, axis=1), at.cumsum(t, axis=2),
+            at.cumsum(v), at.cumprod(v * 0.01 + 1), at.cumsum(iv), at.cumsum(x.T, axis=0)[::2], at.cumsum(x[:0], axis=0),
+            aesara.grad(at.cumsum(v).sum() + (at.cumsum(x, axis=1) ** 2).sum(), [v, x])[1]]
+    return [x, t, v, iv], outs, [rnd((9, 14)), rnd((3, 5, 4), "float64"), rnd(5000), rnd(700, "int64")]
+
+
 @case("diag_eye")
 def _():
     x = at.fmatrix("x")
@@ -606,7 +618,7 @@ def _():
     return [a, b, c, v], outs, [rnd((4, 6)), rnd((3, 6)), rnd((4, 1)), rnd(5, "int64")]
 
 
-PY_LINKER_CASES = {"indexing_embedding", "adv_index_pairs", "classifier_int_labels"}
+PY_LINKER_CASES = {"indexing_embedding", "adv_index_pairs", "classifier_int_labels", "cumsum_cumprod"}
 
 
 def main(names):
@@ -614,7 +626,8 @@ def main(names):
 
     for name in names:
         ins, outs, values = CASES[name]()
-        # AdvancedIncSubtensor1's C code needs NumPy-1 PyArrayMapIter (gone in NumPy 2):
+        # AdvancedIncSubtensor1's C code needs NumPy-1 PyArrayMapIter (gone in NumPy 2) and
+        # CumOp's passes NPY_MAXDIMS as the "flatten" axis (NumPy 2 wants NPY_RAVEL_AXIS):
         # those cases run the reference's Python `perform` implementations instead
         linker = "py" if name in PY_LINKER_CASES else "cvm"
         prog, f = optimized_program(ins, outs, name=name, linker=linker)
