@@ -41,7 +41,7 @@ _SCALAR_OPS = {
     "LT": "lt", "GT": "gt", "LE": "le", "GE": "ge", "EQ": "eq", "NEQ": "neq",
     "IsNan": "isnan", "IsInf": "isinf", "Switch": "switch",
     "OR": "or", "XOR": "xor", "AND": "and", "Invert": "invert",
-    "ScalarMaximum": "maximum", "ScalarMinimum": "minimum",
+    "ScalarMaximum": "maximum", "ScalarMinimum": "minimum", "MulWithoutZeros": "mul_without_zeros",
     "Add": "add", "Mul": "mul", "Sub": "sub", "TrueDivide": "true_divide",
     "IntDiv": "int_div", "FloorDivide": "int_div", "Mod": "mod", "Pow": "pow",
     "Clip": "clip", "Second": "second", "Identity": "identity", "Cast": "cast",
@@ -257,7 +257,7 @@ def _l_dimshuffle(op, apply):
 def _l_careduce(op, apply):
     sop = type(op.scalar_op).__name__
     name = _SCALAR_OPS.get(sop)
-    if name not in ("add", "mul", "maximum", "minimum", "and", "or", "xor"):
+    if name not in ("add", "mul", "maximum", "minimum", "and", "or", "xor", "mul_without_zeros"):
         raise UnsupportedOp(f"CAReduce over scalar op {sop}")
     in_dtype = apply.inputs[0].type.dtype
     out_dtype = apply.outputs[0].type.dtype

@@ -429,6 +429,8 @@ def _careduce(ex, i, node, args):
     (x,) = args
     p = node.params
     axis = tuple(p["axis"])
+    if is_host(x) and p["scalar_op"] not in _NP_REDUCE:
+        x = ex.dev(np.asarray(x))
     if is_host(x):  # shape arithmetic such as prod(shape)
         xa = np.asarray(x).astype(p["acc_dtype"])
         out = _NP_REDUCE[p["scalar_op"]].reduce(xa, axis=axis, dtype=p["acc_dtype"]) if axis else xa

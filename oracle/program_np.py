@@ -137,10 +137,14 @@ def _careduce(node, args, prog):
     x = np.asarray(x)
     acc = np.dtype(p["acc_dtype"])
     axis = tuple(p["axis"])
-    uf = _UFUNC[p["scalar_op"]]
     xa = x.astype(acc)
+    if p["scalar_op"] == "mul_without_zeros":  # aesara/tensor/math.py:2713-2754
+        nz = xa != 0
+        out = np.where(nz.any(axis=axis), np.prod(np.where(nz, xa, 1), axis=axis, dtype=acc), 0)
+        return np.asarray(out).astype(p["out_dtype"])
     if p["scalar_op"] in ("maximum", "minimum") and any(x.shape[a] == 0 for a in axis):
         raise ValueError("zero-size array to reduction operation with no identity")
+    uf = _UFUNC[p["scalar_op"]]
     if axis == ():
         out = xa
     else:

@@ -286,6 +286,21 @@ def _():
                                            rnd((12, 40), "bool"), rnd((30, 70), "uint8")]
 
 
+@case("prod_grad_without_zeros")
+def _():
+    x = at.fmatrix("x")
+    d = at.dvector("d")
+    outs = [aesara.grad(x.prod(), x), aesara.grad(x.prod(axis=1).sum(), x), aesara.grad(d.prod() * 2, d),
+            at.math.ProdWithoutZeros(axis=0)(x), at.math.ProdWithoutZeros()(d)]
+    xv = rnd((5, 6), "float32", 0.5, 1.5)
+    xv[1, 2] = 0.0
+    xv[3, 0] = 0.0
+    xv[3, 4] = 0.0
+    dv = rnd(9, "float64", 0.5, 1.5)
+    dv[4] = 0.0
+    return [x, d], outs, [xv, dv]
+
+
 @case("careduce_big_1d")
 def _():
     x = at.fvector("x")
