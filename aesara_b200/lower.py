@@ -507,6 +507,11 @@ def _l_alloc_diag(op, apply):
     return "AllocDiag", {"offset": int(op.offset)}
 
 
+@lowers("Tri")
+def _l_tri(op, apply):
+    return "Tri", {"dtype": str(op.dtype)}
+
+
 @lowers("Eye")
 def _l_eye(op, apply):
     return "Eye", {"dtype": str(op.dtype)}

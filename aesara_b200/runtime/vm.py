@@ -951,6 +951,39 @@ def _alloc_diag(ex, i, node, args):
     return out
 
 
+_TRI_EXPR = {}
+
+
+@_op("Tri")
+def _tri(ex, i, node, args):
+    """``np.tri(N, M, k)``: out[r, c] = (c <= r + k), evaluated by one generated Elemwise
+    kernel over a row-index column and a column-index row (both from ``ab_arange``)."""
+    n, m, k = (int(np.asarray(a.to_numpy() if isinstance(a, DeviceArray) else a).item()) for a in args)
+    dt = np.dtype(node.params["dtype"])
+    if n * m <= host_eval.MAX_HOST_ELEMS:
+        return np.tri(n, m, k, dtype=dt)
+    from ..ir import DTYPE_CODE
+    from . import lib as _lib
+    from .device import stream_handle
+
+    rows = DeviceArray.empty((n,), "int64")
+    cols = DeviceArray.empty((m,), "int64")
+    lib = _lib.load()
+    _lib.check(lib.ab_arange(DTYPE_CODE["int64"], 0.0, 1.0, k, 1, n, rows.ptr, stream_handle()))   # r + k
+    _lib.check(lib.ab_arange(DTYPE_CODE["int64"], 0.0, 1.0, 0, 1, m, cols.ptr, stream_handle()))
+    expr = _TRI_EXPR.get(dt.name)
+    if expr is None:
+        expr = _TRI_EXPR[dt.name] = {
+            "inputs": ["int64", "int64"], "out_dtypes": [dt.name], "outputs": ["t1"], "name": f"tri_{dt.name}",
+            "stmts": [{"op": "le", "args": ["i1", "i0"], "dtype": "bool", "in_dtypes": ["int64", "int64"]},
+                      {"op": "cast", "args": ["t0"], "dtype": dt.name, "in_dtypes": ["bool"]}]}
+    out = DeviceArray.empty((n, m), dt)
+    r2 = rows.view((n, 1), (rows.strides[0], 0))
+    c2 = cols.view((1, m), (0, cols.strides[0]))
+    K.ElemwiseKernel.get(expr).launch((n, m), [r2, c2], [out])
+    return out
+
+
 @_op("Eye")
 def _eye(ex, i, node, args):
     n, m, k = (int(np.asarray(a.to_numpy() if isinstance(a, DeviceArray) else a).item()) for a in args)

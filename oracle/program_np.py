@@ -312,6 +312,12 @@ def _alloc_diag(node, args, prog):  # aesara/tensor/basic.py:3600 (perform :3640
     return np.diag(np.asarray(args[0]), node.params["offset"])
 
 
+@_h("Tri")
+def _tri(node, args, prog):  # aesara/tensor/basic.py:1178 (perform :1196)
+    n, m, k = (int(np.asarray(a).item()) for a in args)
+    return np.tri(n, m, k, dtype=node.params["dtype"])
+
+
 @_h("Eye")
 def _eye(node, args, prog):  # aesara/tensor/basic.py:1318 (perform :1339)
     n, m, k = (int(np.asarray(a).item()) for a in args)

@@ -617,7 +617,8 @@ def _():
     n = at.lscalar("n")
     outs = [at.diag(x) * 2, x.diagonal(1) + 1, x.diagonal(-2), t.diagonal(0, 0, 2).sum(axis=1), at.diag(x).sum(),
             at.eye(n) * 3, at.eye(n, n + 4, 2) + 1, at.eye(n + 9, n, -3, dtype="int32"), x + at.eye(x.shape[0], x.shape[1]),
-            aesara.grad(at.diag(x).sum() * 2, x)]
+            aesara.grad(at.diag(x).sum() * 2, x), at.tril(x), at.triu(x, 1) * 2, at.tri(n, n + 3, -1, dtype="int32"),
+            at.tril(at.ones((n, n)), 2).sum(axis=0)]
     return [x, t, n], outs, [rnd((9, 12)), rnd((5, 4, 6)), np.int64(11)]
 
 
