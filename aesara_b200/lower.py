@@ -484,6 +484,21 @@ def _l_advincsub(op, apply):
                                     "ignore_duplicates": bool(getattr(op, "ignore_duplicates", False))}
 
 
+@lowers("BatchedDot")
+def _l_batched_dot(op, apply):
+    # tensor/blas.py:2232 BatchedDot: z[b] = dot(x[b], y[b]) for 2-D / 3-D operands
+    return "BatchedDot", {}
+
+
+@lowers("IfElse")
+def _l_ifelse(op, apply):
+    # aesara/ifelse.py:44: outputs = the `then` values if the condition is true, else the
+    # `else` values.  The reference VM evaluates only the taken branch (lazy thunk); this
+    # executor runs nodes in schedule order, so both branches exist by the time the node
+    # runs and it only selects (same values, no laziness).
+    return "IfElse", {"n_outs": int(op.n_outs), "as_view": bool(op.as_view)}
+
+
 @lowers("CumOp")
 def _l_cumop(op, apply):
     return "CumOp", {"axis": None if op.axis is None else int(op.axis), "mode": str(op.mode)}

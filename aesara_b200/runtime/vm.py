@@ -897,6 +897,33 @@ def _advincsub(ex, i, node, args):
     return x
 
 
+@_op("BatchedDot")
+def _batched_dot(ex, i, node, args):
+    x, y = _as_dev_inputs(ex, i, node, args)
+    if x.shape[0] != y.shape[0]:
+        raise TypeError(f"Inputs must have the same size in axis 0, but have sizes [{x.shape[0]}, {y.shape[0]}].")
+    nb = x.shape[0]
+    xm = x if x.ndim == 3 else x.view((nb, 1, x.shape[1]), (x.strides[0], 0, x.strides[1]))
+    ym = y if y.ndim == 3 else y.view((nb, y.shape[1], 1), (y.strides[0], y.strides[1], 0))
+    if xm.shape[2] != ym.shape[1]:
+        raise ValueError(f"Shape mismatch: x has {xm.shape[2]} cols but y has {ym.shape[1]} rows")
+    m, n = xm.shape[1], ym.shape[2]
+    out = DeviceArray.empty((nb, m, n), x.dtype)
+    for b in range(nb):  # one product per batch entry (tensor-core path when large enough)
+        K.gemm(out.index((b,)), 1.0, xm.index((b,)), ym.index((b,)), 0.0, ex.precision, cache=ex.pack_cache)
+    shape = (nb,) + ((m,) if x.ndim == 3 else ()) + ((n,) if y.ndim == 3 else ())
+    return out.reshape_view(shape)
+
+
+@_op("IfElse")
+def _ifelse(ex, i, node, args):
+    n = node.params["n_outs"]
+    c = args[0]
+    cond = bool(np.asarray(c.to_numpy() if isinstance(c, DeviceArray) else c).item())
+    vals = args[1 : 1 + n] if cond else args[1 + n : 1 + 2 * n]
+    return vals[0] if n == 1 else list(vals)
+
+
 @_op("CumOp")
 def _cumop(ex, i, node, args):
     from ..ir import DTYPE_CODE

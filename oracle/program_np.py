@@ -294,6 +294,23 @@ def _advincsub(node, args, prog):  # aesara/tensor/subtensor.py:2727 (perform :2
     return out
 
 
+@_h("BatchedDot")
+def _batched_dot(node, args, prog):  # aesara/tensor/blas.py:2232 (perform :2277)
+    x, y = (np.asarray(a) for a in args)
+    if x.shape[0] != y.shape[0]:
+        raise TypeError("BatchedDot: inputs must have the same size in axis 0")
+    return np.stack([np.dot(x[b], y[b]) for b in range(x.shape[0])]) if x.shape[0] else \
+        np.zeros((0,) + np.dot(x[:0].sum(0), y[:0].sum(0)).shape, dtype=np.result_type(x, y))
+
+
+@_h("IfElse")
+def _ifelse(node, args, prog):  # aesara/ifelse.py:44 (thunk :232-300)
+    n = node.params["n_outs"]
+    cond = bool(np.asarray(args[0]).item())
+    vals = args[1 : 1 + n] if cond else args[1 + n : 1 + 2 * n]
+    return [np.array(v, copy=True) for v in vals]
+
+
 @_h("CumOp")
 def _cumop(node, args, prog):  # aesara/tensor/extra_ops.py:253 (C code :325-375: accumulates in x's dtype)
     x = np.asarray(args[0])

@@ -598,6 +598,19 @@ def _():
                                            rnd(7), np.int64(11)]
 
 
+@case("batched_dot_ifelse")
+def _():
+    from aesara.ifelse import ifelse
+
+    a, b = at.ftensor3("a"), at.ftensor3("b")
+    m = at.fmatrix("m")
+    c = at.iscalar("c")
+    bd = at.batched_dot(a, b)
+    outs = [bd, at.batched_dot(a, m[: a.shape[0], : a.shape[2]]), at.batched_dot(m[: a.shape[0], : a.shape[1]], a),
+            ifelse(c, bd * 2, bd - 1), ifelse(at.gt(m.sum(), 1e6), m + 1, m * 3), aesara.grad((bd ** 2).sum(), a)]
+    return [a, b, m, c], outs, [rnd((4, 5, 6)), rnd((4, 6, 3)), rnd((7, 9)), np.int32(1)]
+
+
 @case("cumsum_cumprod")
 def _():
     x = at.fmatrix("x")
@@ -634,7 +647,7 @@ def _():
     return [a, b, c, v], outs, [rnd((4, 6)), rnd((3, 6)), rnd((4, 1)), rnd(5, "int64")]
 
 
-PY_LINKER_CASES = {"indexing_embedding", "adv_index_pairs", "classifier_int_labels", "cumsum_cumprod"}
+PY_LINKER_CASES = {"indexing_embedding", "adv_index_pairs", "classifier_int_labels", "cumsum_cumprod", "batched_dot_ifelse"}
 
 
 def main(names):
