@@ -12,7 +12,7 @@ from ..codegen.careduce import careduce_source
 from ..codegen.elemwise import elemwise_source
 from ..ir import DTYPE_CODE
 from . import lib as _lib
-from .device import DeviceArray, c_strides, f_strides, stream_handle
+from .device import DeviceArray, stream_handle
 
 
 class ElemwiseKernel:
