@@ -6,10 +6,11 @@ reference C-linker compiles for each ``ScalarOp`` (``aesara/scalar/basic.py``
 for sigmoid / softplus / log1mexp).  Evaluates the IR scalar expressions of
 ``aesara_b200.ir`` over whole arrays.
 
-Pinned against the reference itself: ``oracle/pin_against_reference.py`` runs the
-real reference C-linker (``Mode("cvm")``) in the build container on seeded
-inputs and compares; the resulting vectors are committed under
-``tests/golden/``.
+Pinned against the reference itself: ``tests/golden/make_golden.py`` runs the real
+reference (C-linker ``Mode("cvm")``; its Python ``perform`` for the few Ops whose C code no
+longer builds on NumPy 2) in the build container on seeded inputs and commits programs,
+inputs and reference outputs under ``tests/golden/``; ``tests/test_oracle.py`` checks this
+oracle against every one of them.
 """
 
 import numpy as np
