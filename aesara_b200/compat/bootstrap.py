@@ -25,7 +25,6 @@ import sys
 import types
 
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
-_DEFAULT_REFERENCE = "/root/reference"
 
 _CXXFLAGS = (
     "-DNPY_PY3K=1 -DPyInt_AsLong=PyLong_AsLong -DPyInt_FromLong=PyLong_FromLong "
@@ -35,10 +34,12 @@ _CXXFLAGS = (
 
 
 def reference_path():
-    """Directory that contains the ``aesara`` package, or None."""
-    for cand in (os.environ.get("AESARA_B200_REFERENCE"), _DEFAULT_REFERENCE):
-        if cand and os.path.isdir(os.path.join(cand, "aesara")):
-            return cand
+    """Directory named by ``$AESARA_B200_REFERENCE`` that contains an ``aesara`` package
+    which is not installed (a source checkout), or None: then ``import aesara`` must work
+    on its own, as for any linker plugin."""
+    cand = os.environ.get("AESARA_B200_REFERENCE")
+    if cand and os.path.isdir(os.path.join(cand, "aesara")):
+        return cand
     return None
 
 
@@ -115,7 +116,8 @@ def load_aesara(compiledir=None):
 
     _numpy2_aliases()
     if _SHIMS not in sys.path:
-        sys.path.insert(0, _SHIMS)
+        # appended: installed cons / etuples / unification packages win over the stand-ins
+        sys.path.append(_SHIMS)
     ref = reference_path()
     if ref is not None and ref not in sys.path:
         sys.path.append(ref)

@@ -25,6 +25,8 @@ from __future__ import annotations
 
 from copy import copy
 
+import numpy as np
+
 from .compat.bootstrap import load_aesara
 
 load_aesara()
@@ -48,7 +50,8 @@ class _NodeThunk:
 
 
 class B200VM:
-    """The callable returned by :meth:`B200Linker.make_all`."""
+    """The callable returned by :meth:`B200Linker.make_all` — what ``VM``/``CVM`` is to
+    ``VMLinker`` (``aesara/link/vm.py:86-335, 1005-1174``)."""
 
     need_update_inputs = False
 
@@ -64,6 +67,9 @@ class B200VM:
         self.position_of_error = -1
         self.call_counts = [0] * len(order)
         self.call_times = [0.0] * len(order)
+        # cells the caller forbids us to recycle between calls are emptied first
+        # (VMLinker.make_vm: pre_call_clear, vm.py:1017; Loop.__call__ vm.py:408-409)
+        self.pre_call_clear = [storage_map[v] for v in (linker.no_recycling or []) if v in storage_map]
         upd = getattr(fgraph, "update_mapping", None) or {}
         self._updates = [(int(o), int(i)) for o, i in upd.items()]
         # FunctionMaker appends the update expressions after the user's outputs
@@ -74,15 +80,39 @@ class B200VM:
         self.time_thunks = bool(getattr(linker, "profile", None))
         if self.time_thunks and hasattr(executor, "time_nodes"):
             executor.time_nodes = True
+        self._replay = None
+        if linker.cuda_graph and not self.time_thunks:
+            from .runtime.graph import GraphReplay
+
+            self._replay = GraphReplay(executor)
 
     def __call__(self, output_subset=None):
         from .runtime.vm import NodeError
         from .sharedvar import is_device_value, owns_cell
 
+        for cell in self.pre_call_clear:
+            cell[0] = None
+        args = [cell[0] for cell in self.input_storage]
         try:
-            outs = self.executor(*[cell[0] for cell in self.input_storage])
+            if output_subset is not None:
+                # only the ancestors of the requested outputs (and of every update) run
+                # (Stack.__call__, vm.py:536-563)
+                outs = self.executor(*args, output_subset=output_subset)
+            elif self._replay is not None and all(
+                    is_device_value(a) or np.size(a) <= 64 for a in args):
+                # device-resident arguments only: host arrays are uploaded by a copy stream,
+                # which is not part of a captured evaluation
+                outs = self._replay(*args)
+            else:
+                outs = self.executor(*args)
         except NodeError as e:
             self.position_of_error = e.position
+            # raise_with_op reads shapes / strides / small values of the failing node's
+            # inputs out of the thunk's cells (link/utils.py:340-356)
+            if e.inputs is not None:
+                for cell, val in zip(self.thunks[e.position].inputs, e.inputs):
+                    if cell[0] is None:
+                        cell[0] = val
             raise e.original from None
         finally:
             self._collect_times()
@@ -134,11 +164,18 @@ class B200VM:
 class B200Linker(LocalLinker):
     """Link an optimised ``FunctionGraph`` to hand-written sm_100a kernels."""
 
-    def __init__(self, allow_gc=True, precision="fp32", device_outputs=False, schedule=None):
+    def __init__(self, allow_gc=True, precision="fp32", device_outputs=False, schedule=None,
+                 cuda_graph=False):
         super().__init__(allow_gc=allow_gc, scheduler=schedule)
         self.fgraph = None
         self.precision = precision
         self.device_outputs = device_outputs
+        # replay each evaluation as ONE CUDA graph (runtime/graph.py) once the argument
+        # addresses and shapes repeat: removes the per-node host cost, which is what the C
+        # twin of the reference VM exists for (lazylinker_c.c).  Off by default because a
+        # replayed evaluation returns the SAME output buffers every call (device outputs
+        # must be consumed or copied before the next call).
+        self.cuda_graph = cuda_graph
         self.no_recycling = []
         self.program = None
 
@@ -148,7 +185,8 @@ class B200Linker(LocalLinker):
         if self.fgraph is not None and self.fgraph is not fgraph:
             # a linker instance is bound to one graph (pattern of link/basic.py:300-326)
             return type(self)(allow_gc=self.allow_gc, precision=self.precision,
-                              device_outputs=self.device_outputs).accept(fgraph, no_recycling, profile)
+                              device_outputs=self.device_outputs,
+                              cuda_graph=self.cuda_graph).accept(fgraph, no_recycling, profile)
         self.fgraph = fgraph
         self.no_recycling = no_recycling
         self.profile = profile
@@ -181,12 +219,13 @@ class B200Linker(LocalLinker):
         )
 
 
-def mode(precision="fp32", device_outputs=False, optimizer=None):
+def mode(precision="fp32", device_outputs=False, optimizer=None, cuda_graph=False):
     """An Aesara ``Mode`` using this backend with the ``fast_run`` rewrites the
     C-linker gets."""
     if optimizer is None:
         optimizer = RewriteDatabaseQuery(include=["fast_run"])
-    return Mode(B200Linker(precision=precision, device_outputs=device_outputs), optimizer)
+    return Mode(B200Linker(precision=precision, device_outputs=device_outputs,
+                           cuda_graph=cuda_graph), optimizer)
 
 
 def register():
@@ -195,21 +234,31 @@ def register():
         register_linker("b200", B200Linker())
     if "B200" not in predefined_modes:
         predefined_modes["B200"] = mode()
-    # get_target_language() (mode.py:535-555) raises for linker classes it does not
-    # know; rewrites that consult it (local_careduce_fusion) treat us like a C target
+    # get_target_language() (mode.py:535-555) raises for linker classes it does not know.
+    # Rewrites that consult it (local_careduce_fusion, tensor/rewriting/elemwise.py:966) hold
+    # their own reference (``from aesara.compile.mode import get_target_language``), so the
+    # replacement is installed in every loaded module that has the original.  This backend
+    # consumes the graphs the C-linker gets, so it answers like ``VMLinker`` with a compiler.
+    import sys
+
     import aesara.compile.mode as _m
 
-    if not getattr(_m.get_target_language, "_b200", False):
-        _orig = _m.get_target_language
+    _orig = _m.get_target_language
+    if not getattr(_orig, "_b200", False):
 
         def get_target_language(mode=None):
             m = _m.get_default_mode() if mode is None else mode
             if isinstance(getattr(m, "linker", None), B200Linker):
-                return ("c",)
+                return ("c", "py")
             return _orig(mode)
 
         get_target_language._b200 = True
-        _m.get_target_language = get_target_language
+        for mod in list(sys.modules.values()):
+            if mod is not None and getattr(mod, "__dict__", {}).get("get_target_language") is _orig:
+                mod.get_target_language = get_target_language
 
 
 register()
+from .sharedvar import register_shared_constructor  # noqa: E402
+
+register_shared_constructor()

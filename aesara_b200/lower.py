@@ -230,6 +230,14 @@ def lower_apply(apply, ctx) -> Node:
     ins = [ctx.var_id(v) for v in apply.inputs]
     outs = [ctx.var_id(v) for v in apply.outputs]
     opname, params = fn(op, apply)
+    # generic destroy_map (graph/op.py: "destroy_map {out: [in]}"): which inputs this node
+    # overwrites — the executor invalidates cached GEMM operand planes of those buffers and
+    # refuses to defer a fused region across such a node (runtime/vm.py)
+    dm = getattr(op, "destroy_map", None) or {}
+    destroyed = sorted({int(i) for v in dm.values() for i in v})
+    if destroyed:
+        params = dict(params)
+        params["destroy"] = destroyed
     return Node(op=opname, inputs=ins, outputs=outs, params=params, label=str(apply)[:200])
 
 
@@ -548,10 +556,82 @@ def _l_split(op, apply):
 
 
 # -- Scan --------------------------------------------------------------------------------
+def optimized_inner_fgraph(op):
+    """The inner graph of a ``Scan`` as the reference would *execute* it.
+
+    ``op.fgraph`` as stored in the outer graph is the raw inner function: the reference
+    rewrites it only when ``Scan.fn`` is first touched (``scan/op.py:1431-1459``:
+    ``pfunc(..., mode=self.mode_instance, fgraph=self.fgraph)`` mutates it in place with the
+    protections ``prepare_fgraph`` sets up, ``:1300-1428``).  Lowering must not depend on
+    whether some other linker happened to trigger that side effect, so the same compilation
+    is run here on a *clone* of the Op with a linker that links nothing: what comes back is
+    the rewritten graph (``Dot`` -> ``Gemm``, fused ``Composite``s, in-place ops where the
+    Supervisor allows them, ``DeepCopyOp`` on outputs that alias inputs)."""
+    from aesara.compile.mode import Mode
+
+    if getattr(op, "_fn", None) is not None:
+        # the reference already compiled this Op (a C-linker function over the same graph,
+        # debug.check_function): op.fgraph IS the rewritten graph
+        return op.fgraph
+    op2 = op.clone()  # copy(op) + fgraph.clone()  (scan/op.py:1469-1472)
+    op2._fn = None
+    inner_mode = op.mode_instance
+    op2.mode_instance = Mode(linker=_LinkNothing(), optimizer=inner_mode.provided_optimizer,
+                             db=inner_mode.optdb)
+    op2.fn  # noqa: B018  -- compiles: rewrites op2.fgraph in place
+    return op2.fgraph
+
+
+def _link_nothing_cls():
+    from aesara.link.basic import Container, LocalLinker
+    from aesara.link.utils import map_storage
+
+    class LinkNothing(LocalLinker):
+        """A linker that only allocates the storage cells ``Function`` wants to see."""
+
+        def __init__(self):
+            super().__init__()
+            self.fgraph = None
+
+        def accept(self, fgraph, no_recycling=None, profile=None):
+            if self.fgraph is not None and self.fgraph is not fgraph:
+                return type(self)().accept(fgraph, no_recycling, profile)
+            self.fgraph = fgraph
+            self.no_recycling = no_recycling or []
+            return self
+
+        def make_all(self, input_storage=None, output_storage=None, storage_map=None):
+            fgraph = self.fgraph
+            order = self.schedule(fgraph)
+            input_storage, output_storage, storage_map = map_storage(
+                fgraph, order, input_storage, output_storage, storage_map)
+
+            def fn():
+                raise RuntimeError("this inner function exists for its rewritten graph only")
+
+            fn.allow_gc = False
+            fn.storage_map = storage_map
+            return (fn, [Container(i, s) for i, s in zip(fgraph.inputs, input_storage)],
+                    [Container(o, s, readonly=True) for o, s in zip(fgraph.outputs, output_storage)],
+                    [], order)
+
+    return LinkNothing
+
+
+_LINK_NOTHING = None
+
+
+def _LinkNothing():
+    global _LINK_NOTHING
+    if _LINK_NOTHING is None:
+        _LINK_NOTHING = _link_nothing_cls()
+    return _LINK_NOTHING()
+
+
 @lowers("Scan")
 def _l_scan(op, apply):
     info = op.info
-    inner = lower_fgraph(op.fgraph, name=f"scan_inner:{getattr(op, 'name', None)}")
+    inner = lower_fgraph(optimized_inner_fgraph(op), name=f"scan_inner:{getattr(op, 'name', None)}")
     return "Scan", {
         "info": {
             "n_seqs": info.n_seqs,

@@ -36,15 +36,66 @@ def _op(name):
 class NodeError(RuntimeError):
     """Raised with the position of the failing node (``vm.position_of_error``)."""
 
-    def __init__(self, position, node, exc):
+    def __init__(self, position, node, exc, inputs=None):
         super().__init__(f"{type(exc).__name__}: {exc}\nwhile running node {position}: {node.label or node.op}")
         self.position = position
         self.node = node
         self.original = exc
+        # the values the failing node was given (what ``raise_with_op`` prints shapes and
+        # strides of, aesara/link/utils.py:340-356); filled in by the executor
+        self.inputs = inputs
 
 
 def is_host(v):
     return not isinstance(v, DeviceArray)
+
+
+# Input positions whose *values* a node needs on the host (allocation shapes, indices, axes,
+# BLAS scalars, loop counts): everything the reference computes with int64 shape arithmetic
+# (SURVEY.md a9).  "all" = every input, ("from", k) = inputs k.. .
+_HOST_SLOTS = {
+    "AllocEmpty": "all", "MakeVector": "all", "ScalarOp": "all", "Tri": "all", "Eye": "all",
+    "ARange": "all", "ScalarFromTensor": "all",
+    "Alloc": ("from", 1), "BroadcastTo": ("from", 1), "Subtensor": ("from", 1),
+    "IncSubtensor": ("from", 2), "Assert": ("from", 1),
+    "Reshape": (1,), "Join": (0,), "Split": (1, 2), "Gemm": (1, 4), "Gemv": (1, 4), "Ger": (1,),
+    "Dot22Scalar": (2,), "IfElse": (0,),
+}
+# node kinds through which "needed on the host" propagates from an output to the inputs (the
+# value is *computed* from them); Shape/Shape_i read only metadata and stop the propagation
+_HOST_TRANSPARENT = {"Elemwise", "CAReduce", "DimShuffle", "Subtensor", "TensorFromScalar",
+                     "ScalarFromTensor", "Reshape", "MakeVector", "Join", "View", "DeepCopy",
+                     "ScalarOp", "Assert", "Alloc", "BroadcastTo", "IfElse", "Split",
+                     "AdvancedSubtensor1", "ARange", "MaxAndArgmax", "CumOp"}
+
+
+def host_needed_vars(program):
+    """Variables whose values some node needs on the host, closed backwards through the
+    nodes that compute them.  A tensor *argument* of the function outside this set is data,
+    whatever its size, and is uploaded; inside it (and small) it stays a host value so that
+    shapes and indices never cost a device synchronisation."""
+    need = set()
+    for n in program.nodes:
+        slots = _HOST_SLOTS.get(n.op)
+        if n.op == "Scan":
+            info = n.params["info"]
+            n_outs = (len(info["mit_mot_in_slices"]) + len(info["mit_sot_in_slices"])
+                      + len(info["sit_sot_in_slices"]))
+            first_nit = 1 + info["n_seqs"] + n_outs + info["n_shared_outs"]
+            slots = (0,) + tuple(range(first_nit, first_nit + info["n_nit_sot"]))
+        if slots is None:
+            continue
+        if slots == "all":
+            idx = range(len(n.inputs))
+        elif slots[0] == "from":
+            idx = range(slots[1], len(n.inputs))
+        else:
+            idx = [k for k in slots if k < len(n.inputs)]
+        need.update(n.inputs[k] for k in idx)
+    for n in reversed(program.nodes):
+        if n.op in _HOST_TRANSPARENT and any(v in need for v in n.outputs):
+            need.update(n.inputs)
+    return need
 
 
 class ProgramExecutor:
@@ -89,6 +140,8 @@ class ProgramExecutor:
         for i, n in enumerate(program.nodes):
             for v in n.inputs:
                 self._first_use.setdefault(v, i)
+        self._host_needed = host_needed_vars(program)
+        self._subset_cache = {}
         self._copy_streams = {}
         self._inflight = []
         self.pack_cache = K.PackCache()
@@ -97,9 +150,12 @@ class ProgramExecutor:
         self._destroys = []
         for n in program.nodes:
             d = []
-            if n.op == "Elemwise":
+            if "destroy" in n.params:  # the Op's own destroy_map, emitted by lower.py
+                d = sorted(int(v) for v in n.params["destroy"])
+            elif n.op == "Elemwise":
                 d = sorted(set(int(v) for v in n.params.get("inplace", {}).values()))
-            elif n.op in ("Gemm", "Gemv", "Ger", "IncSubtensor") and n.params.get("inplace"):
+            elif n.op in ("Gemm", "Gemv", "Ger", "IncSubtensor", "AdvancedIncSubtensor1",
+                          "AdvancedIncSubtensor") and n.params.get("inplace"):
                 d = [0]
             elif n.op == "Scan":
                 d = sorted({int(i) for v in n.params.get("destroy_map", {}).values() for i in v})
@@ -185,10 +241,43 @@ class ProgramExecutor:
         return d
 
     # ------------------------------------------------------------------
-    def __call__(self, *inputs):
+    def needed_nodes(self, output_subset):
+        """Which nodes must run so that the outputs at the given positions (plus every
+        update output, ``aesara/link/vm.py:540-551``) are computed: their ancestors, with
+        fused regions kept whole."""
+        key = tuple(sorted(set(int(k) for k in output_subset) | {o for o, _ in self.program.updates}))
+        hit = self._subset_cache.get(key)
+        if hit is not None:
+            return hit
+        prog = self.program
+        want = {prog.outputs[k] for k in key}
+        needed = [False] * len(prog.nodes)
+        changed = True
+        while changed:
+            changed = False
+            for i in range(len(prog.nodes) - 1, -1, -1):
+                n = prog.nodes[i]
+                if not needed[i] and any(v in want for v in n.outputs):
+                    needed[i] = changed = True
+                if needed[i]:
+                    before = len(want)
+                    want.update(n.inputs)
+                    changed = changed or len(want) != before
+            for f in self._fusions:
+                if any(needed[m] for m in f.members) and not all(needed[m] for m in f.members):
+                    for m in f.members:
+                        needed[m] = True
+                    changed = True
+        self._subset_cache[key] = (needed, key)
+        return needed, key
+
+    def __call__(self, *inputs, output_subset=None):
         prog = self.program
         if len(inputs) != len(prog.inputs):
             raise TypeError(f"expected {len(prog.inputs)} inputs, got {len(inputs)}")
+        needed = None
+        if output_subset is not None:
+            needed, computed_outputs = self.needed_nodes(output_subset)
         env = dict(self._const_host)
         self.pack_cache.clear()
         # host tensors are uploaded on a copy stream in order of first use, so that a
@@ -214,7 +303,9 @@ class ProgramExecutor:
                         f"input {var.name or vid}: wrong number of dimensions: expected "
                         f"{var.ndim}, got {val.ndim} with shape {val.shape}"
                     )
-                if val.size > host_eval.MAX_HOST_ELEMS:
+                # data goes to the device whatever its size; only values that drive shapes /
+                # indices / BLAS scalars (host_needed_vars) stay host-side while they are small
+                if vid not in self._host_needed or val.size > host_eval.MAX_HOST_ELEMS:
                     uploads.append((self._first_use.get(vid, 0), vid, val))
                     continue
             elif var.kind == "scalar":
@@ -235,6 +326,8 @@ class ProgramExecutor:
         nodes = prog.nodes
         for i, step in enumerate(self._steps):
             node = nodes[i]
+            if needed is not None and not needed[i]:
+                continue
             if pending:
                 for v in node.inputs:
                     ev = pending.pop(v, None)
@@ -252,7 +345,7 @@ class ProgramExecutor:
                     done = fusion.run(self, env)
                 except Exception as exc:
                     self.position_of_error = i
-                    raise NodeError(i, node, exc) from exc
+                    raise NodeError(i, node, exc, [env.get(v) for v in node.inputs]) from exc
                 if not done:
                     self._run_nodes(fusion.members, env)
                 else:
@@ -280,7 +373,7 @@ class ProgramExecutor:
                 raise
             except Exception as exc:
                 self.position_of_error = i
-                raise NodeError(i, node, exc) from exc
+                raise NodeError(i, node, exc, [env.get(v) for v in node.inputs]) from exc
             if events is not None:
                 e1.record()
                 events.append((i, e0, e1))
@@ -304,9 +397,14 @@ class ProgramExecutor:
         self.pack_cache.clear()
         for ev in pending.values():  # inputs no node consumed (returned as they are)
             torch.cuda.current_stream().wait_event(ev)
-        outs = [env[v] for v in prog.outputs]
+        if needed is None:
+            outs = [env[v] for v in prog.outputs]
+        else:  # outputs nobody asked for are not computed (None, as in the reference VM)
+            outs = [env[v] if k in computed_outputs else None for k, v in enumerate(prog.outputs)]
         if self.host_outputs:
-            outs = DeviceArray.download_all(outs)
+            got = DeviceArray.download_all([o for o in outs if o is not None])
+            it = iter(got)
+            outs = [None if o is None else next(it) for o in outs]
         return outs
 
     def _run_nodes(self, indices, env):
@@ -320,7 +418,7 @@ class ProgramExecutor:
                 raise
             except Exception as exc:
                 self.position_of_error = i
-                raise NodeError(i, node, exc) from exc
+                raise NodeError(i, node, exc, [env.get(v) for v in node.inputs]) from exc
             if len(node.outputs) == 1:
                 env[node.outputs[0]] = outs
             else:

@@ -126,3 +126,40 @@ def shared(value, name=None, strict=False, allow_downcast=None, borrow=False, sh
     if dev is not None:
         var.set_value(dev, borrow=borrow)
     return var
+
+
+# -- registration with ``aesara.shared`` (compile/sharedvalue.py:213 ``shared_constructor``) --
+def _device_array_constructor(value, name=None, strict=False, allow_downcast=None, borrow=False,
+                              shape=None, **kwargs):
+    return shared(value, name=name, strict=strict, allow_downcast=allow_downcast, borrow=borrow,
+                  shape=shape)
+
+
+_NDARRAY_DEFAULT = None
+
+
+def register_shared_constructor(ndarrays=False):
+    """Teach ``aesara.shared`` about device values.
+
+    Always: ``aesara.shared(DeviceArray)`` yields a :class:`B200SharedVariable` holding that
+    array (the ``singledispatch`` registry of ``compile/sharedvalue.py:213-222``, the way
+    ``tensor/sharedvar.py:48`` registers ``np.ndarray``).
+
+    ``ndarrays=True``: NumPy arrays given to ``aesara.shared`` also become
+    ``B200SharedVariable``s, so an unchanged user script keeps its parameters on the B200
+    between calls (their values move to the device at the first ``updates=`` of a B200
+    function).  Opt-in, because a function compiled with another linker that shares such a
+    variable needs ``sync_to_host()`` first.  ``ndarrays=False`` restores the default."""
+    global _NDARRAY_DEFAULT
+    from aesara.compile.sharedvalue import shared_constructor
+
+    from .runtime.device import DeviceArray
+
+    if shared_constructor.dispatch(DeviceArray) is not _device_array_constructor:
+        shared_constructor.register(DeviceArray, _device_array_constructor)
+    if _NDARRAY_DEFAULT is None:
+        _NDARRAY_DEFAULT = shared_constructor.dispatch(np.ndarray)
+    if ndarrays:
+        shared_constructor.register(np.ndarray, _device_array_constructor)
+    else:
+        shared_constructor.register(np.ndarray, _NDARRAY_DEFAULT)

@@ -29,6 +29,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 warnings.simplefilter("ignore")
 
+from oracle import ref as _ref  # noqa: E402
+
+_ref.materialise()
+_ref.activate()
 from aesara_b200 import graphs as G  # noqa: E402
 from aesara_b200.compat.bootstrap import load_aesara  # noqa: E402
 

@@ -55,7 +55,7 @@ class _OracleExecutor:
         self.trace = None
         self.time_nodes = False
 
-    def __call__(self, *inputs):
+    def __call__(self, *inputs, output_subset=None):
         from oracle.program_np import run_program
 
         host = []
@@ -67,6 +67,9 @@ class _OracleExecutor:
                     _FakeDeviceArray.uploads += 1
                 host.append(np.array(i) if isinstance(i, np.ndarray) else i)
         outs = run_program(self.program, host, trace=self.trace)
+        if output_subset is not None:
+            keep = set(output_subset) | {o for o, _ in self.program.updates}
+            outs = [o if k in keep else None for k, o in enumerate(outs)]
         if self.device_results:
             outs = [_FakeDeviceArray(o) if isinstance(o, np.ndarray) and o.ndim > 0 else o for o in outs]
         return outs
@@ -84,25 +87,46 @@ def test_mode_and_linker_are_registered(aes):
     assert isinstance(m.linker, L.B200Linker)
     from aesara.compile.mode import get_target_language
 
-    assert get_target_language(m) == ("c",)
+    assert get_target_language(m) == ("c", "py")  # the graphs the C-linker gets
+    # the rewrite that consults it holds its own reference to the function
+    import aesara.tensor.rewriting.elemwise as E
+
+    assert E.get_target_language(m) == ("c", "py")
 
 
-@pytest.mark.parametrize("cfg", ["cfg2_fused", "cfg3_mlp", "cfg5_logreg", "cfg4_lstm"])
-def test_lowering_reproduces_committed_fixture(aes, cfg):
-    """The program the linker lowers today equals the committed fixture (so the
-    fixtures the GPU box runs are what the linker would execute)."""
+def _same_program(a, b, path="program"):
+    assert [n.op for n in a.nodes] == [n.op for n in b.nodes], path
+    for k, (x, y) in enumerate(zip(a.nodes, b.nodes)):
+        assert x.params.get("expr", {}).get("name") == y.params.get("expr", {}).get("name"), f"{path} node {k}"
+        if x.op == "Scan":
+            assert x.params["info"] == y.params["info"]
+            _same_program(x.params["inner"], y.params["inner"], f"{path} node {k} inner")
+
+
+@pytest.mark.parametrize("cfg", ["cfg1_readme", "cfg2_fused", "cfg3_mlp", "cfg5_logreg", "cfg4_lstm"])
+def test_linker_path_lowers_to_the_committed_fixture(aes, cfg):
+    """What ``aesara.function(..., mode="B200")`` links — outer graph AND the inner graph of
+    a Scan — is the program committed under tests/golden (which the GPU box replays), and it
+    does not depend on another linker having compiled the Scan first (the inner
+    graph is rewritten by lower.optimized_inner_fgraph, never by a side effect of op.fn)."""
+    aesara, L = aes
     from aesara_b200 import graphs as G
     from tests._cases import load_case
 
-    build = {"cfg2_fused": G.cfg2_fused_elemwise, "cfg3_mlp": G.cfg3_mlp,
+    build = {"cfg1_readme": G.cfg1_readme, "cfg2_fused": G.cfg2_fused_elemwise, "cfg3_mlp": G.cfg3_mlp,
              "cfg5_logreg": G.cfg5_logreg, "cfg4_lstm": G.cfg4_lstm_scan}[cfg]
     i, o = build()
-    prog, _ = G.optimized_program(i, o, name=cfg)
+    f = aesara.function(i, o, mode=L.mode(), on_unused_input="ignore")
+    prog = f.maker.linker.program
     want, _, _ = load_case(cfg)
-    assert [n.op for n in prog.nodes] == [n.op for n in want.nodes]
-    assert [n.params.get("expr", {}).get("name") for n in prog.nodes] == [
-        n.params.get("expr", {}).get("name") for n in want.nodes
-    ]
+    _same_program(prog, want)
+    if cfg == "cfg4_lstm":
+        inner = [n for n in prog.nodes if n.op == "Scan"][0].params["inner"]
+        assert [n.op for n in inner.nodes].count("Gemm") == 1      # Dot -> Gemm happened
+        assert sum(n.op == "Elemwise" and len(n.params["expr"]["stmts"]) >= 3 for n in inner.nodes) == 2
+        # and the C-linker compiling the same graph afterwards changes nothing
+        prog_c, _ = G.optimized_program(*build(), name=cfg)
+        _same_program(prog_c, want)
 
 
 def test_function_semantics_through_the_linker(aes, monkeypatch):
@@ -246,3 +270,104 @@ def test_dual_run_checker(aes, monkeypatch):
     with pytest.raises(DualRunMismatch) as ei:
         check_function([X, w], out, vals)
     assert "CAReduce" in str(ei.value.node.op.__class__.__mro__) or "Sum" in str(ei.value.node) or "Max" in str(ei.value.node)
+
+
+def test_output_subset_no_recycling_and_error_cells(aes, monkeypatch):
+    """VM semantics ``Function.__call__`` relies on (compile/function/types.py:830, 969-1048):
+    ``output_subset`` computes only what was asked for plus the updates (vm.py:536-563),
+    ``no_recycling`` cells are emptied before each call (vm.py:1017), and on failure the
+    failing node's input cells hold the values ``raise_with_op`` prints (link/utils.py:340)."""
+    aesara, L = aes
+    import aesara.tensor as at
+    import aesara_b200.runtime.vm as vm
+    from aesara_b200.runtime.vm import NodeError, ProgramExecutor
+
+    x = at.fvector("x")
+    cnt = aesara.shared(np.zeros((), "float32"), name="cnt")
+    outs = [at.tanh(x), at.exp(x).sum(), x * 3]
+    # needed-node analysis on the real executor (construction needs no GPU)
+    f_real = aesara.function([x], outs, updates=[(cnt, cnt + x.sum())], mode=L.mode())
+    ex = f_real.vm.executor
+    assert isinstance(ex, ProgramExecutor)
+    needed, computed = ex.needed_nodes([1])
+    ops = [n.op for n, k in zip(ex.program.nodes, needed) if k]
+    assert computed == (1, 3) and 0 < sum(needed) < len(needed)
+    assert "CAReduce" in ops
+    all_needed, _ = ex.needed_nodes([0, 1, 2])
+    assert all(all_needed)
+
+    monkeypatch.setattr(vm, "ProgramExecutor", _OracleExecutor)
+    monkeypatch.setattr(_OracleExecutor, "device_results", False)
+    f = aesara.function([x], outs, updates=[(cnt, cnt + x.sum())], mode=L.mode())
+    xv = np.arange(4, dtype="float32")
+    r = f(xv, output_subset=[2])
+    assert len(r) == 1
+    np.testing.assert_allclose(r[0], 3 * xv)
+    np.testing.assert_allclose(cnt.get_value(), xv.sum())      # the update still ran
+    full = f(xv)
+    assert len(full) == 3
+    np.testing.assert_allclose(cnt.get_value(), 2 * xv.sum())
+
+    # no_recycling: FunctionMaker passes the outputs (types.py:1604-1611)
+    assert f.vm.pre_call_clear, "no_recycling cells were not registered"
+    for cell in f.vm.pre_call_clear:
+        cell[0] = "stale"
+    f(xv)
+    # error: the failing node's input cells are populated for raise_with_op
+    class Boom(_OracleExecutor):
+        def __call__(self, *a, **k):
+            raise NodeError(0, self.program.nodes[0], ValueError("boom"), ["VALUE"] * len(self.program.nodes[0].inputs))
+
+    monkeypatch.setattr(vm, "ProgramExecutor", Boom)
+    g = aesara.function([x], at.tanh(x), mode=L.mode())
+    with pytest.raises(ValueError, match="boom") as ei:
+        g(xv)
+    assert "Apply node that caused the error" in str(ei.value)
+    assert "Inputs shapes" in str(ei.value)
+    assert g.vm.position_of_error == 0
+
+
+def test_shared_constructor_registration(aes):
+    """``aesara.shared`` itself yields device-resident parameters (SURVEY 8f N4 wording):
+    always for device values, for NumPy values after the opt-in."""
+    aesara, L = aes
+    from aesara_b200.sharedvar import B200SharedVariable, register_shared_constructor
+
+    class Dev(_FakeDeviceArray):
+        pass
+
+    from aesara.compile.sharedvalue import shared_constructor
+    from aesara_b200.runtime.device import DeviceArray
+
+    assert shared_constructor.dispatch(DeviceArray).__name__ == "_device_array_constructor"
+    v = aesara.shared(np.zeros(3, "float32"))
+    assert not isinstance(v, B200SharedVariable)
+    register_shared_constructor(ndarrays=True)
+    try:
+        w = aesara.shared(np.ones((2, 3), "float32"), name="w")
+        assert isinstance(w, B200SharedVariable) and w.type.dtype == "float32" and w.type.ndim == 2
+        np.testing.assert_array_equal(w.get_value(), np.ones((2, 3), "float32"))
+    finally:
+        register_shared_constructor(ndarrays=False)
+    assert not isinstance(aesara.shared(np.zeros(3, "float32")), B200SharedVariable)
+
+
+def test_in_place_scatter_is_a_destroyer(aes):
+    """AdvancedIncSubtensor1{inplace} rewrites its input buffer; the executor must
+    know, or cached GEMM operand planes of that buffer go stale."""
+    aesara, L = aes
+    import aesara.tensor as at
+
+    W = at.fmatrix("W")
+    idx = at.lvector("idx")
+    y = at.fmatrix("y")
+    x = at.fmatrix("x")
+    W2 = at.inc_subtensor((W * 1.0)[idx], y)
+    out = x @ W2
+    f = aesara.function([W, idx, y, x], out, mode=L.mode())
+    ex = f.vm.executor
+    scat = [i for i, n in enumerate(ex.program.nodes) if n.op == "AdvancedIncSubtensor1"]
+    assert scat
+    for i in scat:
+        if ex.program.nodes[i].params["inplace"]:
+            assert ex._destroys[i] == [0]
