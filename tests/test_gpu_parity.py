@@ -21,13 +21,27 @@ def rt():
     return ProgramExecutor
 
 
+# fixtures whose whole program is int64 shape arithmetic: nothing to launch
+PURE_METADATA = ()
+_LAUNCHES = {}
+
+
 @pytest.mark.parametrize("name", case_names())
 def test_cuda_matches_reference_and_oracle(rt, name):
     from oracle.program_np import run_program
 
+    from aesara_b200.runtime import lib
+
     prog, ins, want = load_case(name)
     ex = rt(prog)
+    before = lib.load().ab_launch_count()
     got = ex(*[np.array(a) for a in ins])
+    launched = lib.load().ab_launch_count() - before
+    _LAUNCHES[name] = launched
+    # every fixture must reach CUDA: tensor arguments are uploaded whatever their size
+    # (runtime/vm.py host_needed_vars); only programs that are shape arithmetic from end to
+    # end may finish without a launch
+    assert launched > 0 or name in PURE_METADATA, f"{name}: no kernel of libaesara_b200.so ran"
     oracle = run_program(prog, [np.array(a) for a in ins])
     blas = uses_blas(prog)
     for k, (g, w, o) in enumerate(zip(got, want, oracle)):
@@ -468,3 +482,17 @@ def test_gemm_full_size_tile_independence(rt):
     l = lo.owner.view(torch.float32).view(M, N)
     rel = ((l - full.owner.view(torch.float32).view(M, N)).abs().max() / f.abs().max()).item()
     assert rel < 2e-2
+
+
+def test_zz_launch_counts_are_recorded():
+    """Writes the per-fixture launch counts next to the run (gpurun_out/) for the record."""
+    import json
+    import os
+
+    if not _LAUNCHES:
+        pytest.skip("parity matrix did not run in this session")
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "golden_launch_counts.json"), "w") as f:
+        json.dump(_LAUNCHES, f, indent=1, sort_keys=True)
+    assert all(v > 0 for k, v in _LAUNCHES.items() if k not in PURE_METADATA)
