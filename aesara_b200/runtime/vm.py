@@ -50,6 +50,18 @@ def is_host(v):
     return not isinstance(v, DeviceArray)
 
 
+def touched_bytes(v):
+    """Bytes of device memory a kernel moves for this operand: broadcast (stride 0)
+    dimensions are read once ("distinct input bytes + output bytes")."""
+    if not isinstance(v, DeviceArray):
+        return 0
+    n = v.itemsize
+    for s, st in zip(v.shape, v.strides):
+        if st != 0 or s == 0:
+            n *= s
+    return n
+
+
 # Input positions whose *values* a node needs on the host (allocation shapes, indices, axes,
 # BLAS scalars, loop counts): everything the reference computes with int64 shape arithmetic
 # (SURVEY.md a9).  "all" = every input, ("from", k) = inputs k.. .
@@ -160,6 +172,24 @@ class ProgramExecutor:
             elif n.op == "Scan":
                 d = sorted({int(i) for v in n.params.get("destroy_map", {}).values() for i in v})
             self._destroys.append(d)
+        # function inputs some node rewrites in place (directly or through a view of them):
+        # their device copies are never shared between calls
+        root = {}
+        for n in program.nodes:
+            if n.op in ("DimShuffle", "Subtensor", "Reshape", "View", "BroadcastTo", "ExtractDiag",
+                        "Assert", "IfElse") and n.inputs:
+                for o in n.outputs:
+                    root[o] = root.get(n.inputs[0], n.inputs[0])
+        self._destroyed_inputs = set()
+        for n, d in zip(program.nodes, self._destroys):
+            for pos in d:
+                if pos < len(n.inputs):
+                    v = n.inputs[pos]
+                    self._destroyed_inputs.add(root.get(v, v))
+            if d:  # an in-place result aliases the operand it overwrote
+                for o in n.outputs:
+                    v = n.inputs[d[0]]
+                    root[o] = root.get(v, v)
         # row-region fusion (runtime/rowfuse.py): member nodes are skipped and the region runs
         # as one kernel at the position of its last node; operands of skipped nodes must
         # stay alive until then
@@ -306,7 +336,12 @@ class ProgramExecutor:
                 # data goes to the device whatever its size; only values that drive shapes /
                 # indices / BLAS scalars (host_needed_vars) stay host-side while they are small
                 if vid not in self._host_needed or val.size > host_eval.MAX_HOST_ELEMS:
-                    uploads.append((self._first_use.get(vid, 0), vid, val))
+                    if val.size <= host_eval.MAX_HOST_ELEMS and vid not in self._destroyed_inputs:
+                        # a handful of bytes: staged once per distinct value (a replayed CUDA
+                        # graph holds no host copy, runtime/graph.py keys on these bytes)
+                        env[vid] = self.dev(val, key=("arg", vid))
+                    else:
+                        uploads.append((self._first_use.get(vid, 0), vid, val))
                     continue
             elif var.kind == "scalar":
                 val = np.dtype(var.dtype).type(val)
@@ -352,7 +387,11 @@ class ProgramExecutor:
                     self.fused_regions_run += 1
                 if events is not None:
                     e1.record()
-                    events.append((i, e0, e1))
+                    inside = {v for m in fusion.members for v in nodes[m].outputs}
+                    ext = {v for m in fusion.members for v in nodes[m].inputs if v not in inside}
+                    nbytes = sum(touched_bytes(env.get(v)) for v in ext)
+                    nbytes += sum(touched_bytes(env.get(v)) for v in inside)
+                    events.append((i, e0, e1, nbytes))
                 if self.trace is not None:
                     # values a fused region does not materialise are simply absent
                     for m in fusion.members:
@@ -374,14 +413,21 @@ class ProgramExecutor:
             except Exception as exc:
                 self.position_of_error = i
                 raise NodeError(i, node, exc, [env.get(v) for v in node.inputs]) from exc
-            if events is not None:
-                e1.record()
-                events.append((i, e0, e1))
             if len(node.outputs) == 1:
                 env[node.outputs[0]] = outs
             else:
                 for vid, o in zip(node.outputs, outs):
                     env[vid] = o
+            if events is not None:
+                e1.record()
+                seen, nbytes = set(), 0
+                for v in node.inputs:
+                    a = env.get(v)
+                    if isinstance(a, DeviceArray) and (a.ptr, a.shape, a.strides) not in seen:
+                        seen.add((a.ptr, a.shape, a.strides))
+                        nbytes += touched_bytes(a)
+                nbytes += sum(touched_bytes(env.get(v)) for v in node.outputs)
+                events.append((i, e0, e1, nbytes))
             for pos in self._destroys[i]:
                 d = env.get(node.inputs[pos])
                 if isinstance(d, DeviceArray):
@@ -440,7 +486,15 @@ class ProgramExecutor:
         if not self.node_events:
             return []
         torch.cuda.synchronize()
-        return [(i, self.program.nodes[i].op, e0.elapsed_time(e1)) for i, e0, e1 in self.node_events]
+        return [(i, self.program.nodes[i].op, e0.elapsed_time(e1)) for i, e0, e1, _ in self.node_events]
+
+    def node_stats(self):
+        """(node index, op, device ms, bytes of device memory the node's operands span) of the
+        last call (needs ``time_nodes=True``); a fused region is reported at its last node."""
+        if not self.node_events:
+            return []
+        torch.cuda.synchronize()
+        return [(i, self.program.nodes[i].op, e0.elapsed_time(e1), nb) for i, e0, e1, nb in self.node_events]
 
 
 # ---------------------------------------------------------------------------

@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path (BASELINE.json metric): graph-evals/s of an
-optimised Aesara graph executed by the B200 backend, with the roofline of its
-dominant kernels and the CPU baseline timed beside it.
+"""Benchmark of the hot path (BASELINE.json metric): graph-evals/s of an optimised
+Aesara graph executed by the B200 backend, measured THROUGH THE DROP-IN BOUNDARY
+(``aesara.function(..., mode=B200)`` -> ``Function.__call__`` -> ``B200VM`` -> C ABI -> CUDA),
+with the roofline of its dominant kernels and the reference's own C-linker timed beside it.
 
-    python bench.py --gpus 1 --steps 10 --warmup 3                 # headline: MLP fwd+grad
-    python bench.py --workload elemwise                            # fused Elemwise config
-    python bench.py --impl reference                               # CPU arm (oracle port)
-    torchrun --nproc-per-node N bench.py --gpus N ...              # weak scaling over B
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # headline: cfg3 MLP fwd+grad
+    python bench.py --workload elemwise|lstm|logreg|readme          # the other BASELINE configs
+    python bench.py --impl reference                                # the reference C-linker on the host
+    torchrun --nproc-per-node N bench.py --gpus N ...               # weak scaling over batch rows
 
-A "step" is one evaluation of the compiled graph on one batch of synthetic
-inputs.  `value` is measured with inputs resident in HBM; `e2e` goes through the
-public host API (pinned host inputs -> H2D -> graph -> D2H of every output).
+A "step" is one call of the compiled function on one batch of synthetic inputs.
+``value``: device-resident inputs (``trust_input``), outputs left on the device, the
+evaluation replayed as one CUDA graph.  ``device_ms`` / ``roofline``: a second timed region
+of the same K steps launched eagerly with CUDA events around every node.  ``e2e``: the call a
+user makes -- page-locked host ndarrays in, host ndarrays out, copies inside the timed region.
+The front-end the plugin sits behind (graph builder + rewriter) is whichever ``aesara`` is
+importable; on the GPU box that is the travelling copy of the reference (``oracle/_ref``),
+used as the host of the plugin and as the CPU arm, never as a compute fallback.
 """
 
 import argparse
@@ -28,66 +34,65 @@ sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
+TOLERANCE = {"fp32": 1e-5, "tf32": 2e-3, "bf16": 2e-2}
 
 
 # ----------------------------------------------------------------------------- workloads
-def workload_spec(name, args):
+def workload_spec(name, batch=0, hidden=0, n=0, steps_t=0):
     if name == "mlp":
-        B, H = args.batch or 65536, args.hidden or 4096
+        B, H = batch or 65536, hidden or 4096
         return dict(
-            name="mlp", program="cfg3_mlp", B=B, H=H,
+            name="mlp", program="cfg3_mlp", graph="cfg3_mlp", B=B, H=H, rows="B",
             desc=f"cfg3: 2-layer tanh MLP fwd+grad (MSE), batch {B} x hidden {H}, f32 graph",
-            gemm_flops=5 * 2.0 * B * H * H,            # SURVEY §8d: 5 GEMMs x 2BH^2
-            n_gemm=5,
-            elemwise_bytes=14.0 * B * H * 4,           # 14*B*H*s, s=4 (f32 graph)
+            gemm_flops=5 * 2.0 * B * H * H,            # SURVEY 8d: 5 GEMMs x 2BH^2
+            n_gemm=5, shard_inputs=(0, 1),
         )
     if name == "elemwise":
-        n = args.n or (1 << 28)
+        n = n or (1 << 28)
         return dict(
-            name="elemwise", program="cfg2_fused", n=n,
+            name="elemwise", program="cfg2_fused", graph="cfg2_fused_elemwise", n=n, rows="n",
             desc=f"cfg2: fused Elemwise softplus(tanh(x)+y)*z on 3x{n} f32",
-            elemwise_bytes=16.0 * n,                   # 4 arrays x N x 4 B
-            gemm_flops=0.0, n_gemm=0,
+            gemm_flops=0.0, n_gemm=0, shard_inputs=(0, 1, 2),
         )
     if name == "lstm":
-        T, B, H = args.steps_t or 128, args.batch or 8192, args.hidden or 1024
+        T, B, H = steps_t or 128, batch or 8192, hidden or 1024
         return dict(
-            name="lstm", program="cfg4_lstm", T=T, B=B, H=H, graph=True,
+            name="lstm", program="cfg4_lstm", graph="cfg4_lstm_scan", T=T, B=B, H=H, rows="B",
             desc=f"cfg4: Scan LSTM cell, T={T} steps, batch {B}, hidden {H}, f32",
-            gemm_flops=2.0 * T * B * H * 4 * H, n_gemm=T,      # SURVEY §8d: 8.80 TFLOP
-            elemwise_bytes=(T * B * 4 * H + 4 * B * H + H * 4 * H) * 4.0,  # 17.33 GB ideal
+            gemm_flops=2.0 * T * B * H * 4 * H, n_gemm=T,      # SURVEY 8d: 8.80 TFLOP
+            ideal_bytes=(T * B * 4 * H + 4 * B * H + H * 4 * H) * 4.0,  # 17.33 GB (x read once)
         )
     if name == "logreg":
-        N, D = args.n or (1 << 24), args.hidden or 512
+        N, D = n or (1 << 24), hidden or 512
         return dict(
-            name="logreg", program="cfg5_logreg", N=N, D=D, graph=True,
+            name="logreg", program="cfg5_logreg", graph="cfg5_logreg", N=N, D=D, rows="N",
             desc=f"cfg5: logistic-regression cost+grad, {N} rows x {D} f32 per GPU",
-            gemm_flops=0.0, n_gemm=0,
-            elemwise_bytes=(2.0 * N * D + 12.0 * N) * 4,      # SURVEY §8d graph-as-optimised
+            gemm_flops=0.0, n_gemm=0, shard_inputs=(0, 1),
+            graph_bytes=(2.0 * N * D + 12.0 * N) * 4,      # SURVEY 8d graph-as-optimised
             # single-pass row-region fusion (runtime/rowfuse.py): X once, y read by `1 - y` and
             # by the fused kernel, `1 - y` written and read back
             fused_bytes=(1.0 * N * D + 4.0 * N) * 4,
         )
     if name == "readme":
-        n = args.n or 1000
+        n = n or 1000
         return dict(
-            name="readme", program="cfg1_readme", n=n, graph=True,
+            name="readme", program="cfg1_readme", graph="cfg1_readme", n=n, rows=None,
             desc=f"cfg1: README a/a + (M+a).dot(v), {n}x{n} f64",
-            gemm_flops=0.0, n_gemm=0, elemwise_bytes=24.0 * n * n,
+            gemm_flops=0.0, n_gemm=0,
         )
     raise SystemExit(f"unknown workload {name}")
 
 
-def make_inputs_numpy(spec, rng, scale_rows=None):
+def make_inputs_numpy(spec, rng, rows=None):
+    """Seeded host inputs (SURVEY 8d definitions); ``rows`` replaces the batch extent."""
     if spec["name"] == "lstm":
         T, H = spec["T"], spec["H"]
-        B = scale_rows or spec["B"]
+        B = rows or spec["B"]
         x = rng.standard_normal((T, B, 4 * H), dtype=np.float32)
         U = (rng.standard_normal((H, 4 * H), dtype=np.float32) / np.sqrt(H)).astype(np.float32)
         return [x, np.zeros((B, H), np.float32), np.zeros((B, H), np.float32), U]
     if spec["name"] == "logreg":
-        N = scale_rows or spec["N"]
-        D = spec["D"]
+        N, D = rows or spec["N"], spec["D"]
         X = rng.standard_normal((N, D), dtype=np.float32)
         y = (rng.random(N) < 0.5).astype(np.float32)
         w = (rng.standard_normal(D) * 0.01).astype(np.float32)
@@ -96,42 +101,42 @@ def make_inputs_numpy(spec, rng, scale_rows=None):
         n = spec["n"]
         return [np.float64(1.5), rng.standard_normal(n), rng.standard_normal((n, n))]
     if spec["name"] == "mlp":
-        B = scale_rows or spec["B"]
-        H = spec["H"]
+        B, H = rows or spec["B"], spec["H"]
         X = rng.standard_normal((B, H), dtype=np.float32)
         Y = rng.standard_normal((B, H), dtype=np.float32)
         W1 = (rng.standard_normal((H, H), dtype=np.float32) / np.sqrt(H)).astype(np.float32)
         W2 = (rng.standard_normal((H, H), dtype=np.float32) / np.sqrt(H)).astype(np.float32)
         return [X, Y, W1, np.zeros(H, np.float32), W2, np.zeros(H, np.float32)]
-    n = scale_rows or spec["n"]
+    n = rows or spec["n"]
     return [rng.standard_normal(n, dtype=np.float32) for _ in range(3)]
 
 
-def make_inputs_device(spec, seed):
+def make_inputs_device(spec, seed, shared_seed=1234):
+    """Synthetic inputs generated on the device.  Batch data is seeded per rank, parameters
+    (weights) with ``shared_seed`` so that every rank holds the same replica."""
     import torch
 
     from aesara_b200.runtime.device import DeviceArray
 
     g = torch.Generator(device="cuda").manual_seed(seed)
+    gp = torch.Generator(device="cuda").manual_seed(shared_seed)
     if spec["name"] == "mlp":
         B, H = spec["B"], spec["H"]
         X = torch.randn(B, H, device="cuda", generator=g)
         Y = torch.randn(B, H, device="cuda", generator=g)
-        W1 = torch.randn(H, H, device="cuda", generator=g) / H ** 0.5
-        W2 = torch.randn(H, H, device="cuda", generator=g) / H ** 0.5
-        b1 = torch.zeros(H, device="cuda")
-        b2 = torch.zeros(H, device="cuda")
-        ts = [X, Y, W1, b1, W2, b2]
+        W1 = torch.randn(H, H, device="cuda", generator=gp) / H ** 0.5
+        W2 = torch.randn(H, H, device="cuda", generator=gp) / H ** 0.5
+        ts = [X, Y, W1, torch.zeros(H, device="cuda"), W2, torch.zeros(H, device="cuda")]
     elif spec["name"] == "lstm":
         T, B, H = spec["T"], spec["B"], spec["H"]
         x = torch.randn(T, B, 4 * H, device="cuda", generator=g)
-        U = torch.randn(H, 4 * H, device="cuda", generator=g) / H ** 0.5
+        U = torch.randn(H, 4 * H, device="cuda", generator=gp) / H ** 0.5
         ts = [x, torch.zeros(B, H, device="cuda"), torch.zeros(B, H, device="cuda"), U]
     elif spec["name"] == "logreg":
         N, D = spec["N"], spec["D"]
         X = torch.randn(N, D, device="cuda", generator=g)
         y = (torch.rand(N, device="cuda", generator=g) < 0.5).float()
-        w = torch.randn(D, device="cuda", generator=g) * 0.01
+        w = torch.randn(D, device="cuda", generator=gp) * 0.01
         ts = [X, y, w]
         return [DeviceArray.from_torch(t) for t in ts] + [np.float32(0.0)], ts
     elif spec["name"] == "readme":
@@ -143,6 +148,67 @@ def make_inputs_device(spec, seed):
     else:
         ts = [torch.randn(spec["n"], device="cuda", generator=g) for _ in range(3)]
     return [DeviceArray.from_torch(t) for t in ts], ts
+
+
+# ----------------------------------------------------------------------------- front-end
+def front_end():
+    """``aesara`` as the plugin sees it: an installed package, ``$AESARA_B200_REFERENCE``, or
+    the travelling copy of the reference (oracle/_ref).  Returns the module or None."""
+    from aesara_b200.compat import bootstrap
+
+    if not bootstrap.available():
+        from oracle import ref
+
+        ref.activate()
+    if not bootstrap.available():
+        return None
+    return bootstrap.load_aesara()
+
+
+def graph_of(spec):
+    from aesara_b200 import graphs as G
+
+    return getattr(G, spec["graph"])()
+
+
+class ProgramCallable:
+    """Fallback when no front-end is importable: the committed lowered program run by the
+    executor directly (what round 1 measured).  ``boundary`` in the JSON line says which."""
+
+    def __init__(self, spec, precision, device_outputs, cuda_graph):
+        from aesara_b200.ir import Program
+        from aesara_b200.runtime.vm import ProgramExecutor
+
+        prog = Program.load(os.path.join(GOLDEN, spec["program"] + ".json"))
+        self.executor = ProgramExecutor(prog, precision=precision, host_outputs=not device_outputs)
+        self.replay = None
+        if cuda_graph:
+            from aesara_b200.runtime.graph import GraphReplay
+
+            self.replay = GraphReplay(self.executor)
+
+    def __call__(self, *args):
+        return (self.replay or self.executor)(*args)
+
+
+def compile_b200(spec, precision, device_outputs, cuda_graph, shard=None):
+    """-> (callable, executor, boundary).  The callable is an ``aesara`` ``Function`` linked
+    by ``B200Linker`` when a front-end is available."""
+    aesara = front_end()
+    if aesara is None:
+        pc = ProgramCallable(spec, PRECISIONS[precision], device_outputs, cuda_graph)
+        return pc, pc.executor, "lowered program (no front-end importable)"
+    import aesara_b200.linker as L
+
+    i, o = graph_of(spec)
+    kw = {}
+    if shard is not None:
+        kw["shard"] = shard
+    f = aesara.function(i, o, mode=L.mode(precision=precision, device_outputs=device_outputs,
+                                          cuda_graph=cuda_graph, **kw), on_unused_input="ignore")
+    if device_outputs:
+        f.trust_input = True
+    return f, f.vm.executor, "aesara.function(mode=B200) -> Function.__call__"
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -232,127 +298,173 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_baseline(spec, seconds_budget=20.0):
-    """The oracle port (NumPy restatement of the reference's per-Op code) timed on
-    the host cores on a bounded sample of the same workload; extrapolated per row."""
-    from aesara_b200.ir import Program
-    from oracle.program_np import run_program
-
+def _host_threads():
+    n = os.cpu_count() or 1
     try:  # torchrun pins OMP_NUM_THREADS=1: give the BLAS under NumPy every host core back
         from threadpoolctl import threadpool_limits
 
-        threadpool_limits(limits=os.cpu_count())
+        threadpool_limits(limits=n)
     except Exception:
         pass
+    return n
+
+
+def reference_leg(spec, budget_s, want_steps=None):
+    """The reference's OWN CPU implementation of the path: the same symbolic graph compiled by
+    the unmodified reference (oracle/_ref) with its C-linker, ``Mode("cvm", "fast_run")``
+    (aesara/link/vm.py:1057-1174, link/c/c_code/lazylinker_c.c), timed on the host cores with
+    both OpenMP settings.  Full-size evaluations when they fit ``budget_s``,
+    otherwise a stated row sample scaled per row.  Falls back to the NumPy oracle port when no
+    reference copy travelled."""
+    from oracle import ref
+
+    cores = _host_threads()
+    if ref.activate() is None:
+        return port_leg(spec, budget_s)
+    from aesara_b200.compat.bootstrap import load_aesara
+
+    aesara = load_aesara()
+    from aesara.compile.mode import Mode
+
+    fns = {}
+    for omp in (False, True):
+        with aesara.config.change_flags(openmp=omp):
+            i, o = graph_of(spec)
+            f = aesara.function(i, o, mode=Mode("cvm", "fast_run"), on_unused_input="ignore")
+        f.trust_input = True
+        fns[omp] = f
+    rng = np.random.default_rng(0)
+    rows_key = spec["rows"]
+    full = spec[rows_key] if rows_key else None
+
+    def timed(f, ins, reps):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            f(*ins)
+            ts.append(time.perf_counter() - t0)
+        return ts
+
+    def prep(ins):
+        # trust_input skips TensorType.filter: scalars must already be 0-d arrays
+        return [np.asarray(a) for a in ins]
+
+    t_start = time.perf_counter()
+    if full is None:
+        ins = prep(make_inputs_numpy(spec, rng))
+        cal = {omp: min(timed(f, ins, 3)) for omp, f in fns.items()}
+        best = min(cal, key=cal.get)
+        n = want_steps or 20
+        ts = timed(fns[best], ins, n)
+        t = float(np.median(ts))
+        return {"value": 1.0 / t, "unit": "graph-evals/s", "cores": cores, "kind": "reference",
+                "sample": "full size", "steps_timed": n, "ms_per_eval": t * 1e3, "openmp": best,
+                "openmp_false_ms": cal[False] * 1e3, "openmp_true_ms": cal[True] * 1e3,
+                "linker": 'Mode("cvm", "fast_run")'}
+    # calibrate on full/64 rows (at least 256), both OpenMP settings
+    cal_rows = max(min(full, 256), full // 64)
+    ins = prep(make_inputs_numpy(spec, rng, rows=cal_rows))
+    cal = {}
+    for omp, f in fns.items():
+        f(*ins)
+        cal[omp] = min(timed(f, ins, 2))
+    best = min(cal, key=cal.get)
+    f = fns[best]
+    est_full = cal[best] * full / cal_rows
+    left = budget_s - (time.perf_counter() - t_start)
+    if est_full * 2.2 <= left:
+        rows = full
+    else:
+        rows = cal_rows
+        while rows * 2 <= full and est_full * (rows * 2 / full) * 3.2 <= left:
+            rows *= 2
+    if rows != cal_rows:
+        ins = None
+        ins = prep(make_inputs_numpy(spec, rng, rows=rows))
+        f(*ins)  # warm-up at this size (allocations, page faults)
+    per = est_full * rows / full
+    left = budget_s - (time.perf_counter() - t_start)
+    n = int(max(1, min(want_steps or 3, left / max(per, 1e-9))))
+    ts = timed(f, ins, n)
+    t = float(np.median(ts))
+    scale = full / rows
+    out = {"value": 1.0 / (t * scale), "unit": "graph-evals/s", "cores": cores, "kind": "reference",
+           "sample": ("full size, un-extrapolated" if rows == full else
+                      f"{rows} of {full} rows per evaluation; time scaled by {full}/{rows}"),
+           "steps_timed": n, "ms_per_eval": t * scale * 1e3, "ms_per_eval_measured": t * 1e3,
+           "openmp": best, "linker": 'Mode("cvm", "fast_run")',
+           "calibration": {"rows": cal_rows, "openmp_false_ms": cal[False] * 1e3,
+                           "openmp_true_ms": cal[True] * 1e3}}
+    return out
+
+
+def port_leg(spec, budget_s):
+    """NumPy oracle port on a bounded row sample (used only when the reference copy is absent)."""
+    from aesara_b200.ir import Program
+    from oracle.program_np import run_program
+
+    cores = _host_threads()
     prog = Program.load(os.path.join(GOLDEN, spec["program"] + ".json"))
     rng = np.random.default_rng(0)
-    if spec["name"] == "mlp":
-        rows, full = min(spec["B"], 1024), spec["B"]
-        sample = f"B={rows} rows of {full} (H={spec['H']}); time scaled by {full}/{rows}"
-    elif spec["name"] == "lstm":
-        rows, full = min(spec["B"], 128), spec["B"]
-        sample = f"B={rows} batch rows of {full} (T={spec['T']}, H={spec['H']}); time scaled by {full}/{rows}"
-    elif spec["name"] == "logreg":
-        rows, full = min(spec["N"], 1 << 18), spec["N"]
-        sample = f"{rows} of {full} rows (D={spec['D']}); time scaled by {full}/{rows}"
-    elif spec["name"] == "readme":
-        rows, full = None, 1
-        sample = "full size"
-    else:
-        rows, full = min(spec["n"], 1 << 22), spec["n"]
-        sample = f"{rows} of {full} elements; time scaled by {full}/{rows}"
-    ins = make_inputs_numpy(spec, rng, scale_rows=rows)
-    run_program(prog, ins)  # warm-up
-    times = []
-    t_end = time.perf_counter() + seconds_budget
-    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 8):
+    rows_key = spec["rows"]
+    full = spec[rows_key] if rows_key else None
+    rows = None if full is None else max(min(full, 256), full // 64)
+    ins = make_inputs_numpy(spec, rng, rows=rows)
+    run_program(prog, ins)
+    ts = []
+    t_end = time.perf_counter() + budget_s
+    while len(ts) < 2 or (time.perf_counter() < t_end and len(ts) < 8):
         t0 = time.perf_counter()
         run_program(prog, ins)
-        times.append(time.perf_counter() - t0)
-    t = float(np.median(times)) * ((full / rows) if rows else 1.0)
-    return {"value": 1.0 / t, "unit": "graph-evals/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": sample, "ms_per_eval_extrapolated": t * 1e3}
+        ts.append(time.perf_counter() - t0)
+    scale = (full / rows) if rows else 1.0
+    t = float(np.median(ts)) * scale
+    return {"value": 1.0 / t, "unit": "graph-evals/s", "cores": cores, "kind": "port",
+            "sample": "full size" if not rows else f"{rows} of {full} rows; time scaled by {full}/{rows}",
+            "steps_timed": len(ts), "ms_per_eval": t * 1e3}
 
 
-def run_reference_arm(args, spec, rank, world):
+def run_reference_arm(args, spec, rank):
     if rank != 0:
         return
-    cb = None
+    # before libgomp is loaded by the first compiled module (torchrun exports OMP_NUM_THREADS=1)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     t0 = time.perf_counter()
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        cb = cpu_baseline(spec, seconds_budget=5.0)
-        vals.append(cb["value"])
-        if time.perf_counter() - t0 > 120:
-            break
-    v = float(np.median(vals))
-    cb["value"] = v
+    cb = reference_leg(spec, budget_s=150.0, want_steps=args.steps)
+    v = cb["value"]
     line = {
         "impl": "reference", "metric": "graph-evals/s", "value": v, "unit": "graph-evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": spec["desc"], "note": "oracle port (NumPy restatement of the reference "
-                   "C-linker path) on host cores; the reference itself cannot travel to the GPU box"},
-        "cpu_baseline": cb,
+        "n_gpus": args.gpus, "steps": cb["steps_timed"], "steps_requested": args.steps,
+        "warmup": 1, "ms_per_step": cb.get("ms_per_eval_measured", cb["ms_per_eval"]),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if spec["name"] != "readme" else "f64", "data": "synthetic",
+        "config": {"workload": spec["desc"],
+                   "note": ("the unmodified reference (oracle/_ref) through aesara.function with its "
+                            "C-linker on the host cores; each step is " + cb["sample"])
+                   if cb["kind"] == "reference" else
+                   "oracle port (NumPy restatement); no reference copy travelled"},
+        "cpu_baseline": cb, "wall_s": time.perf_counter() - t0,
         "e2e": {"value": v, "unit": "graph-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="mlp", choices=["mlp", "elemwise", "lstm", "logreg", "readme"])
-    ap.add_argument("--steps-t", type=int, default=0, help="Scan length for --workload lstm")
-    ap.add_argument("--graph", type=int, default=-1, help="1/0: replay the evaluation as a CUDA graph")
-    ap.add_argument("--precision", default=None, choices=list(PRECISIONS),
-                    help="GEMM compute policy; default: bf16 for mlp (BASELINE cfg3), fp32 (3xTF32) otherwise")
-    ap.add_argument("--batch", type=int, default=0)
-    ap.add_argument("--hidden", type=int, default=0)
-    ap.add_argument("--n", type=int, default=0)
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    args = ap.parse_args()
-    spec = workload_spec(args.workload, args)
-    if args.precision is None:
-        args.precision = "bf16" if args.workload == "mlp" else "fp32"
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference_arm(args, spec, rank, world)
-        return
+GEMM_OPS = ("Dot22", "Gemm", "Dot22Scalar", "Scan", "Dot", "BatchedDot")
+HBM_OPS = ("Elemwise", "CAReduce", "Gemv", "Ger", "Softmax", "MaxAndArgmax")
 
+
+def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_graph=True,
+            node_region=True, e2e_steps=0, seed=1234):
+    """One workload on this rank's GPU.  Returns a dict of measurements (see main())."""
     import torch
 
-    from aesara_b200.ir import Program
     from aesara_b200.runtime import lib
     from aesara_b200.runtime.device import DeviceArray
-    from aesara_b200.runtime.vm import ProgramExecutor
 
-    torch.cuda.set_device(local_rank)
-    lib.check(lib.load().ab_init(local_rank))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    prec = PRECISIONS[args.precision]
-    prog = Program.load(os.path.join(GOLDEN, spec["program"] + ".json"))
-    use_graph = bool(spec.get("graph")) if args.graph < 0 else bool(args.graph)
-    ex = ProgramExecutor(prog, precision=prec, host_outputs=False, time_nodes=not use_graph)
-    dev_in, keep = make_inputs_device(spec, seed=1234 + rank)
-    run = ex
-    if use_graph:
-        from aesara_b200.runtime.graph import GraphReplay
-
-        run = GraphReplay(ex)
-
+    L = lib.load()
+    f, ex, boundary = compile_b200(spec, precision, device_outputs=True, cuda_graph=use_graph)
+    dev_in, keep = make_inputs_device(spec, seed=seed + rank)
     combiner = None
     if world > 1:
         from aesara_b200.shard import OutputCombiner
@@ -360,7 +472,7 @@ def main():
         combiner = OutputCombiner(world, mode="mean")
 
     def step():
-        outs = run(*dev_in)
+        outs = f(*dev_in)
         if combiner is not None:
             outs = combiner(outs)
         return outs
@@ -370,134 +482,97 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    launches0 = lib.load().ab_launch_count()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    node_ms = {}
-    barrier()
-    e0.record()
-    pending = []
-    for _ in range(args.steps):
-        step()
-        if not use_graph:
-            pending.append(ex.node_events)
-    e1.record()
-    barrier()
-    clk = clocks.stop()
-    ms_total = e0.elapsed_time(e1)
-    launches = lib.load().ab_launch_count() - launches0
-    if use_graph:
-        # a replayed graph re-issues the kernels captured once: count them from one eager call
-        l0 = lib.load().ab_launch_count()
-        ex(*dev_in)
-        torch.cuda.synchronize()
-        launches = (lib.load().ab_launch_count() - l0) * args.steps if run.replays else launches
-    for evs in pending:
-        for i, a, b in evs:
-            node_ms.setdefault(i, []).append(a.elapsed_time(b))
-    t_ms = torch.tensor([ms_total], device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_step = t_ms.item() / args.steps
-    value = world * 1e3 / ms_step  # every rank evaluates its shard once per step
+    def timed_region(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / n
 
-    # per-kind device time (average per step) from the per-node CUDA events
-    gemm_ms, hbm_ms, other_ms = 0.0, 0.0, 0.0
-    fused_gemm = {f.last for f in ex._fusions if type(f).__name__ == "GemmEpilogueFusion"}
-    for i, lst in node_ms.items():
-        # a fused Gemm -> Elemwise region is timed at its last node: it is tensor-pipe work
+    res = {"boundary": boundary}
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    l0 = L.ab_launch_count()
+    ms_step = timed_region(steps)
+    launches = L.ab_launch_count() - l0
+    replay = getattr(getattr(f, "vm", None), "_replay", None) or getattr(f, "replay", None)
+    replayed = bool(replay is not None and replay.replays)
+    res.update(ms_per_step=ms_step, executor="cuda-graph replay" if replayed else "eager launches")
+
+    # second timed region: the same K steps launched eagerly with CUDA events around every node
+    per_node = {}
+    ms_eager = None
+    if node_region:
+        vm = getattr(f, "vm", None)
+        saved = None
+        if vm is not None:
+            saved, vm._replay = vm._replay, None
+        elif hasattr(f, "replay"):
+            saved, f.replay = f.replay, None
+        ex.time_nodes = True
+        step()
+        stats_runs = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l1 = L.ab_launch_count()
+        e0.record()
+        for _ in range(steps):
+            step()
+            stats_runs.append(ex.node_events)
+        e1.record()
+        barrier()
+        launches_eager = L.ab_launch_count() - l1
+        ms_eager = e0.elapsed_time(e1) / steps
+        for evs in stats_runs:
+            for i, a, b, nb in evs:
+                d = per_node.setdefault(i, {"ms": [], "bytes": nb})
+                d["ms"].append(a.elapsed_time(b))
+        ex.time_nodes = False
+        if vm is not None:
+            vm._replay = saved
+        elif hasattr(f, "replay"):
+            f.replay = saved
+        if replayed:
+            launches = launches_eager  # a replayed graph re-issues the kernels captured once
+    clk = clocks.stop()
+    res.update(ms_per_step_eager=ms_eager, gpu_launches=int(launches), clocks=clk,
+               fused_regions_run=ex.fused_regions_run)
+
+    # per-kind device time and per-kernel HBM fractions from the per-node events
+    prog = ex.program
+    fused_gemm = {fu.last for fu in ex._fusions if type(fu).__name__ == "GemmEpilogueFusion" and not fu.broken}
+    fused_any = {fu.last: fu for fu in ex._fusions}
+    gemm_ms = hbm_ms = other_ms = 0.0
+    hbm_nodes = []
+    for i, d in sorted(per_node.items()):
         op = "Gemm" if i in fused_gemm else prog.nodes[i].op
-        t = float(np.mean(lst))
-        if op in ("Dot22", "Gemm", "Dot22Scalar", "Scan"):
+        t = float(np.mean(d["ms"]))
+        if op in GEMM_OPS:
             gemm_ms += t
-        elif op in ("Elemwise", "CAReduce"):
+        elif op in HBM_OPS:
             hbm_ms += t
+            label = prog.nodes[i].label or prog.nodes[i].op
+            if i in fused_any:
+                label = type(fused_any[i]).__name__ + ": " + label
+            if t > 0.02:  # >20 us: a bandwidth figure means something
+                hbm_nodes.append({"node": i, "label": label[:80], "ms": round(t, 4), "bytes": d["bytes"],
+                                  "gbs": d["bytes"] / (t * 1e-3) / 1e9})
         else:
             other_ms += t
-    peaks = measured_peaks()
-    if use_graph:
-        # no per-node events inside a replayed graph: the roofline is taken over the whole
-        # step (conservative: every kernel of the evaluation is charged to the bound resource)
-        roofline_hbm = None
-        if spec["n_gemm"]:
-            ach = spec["gemm_flops"] / (ms_step * 1e-3) / 1e12
-            peak = peaks["bf16"] if args.precision == "bf16" else peaks["bf16"] / 2.0
-            roofline = {"bound": "tensor", "kernel": "whole evaluation (CUDA-graph replay); Gemm = gemm_tcgen05_kernel",
-                        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "peak_source": peaks["src"] + ("" if args.precision == "bf16" else "; tf32 = bf16/2 (nominal ratio)"),
-                        "traffic": None, "ms_per_step": ms_step}
-            ach_h = spec["elemwise_bytes"] / (ms_step * 1e-3) / 1e9
-            roofline_hbm = {"bound": "hbm", "kernel": "whole evaluation", "achieved": ach_h,
-                            "peak": peaks["hbm"], "unit": "GB/s", "frac": ach_h / peaks["hbm"],
-                            "peak_source": peaks["src"], "traffic": None, "ms_per_step": ms_step}
-        else:
-            single_pass = bool(spec.get("fused_bytes")) and ex.fused_regions_run > 0
-            nbytes = spec["fused_bytes"] if single_pass else spec["elemwise_bytes"]
-            ach_h = nbytes / (ms_step * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": "whole evaluation (CUDA-graph replay)"
-                        + ("; ab_rowfused single pass over X" if single_pass else ""),
-                        "achieved": ach_h, "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": ach_h / peaks["hbm"], "peak_source": peaks["src"], "traffic": None,
-                        "ms_per_step": ms_step,
-                        "algorithmic_bytes": nbytes,
-                        "bytes_model": ("single pass: N*D*4 + 16 N (SURVEY 8d: 'report which is implemented')"
-                                        if single_pass else "graph as optimised: 2*N*D*4 + 48 N (SURVEY 8d)")}
-        gemm_ms = hbm_ms = other_ms = None
-    elif spec["n_gemm"]:
-        ach = spec["gemm_flops"] / (gemm_ms * 1e-3) / 1e12
-        peak = peaks["bf16"] if args.precision == "bf16" else peaks["bf16"] / 2.0
-        n_fused = sum(1 for f in ex._fusions if type(f).__name__ == "GemmEpilogueFusion" and not f.broken)
-        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (+operand pack) per Gemm/Dot22 node"
-                    + (f"; {n_fused} of them with the consuming Elemwise node fused into the epilogue" if n_fused else ""),
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "peak_source": peaks["src"] + ("" if args.precision == "bf16" else "; tf32 = bf16/2 (nominal ratio)"),
-                    "traffic": None, "ms_per_step": gemm_ms}
-        ach_h = spec["elemwise_bytes"] / (hbm_ms * 1e-3) / 1e9 if hbm_ms else None
-        roofline_hbm = {"bound": "hbm", "kernel": "fused Elemwise + CAReduce nodes"
-                        + (f" (the algorithmic bytes of all of them over the time of those not absorbed into a GEMM "
-                           f"epilogue: may exceed the peak, SURVEY 8d)" if n_fused else ""),
-                        "achieved": ach_h, "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": ach_h / peaks["hbm"] if ach_h else None,
-                        "peak_source": peaks["src"], "traffic": None, "ms_per_step": hbm_ms}
-    else:
-        ach_h = spec["elemwise_bytes"] / (hbm_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "ab_ew_flat_vec (generated fused Elemwise)",
-                    "achieved": ach_h, "peak": peaks["hbm"], "unit": "GB/s",
-                    "frac": ach_h / peaks["hbm"], "peak_source": peaks["src"], "traffic": None,
-                    "ms_per_step": hbm_ms}
-        roofline_hbm = None
+    res.update(device_ms={"gemm": gemm_ms, "elemwise_careduce": hbm_ms, "other": other_ms}, hbm_nodes=hbm_nodes)
 
-    if roofline.get("bound") == "tensor" and args.precision == "fp32":
-        # fp32-faithful products issue three TF32 MMAs each: the pipe-level ceiling for the
-        # algorithmic flops is a third of the TF32 peak
-        roofline["mma_per_product"] = 3
-        roofline["ceiling_3xtf32"] = roofline["peak"] / 3.0
-        roofline["frac_of_3xtf32_ceiling"] = roofline["achieved"] / (roofline["peak"] / 3.0)
-
-    # DRAM traffic of the dominant kernel, per launch, from the committed ncu --set full summary
-    # of the same command (profiles/; cold-cache, serialised capture)
-    tsrc = None
-    if spec["name"] == "mlp" and args.precision == "bf16":
-        fused = any(type(f).__name__ == "GemmEpilogueFusion" and not f.broken for f in ex._fusions)
-        tsrc = (("r01_gemm_fused_epilogue.txt", "ab_gemm_ep_2cta_f16") if fused
-                else ("r01_gemm_bf16_v4_8warp_epilogue.txt", "gemm_tcgen05_2cta_kernel"))
-    elif spec["name"] == "logreg" and ex.fused_regions_run > 0:
-        tsrc = ("r01_rowfused_logreg.txt", "ab_rowfused")
-    elif spec["name"] == "elemwise":
-        tsrc = ("r01_elemwise_cfg2_v2_unroll1.txt", "ab_ew_flat_vec")
-    if tsrc is not None:
-        roofline["traffic"] = ncu_traffic(*tsrc)
-        roofline["traffic_source"] = f"profiles/{tsrc[0]} ({tsrc[1]}, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
-
-    # end to end through the host API: pinned host inputs, H2D + eval + D2H of every output
-    e2e = None
-    if not args.no_e2e and world == 1:
-        host_in = []
-        h2d = 0
+    # end to end through the public call: pinned host inputs, H2D + eval + D2H of every output
+    if e2e_steps and world == 1:
+        host_in, h2d = [], 0
         for t in keep:
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             h.copy_(t)
@@ -506,57 +581,193 @@ def main():
         template = [None if isinstance(a, DeviceArray) else a for a in dev_in]
         del keep[:]
         del dev_in[:]
-        run = None
+        f = ex = None
+        import gc
+
+        gc.collect()
         torch.cuda.empty_cache()
-        # the public call: host (page-locked) ndarrays in, host ndarrays out
-        ex2 = ProgramExecutor(prog, precision=prec, host_outputs=True)
+        f2, _, _ = compile_b200(spec, precision, device_outputs=False, cuda_graph=False)
         it = iter(host_in)
         host_args = [slot if slot is not None else next(it).numpy() for slot in template]
 
         def e2e_step():
-            res = ex2(*host_args)
-            return sum(np.asarray(r).nbytes for r in res)
+            r = f2(*host_args)
+            r = r if isinstance(r, (list, tuple)) else [r]
+            return sum(np.asarray(a).nbytes for a in r)
 
         d2h = e2e_step()
         torch.cuda.synchronize()
-        n_e2e = max(2, min(args.steps, 5))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(n_e2e):
+        for _ in range(e2e_steps):
             e2e_step()
         b.record()
         torch.cuda.synchronize()
-        e2e_ms = a.elapsed_time(b) / n_e2e
-        e2e = {"value": 1e3 / e2e_ms, "unit": "graph-evals/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": n_e2e}
+        e2e_ms = a.elapsed_time(b) / e2e_steps
+        res["e2e"] = {"value": 1e3 / e2e_ms, "unit": "graph-evals/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                      "call": "Function.__call__ with page-locked host ndarrays in, host ndarrays out"}
+        del f2, host_args, host_in
+    else:
+        del keep[:]
+        del dev_in[:]
+        f = ex = None
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def roofline_of(spec, precision, m, peaks):
+    """The roofline object of the dominant kernel family from one measure() result."""
+    dm = m["device_ms"]
+    if spec["n_gemm"]:
+        t = dm["gemm"] if dm["gemm"] else m["ms_per_step"]
+        ach = spec["gemm_flops"] / (t * 1e-3) / 1e12
+        peak = peaks["bf16"] if precision == "bf16" else peaks["bf16"] / 2.0
+        r = {"bound": "tensor",
+             "kernel": ("ab_lstm_scan (persistent 2-CTA tcgen05 Scan kernel)" if spec["name"] == "lstm" else
+                        "tcgen05 GEMM launches (+operand packs) of the Gemm/Dot22 nodes, consumer Elemwise fused in"),
+             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+             "peak_source": peaks["src"] + (" sustained bf16" if precision == "bf16"
+                                            else "; tf32 = bf16/2 (nominal ratio)"),
+             "traffic": None, "ms_per_step": t,
+             "timed": "CUDA events around every node over the eager timed region"}
+        if precision == "fp32":
+            # fp32-faithful products issue three TF32 MMAs each
+            r["mma_per_product"] = 3
+            r["ceiling_3xtf32"] = peak / 3.0
+            r["frac_of_3xtf32_ceiling"] = ach / (peak / 3.0)
+        if spec["name"] == "lstm":
+            r["hbm_ideal_gbs"] = spec["ideal_bytes"] / (t * 1e-3) / 1e9
+        return r
+    if spec["name"] == "readme":
+        return {"bound": "hbm", "kernel": "launch-latency bound (24 MB working set in L2)", "achieved": None,
+                "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
+    t = dm["elemwise_careduce"] or m["ms_per_step"]
+    single_pass = bool(spec.get("fused_bytes")) and m["fused_regions_run"] > 0
+    if spec["name"] == "logreg":
+        nbytes = spec["fused_bytes"] if single_pass else spec["graph_bytes"]
+        kern = "ab_rowfused (single pass over X)" if single_pass else "Gemv + Elemwise + Sum, node by node"
+    else:
+        nbytes = sum(n["bytes"] for n in m["hbm_nodes"]) or 16.0 * spec["n"]
+        kern = "ab_ew_flat_vec (generated fused Elemwise)"
+    ach = nbytes / (t * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": ach / peaks["hbm"], "peak_source": peaks["src"], "traffic": None, "ms_per_step": t,
+            "algorithmic_bytes": nbytes}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="mlp", choices=["mlp", "elemwise", "lstm", "logreg", "readme"])
+    ap.add_argument("--steps-t", type=int, default=0, help="Scan length for --workload lstm")
+    ap.add_argument("--graph", type=int, default=1, help="1/0: replay the evaluation as a CUDA graph for `value`")
+    ap.add_argument("--precision", default=None, choices=list(PRECISIONS),
+                    help="GEMM compute policy; default: bf16 for mlp (BASELINE cfg3), fp32 (3xTF32) otherwise")
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--hidden", type=int, default=0)
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the one-liners of the other configs")
+    args = ap.parse_args()
+    spec = workload_spec(args.workload, args.batch, args.hidden, args.n, args.steps_t)
+    if args.precision is None:
+        args.precision = "bf16" if args.workload == "mlp" else "fp32"
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, spec, rank)
+        return
+
+    import torch
+
+    from aesara_b200.runtime import lib
+
+    torch.cuda.set_device(local_rank)
+    lib.check(lib.load().ab_init(local_rank))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = measured_peaks()
+    m = measure(spec, args.precision, args.steps, args.warmup, rank, world, dist,
+                use_graph=bool(args.graph), e2e_steps=0 if args.no_e2e else max(2, min(args.steps, 5)))
+    ms_step = m["ms_per_step"]
+    value = world * 1e3 / ms_step  # every rank evaluates its shard once per step
+    roofline = roofline_of(spec, args.precision, m, peaks)
+
+    # DRAM traffic of the dominant kernel, per launch, from the committed ncu --set full summary
+    tsrc = None
+    if spec["name"] == "mlp" and args.precision == "bf16":
+        tsrc = ("r01_gemm_fused_epilogue.txt", "ab_gemm_ep_2cta_f16")
+    elif spec["name"] == "logreg" and m["fused_regions_run"] > 0:
+        tsrc = ("r01_rowfused_logreg.txt", "ab_rowfused")
+    elif spec["name"] == "elemwise":
+        tsrc = ("r01_elemwise_cfg2_v2_unroll1.txt", "ab_ew_flat_vec")
+    if tsrc is not None:
+        roofline["traffic"] = ncu_traffic(*tsrc)
+        roofline["traffic_source"] = f"profiles/{tsrc[0]} ({tsrc[1]}, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+
+    also = None
+    if rank == 0 and world == 1 and not args.no_also and args.workload == "mlp":
+        # the other BASELINE configs and the fp32-faithful policy, a few steps each, so that the
+        # driver's record carries them (value, ms, roofline fraction)
+        also = {}
+        todo = [("mlp_fp32_faithful", workload_spec("mlp", args.batch, args.hidden), "fp32", 3),
+                ("elemwise_cfg2", workload_spec("elemwise"), "fp32", 10),
+                ("lstm_cfg4", workload_spec("lstm"), "fp32", 3),
+                ("logreg_cfg5", workload_spec("logreg"), "fp32", 10),
+                ("readme_cfg1", workload_spec("readme"), "fp32", 50)]
+        for key, sp, prec, k in todo:
+            try:
+                mm = measure(sp, prec, k, 3, use_graph=True)
+                rr = roofline_of(sp, prec, mm, peaks)
+                also[key] = {"workload": sp["desc"], "ms_per_step": mm["ms_per_step"],
+                             "value": 1e3 / mm["ms_per_step"], "steps": k, "executor": mm["executor"],
+                             "bound": rr["bound"], "achieved": rr["achieved"], "unit": rr["unit"],
+                             "frac": rr.get("frac"), "kernel": rr["kernel"],
+                             "frac_of_3xtf32_ceiling": rr.get("frac_of_3xtf32_ceiling"),
+                             "gpu_launches": mm["gpu_launches"]}
+            except Exception as e:  # an auxiliary line must not take the headline down
+                also[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
-        cb = None if args.no_cpu else cpu_baseline(spec)
+        cb = None if args.no_cpu else reference_leg(spec, budget_s=30.0)
         if world == 1:
             par = "single"
         else:
-            from aesara_b200.shard import exchange_plan
-
-            how = exchange_plan(combiner.layout.total, world) if combiner.layout is not None else "allgather"
-            par = (f"dp{world} (batch rows sharded; outputs combined by one NCCL "
-                   + ("all-reduce of the pre-weighted packed outputs)" if how == "allreduce"
-                      else "all-gather of the packed outputs + local weighted sum)"))
+            par = (f"dp{world} (batch rows sharded; outputs combined by one NCCL collective over the "
+                   "packed outputs: all-reduce when large, all-gather + local weighted sum when small)")
         line = {
             "metric": "graph-evals/s", "value": value, "unit": "graph-evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32 (3xTF32)"}[args.precision]
-            if spec["n_gemm"] else "f32",
+            if spec["n_gemm"] else ("f64" if spec["name"] == "readme" else "f32"),
             "data": "synthetic",
-            "config": {"workload": spec["desc"], "parallelism": par,
+            "config": {"workload": spec["desc"], "parallelism": par, "boundary": m["boundary"],
                        "l2": ("working set fits L2: launch-latency bound, reported as evals/s only"
                               if spec["name"] == "readme" else "inputs >> 126 MB L2, no flush needed"),
-                       "executor": "cuda-graph replay" if use_graph else "eager launches + per-node CUDA events",
+                       "executor": m["executor"],
                        "gemm_precision": args.precision if spec["n_gemm"] else None,
+                       "stated_tolerance": (f"norm-wise rtol {TOLERANCE[args.precision]} vs the reference "
+                                            "C-linker (tests/test_gpu_parity.py, tests/test_gpu_function.py)")
+                       if spec["n_gemm"] else "rtol 1e-5 vs the reference C-linker",
                        "per_gpu": {k: spec[k] for k in ("B", "H", "n", "N", "D", "T") if k in spec}},
-            "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "device_ms": {"gemm": gemm_ms, "elemwise_careduce": hbm_ms, "other": other_ms},
-            "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "roofline": roofline,
+            "hbm_kernels": [dict(n, frac=n["gbs"] / peaks["hbm"]) for n in m["hbm_nodes"]],
+            "device_ms": m["device_ms"], "ms_per_step_eager": m["ms_per_step_eager"],
+            "cpu_baseline": cb, "e2e": m.get("e2e"), "gpu_launches": m["gpu_launches"],
+            "clocks": m["clocks"], "also": also,
         }
         print(json.dumps(line))
     if dist is not None:

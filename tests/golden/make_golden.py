@@ -651,6 +651,170 @@ def _():
     return [a, b, c, v], outs, [rnd((4, 6)), rnd((3, 6)), rnd((4, 1)), rnd(5, "int64")]
 
 
+# ---------------------------------------------------------------- device-sized twins
+# Round-1 review: fixtures with a few dozen elements say little about a launch geometry.  The
+# cases below repeat the small tables above at >= 1000 elements per tensor (several CTAs, the
+# vectorised and the ragged tail paths), and add device-sized Join / Split / Shape, NaN / inf /
+# IntDiv, outer-broadcast and 3-D transposed-view cases.
+@case("ew_outer_broadcast_big")
+def _():
+    a, b = at.fmatrix("a"), at.fmatrix("b")
+    return [a, b], [a + b, at.maximum(a, b) * 2, a * b - at.minimum(a, b)], [rnd((1, 1501)), rnd((1103, 1))]
+
+
+@case("ew_transposed_views_big")
+def _():
+    a, b = at.fmatrix("a"), at.fmatrix("b")
+    t = at.tensor3("t", dtype="float32")
+    outs = [a.T * b + 1, at.tanh(t.dimshuffle(2, 0, 1)) - t.dimshuffle(2, 0, 1) ** 2,
+            (a.T + b)[::-1, ::2], t.dimshuffle(1, 2, 0) * 2 + t.dimshuffle(1, 2, 0)[::-1],
+            at.exp(t.dimshuffle(0, 2, 1))[:, ::3, 1:] * 0.5]
+    return [a, b, t], outs, [rnd((67, 45)), rnd((45, 67)), rnd((31, 42, 53))]
+
+
+@case("nan_inf_semantics_f32_big")
+def _():
+    x, y = at.fvector("x"), at.fvector("y")
+    outs = [at.maximum(x, y), at.minimum(x, y), at.lt(x, y), at.ge(x, y), at.eq(x, x), at.neq(x, y),
+            at.switch(at.isnan(x), y, x), x / y, x // y, x % y, at.sqrt(x), at.log(abs(x)), at.exp(x * 40),
+            at.isinf(x / y), at.sgn(x), abs(x), at.clip(x, y, y + 2), at.floor(x), at.tanh(x * 1e6),
+            at.sigmoid(x * 200), at.softplus(x * 200), at.log1p(x), at.true_div(1.0, x) * 0.0, at.pow(x, y),
+            at.int_div(x, y) * 2 + at.mod(x, y), at.ceil(x), at.trunc(y), at.round(x)]
+    sp = np.array([0.0, -0.0, 1.5, -2.5, np.nan, np.inf, -np.inf, 3.0, -3.0, 1e-30, 7.25, -7.25, 0.5, 2.0,
+                   -1.0, 9.0, 1e30, -1e30, 2.5, -0.5], "float32")
+    # every special value against every special value, then ordinary values
+    xs, ys = np.meshgrid(sp, sp, indexing="ij")
+    xv = np.concatenate([xs.ravel(), rnd(1000, "float32", -9.5, 9.5)]).astype("float32")
+    yv = np.concatenate([ys.ravel(), rnd(1000, "float32", -4.0, 4.0)]).astype("float32")
+    return [x, y], outs, [xv, yv]
+
+
+@case("incsubtensor_variants_big")
+def _():
+    x = at.fmatrix("x")
+    v = at.fvector("v")
+    s = at.fscalar("s")
+    outs = [at.set_subtensor(x[1:40], 0.5), at.inc_subtensor(x[::2, 1::3], s), at.set_subtensor(x[:, 2], v[:x.shape[0]]),
+            at.inc_subtensor(x[-1], v[:x.shape[1]] * 2), at.set_subtensor(x[20:50, 10:30], x[0:30, 40:60] + 1),
+            at.inc_subtensor(v[::-1][:300], 10.0), at.set_subtensor(x[3, 4], s * s), at.inc_subtensor(x[1:1], 7.0),
+            at.inc_subtensor(x[::-3, ::-2], x[::-3, ::-2] * 2), at.set_subtensor(x.T[5:25], v[:x.shape[0]])]
+    return [x, v, s], outs, [rnd((71, 93)), rnd(1200), np.float32(1.25)]
+
+
+@case("join_split_shape_big")
+def _():
+    a, b, c = at.fmatrix("a"), at.fmatrix("b"), at.fmatrix("c")
+    v = at.lvector("v")
+    t = at.ftensor3("t")
+    j0 = at.join(0, a, b)
+    j1 = at.join(1, a, c)
+    s = at.split(j1, [20, 47], n_splits=2, axis=1)
+    s3 = at.split(t, [5, 0, 12], n_splits=3, axis=1)
+    outs = [j0, j1 * 2, s[0] + 1, s[1] - 1, at.join(0, v, v * 2), j0.reshape((-1, 2)),
+            at.concatenate([a.T, b.T], axis=1), at.stack([a, a * 3], axis=0),
+            at.join(2, t, t[:, :, ::-1] * 2), s3[0] * 2, s3[1].shape[1] + s3[2].sum(axis=1),
+            at.join(0, a[::2], b[::-1], a[:0]), j0.shape[0] * 1000 + j1.shape[1], at.shape(at.join(1, t, t))[1:],
+            at.join(-2, a.T, c.T)]
+    return [a, b, c, v, t], outs, [rnd((41, 60)), rnd((33, 60)), rnd((41, 7)), rnd(1500, "int64"), rnd((9, 17, 23))]
+
+
+@case("alloc_and_shape_ops_big")
+def _():
+    x = at.fmatrix("x")
+    v = at.fvector("v")
+    n = at.lscalar("n")
+    outs = [at.zeros((n, 30)) + v[:30], at.ones_like(x) * v[:x.shape[1]], at.alloc(v, n, v.shape[0]) * 2,
+            at.fill(x, 2.5) + x, x.shape[0] * 2 + x.shape[1], at.zeros_like(x, dtype="int32") + n,
+            at.alloc(np.float32(1.5), n * 30), at.prod(x.shape) + at.cast(n, "int64"),
+            at.tile(v[:20], (30, 2)), at.repeat(v[:300], 4), at.stack([v, v * 2]).T.sum(axis=1),
+            at.full_like(x, 4.0)[1:, :2] - x[1:, :2], at.shape(x * 2)[::-1] + at.shape(v)[0]]
+    return [x, v, n], outs, [rnd((44, 61)), rnd(61 * 20), np.int64(50)]
+
+
+@case("prod_grad_without_zeros_big")
+def _():
+    x = at.fmatrix("x")
+    d = at.dvector("d")
+    outs = [aesara.grad(x.prod(), x), aesara.grad(x.prod(axis=1).sum(), x), aesara.grad(d.prod() * 2, d),
+            at.math.ProdWithoutZeros(axis=0)(x), at.math.ProdWithoutZeros()(d)]
+    xv = rnd((40, 50), "float32", 0.97, 1.03)
+    xv[1, 2] = 0.0
+    xv[3, 0] = 0.0
+    xv[3, 4] = 0.0
+    xv[30, 44] = 0.0
+    dv = rnd(1100, "float64", 0.99, 1.01)
+    dv[400] = 0.0
+    return [x, d], outs, [xv, dv]
+
+
+@case("blas_edge_shapes_big")
+def _():
+    a, b, c = at.fmatrix("a"), at.fmatrix("b"), at.fmatrix("c")
+    v = at.fvector("v")
+    z = at.fmatrix("z")
+    outs = [at.dot(a[:1], b), at.dot(a, b[:, :1]), at.dot(a[:, :1], b[:1]), at.dot(a[:0], b), at.dot(a, b[:, :0]),
+            at.dot(a[:1], v[:a.shape[1]]), at.dot(v[:a.shape[0]], a), z + 0.5 * at.dot(a, b), at.dot(c, c.T) - at.dot(c.T, c)[:4, :4].sum(),
+            at.dot(a, b).T + at.dot(b.T, a.T), at.outer(v, v)[:3] + 1, at.dot(v, v) * v]
+    return [a, b, c, v, z], outs, [rnd((50, 70)), rnd((70, 60)), rnd((40, 90)), rnd(1080), rnd((50, 60))]
+
+
+@case("ew_scalar_0d_big")
+def _():
+    a, b = at.fscalar("a"), at.dscalar("b")
+    x = at.fvector("x")
+    return [a, b, x], [a * x + a, at.exp(b) * b, a + b, x.sum() * a, x * at.cast(b, "float32") - a],\
+        [np.float32(1.5), np.float64(-0.25), rnd(3301)]
+
+
+@case("scan_cumsum_allsteps_big")
+def _():
+    x = at.fmatrix("x")
+    s0 = at.fvector("s0")
+    res, _ = aesara.scan(lambda x_t, s: s * 0.5 + x_t, sequences=[x], outputs_info=[s0])
+    return [x, s0], [res, res[-1]], [rnd((9, 1400)), rnd(1400)]
+
+
+@case("scan_two_taps_nitsot_big")
+def _():
+    x = at.fmatrix("x")
+    init = at.fmatrix("init")  # two initial rows
+
+    def step(x_t, f_tm2, f_tm1):
+        f = f_tm1 + f_tm2 * 0.5 + x_t
+        return f, at.tanh(f) * 2
+
+    (f, g), _ = aesara.scan(step, sequences=[x], outputs_info=[dict(initial=init, taps=[-2, -1]), None])
+    return [x, init], [f, g, g[-1].sum()], [rnd((9, 1200), "float32", -1, 1), rnd((2, 1200), "float32", -1, 1)]
+
+
+@case("scan_seq_taps_shared_nsteps_big")
+def _():
+    x = at.fmatrix("x")
+    k = at.lscalar("k")
+
+    def step(x_tm1, x_t, x_tp1, acc):
+        return acc + x_tm1 * x_tp1 - x_t
+
+    out, _ = aesara.scan(step, sequences=[dict(input=x, taps=[-1, 0, 1])],
+                         outputs_info=[at.zeros_like(x[0])], n_steps=k)
+    return [x, k], [out, out[-1] * 2], [rnd((11, 1300)), np.int64(7)]
+
+
+@case("scan_while_until_big")
+def _():
+    from aesara.scan.utils import until
+
+    x0 = at.fvector("x0")
+    limit = at.fscalar("limit")
+
+    def step(v, lim):
+        nv = v * 1.25 + 0.5
+        return nv, until(nv.mean() > lim)
+
+    vs, _ = aesara.scan(step, outputs_info=[x0], non_sequences=[limit], n_steps=60)
+    return [x0, limit], [vs, vs[-1], vs.shape[0]], [rnd(2000, "float32", 0, 1), np.float32(300.0)]
+
+
 PY_LINKER_CASES = {"indexing_embedding", "adv_index_pairs", "classifier_int_labels", "cumsum_cumprod", "batched_dot_ifelse"}
 
 

@@ -92,6 +92,48 @@ def test_host_eval_matches_oracle_on_shape_arithmetic():
     assert n >= 5
 
 
+def test_host_eval_matches_oracle_on_float_expressions():
+    """Every scalar expression of every fixture that the host evaluator accepts gives the
+    oracle's value on float (and mixed) operands too: host_eval is a third implementation of
+    the scalar ops (after the generated CUDA bodies and the oracle) and is pinned here."""
+    from aesara_b200.runtime import host_eval
+    from oracle.scalar_np import eval_expr
+
+    rng = np.random.default_rng(5)
+    special = np.array([0.0, -0.0, 1.5, -2.5, 3.0, -3.0, 0.5, 7.25, -7.25, 2.0])
+    n_expr = n_float = 0
+    for name in case_names():
+        prog, _, _ = load_case(name)
+        progs = [prog] + [n.params["inner"] for n in prog.nodes if n.op == "Scan"]
+        for pg in progs:
+            for node in pg.nodes:
+                if node.op not in ("Elemwise", "ScalarOp"):
+                    continue
+                expr = node.params["expr"]
+                if not host_eval.supports(expr):
+                    continue
+                n_expr += 1
+                is_float = any(d.startswith("float") for d in expr["inputs"])
+                n_float += is_float
+                for trial in range(4):
+                    args = []
+                    for d in expr["inputs"]:
+                        dt = np.dtype(d)
+                        if dt.kind == "f":
+                            v = rng.choice(special) if trial % 2 else rng.standard_normal() * 3
+                        elif dt.kind == "b":
+                            v = rng.random() < 0.5
+                        else:
+                            v = rng.integers(0 if dt.kind == "u" else -5, 9)
+                        args.append(np.asarray(v).astype(dt))
+                    a = host_eval.eval_expr(expr, args)
+                    b = eval_expr(expr, args)
+                    for x, y in zip(a, b):
+                        assert np.asarray(x).dtype == np.asarray(y).dtype, (name, expr.get("name"))
+                        np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=f"{name}: {expr.get('name')}")
+    assert n_expr >= 100 and n_float >= 30
+
+
 def _scan_runner(name):
     from aesara_b200.runtime.vm import ProgramExecutor
 
