@@ -53,14 +53,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a0,
   gemm_1cta_body<KIND>(map_a0, map_a1, map_b0, map_b1, p);
 }
 
-template <int KIND>
+template <int KIND, int PAIRS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a0,
                          const __grid_constant__ CUtensorMap map_a1,
                          const __grid_constant__ CUtensorMap map_b0,
                          const __grid_constant__ CUtensorMap map_b1,
                          const __grid_constant__ GemmParams p) {
-  gemm_2cta_body<KIND>(map_a0, map_a1, map_b0, map_b1, p);
+  gemm_2cta_body<KIND, PAIRS>(map_a0, map_a1, map_b0, map_b1, p);
 }
 // ------------------------------------------------------------------ operand packing
 // out planes are [R, pitch] row-major (K-major): out[r*pitch + c] = f(in[r*s_r + c*s_c]).
@@ -321,13 +321,47 @@ bool use_two_cta(long long M, long long N) {
   return allow_2cta && M >= 256 && N >= 256 && (sm_count() % 2 == 0);
 }
 
+// 4-CTA clusters (two CTA pairs stacked along M sharing the B tile by TMA multicast, see
+// gemm_2cta_body<KIND, 2>) for problems with at least two full cluster tiles of rows
+int cluster_pairs(long long M, long long N) {
+  const bool allow = getenv("AB_GEMM_NO_CLUSTER4") == nullptr;  // read per call: tests toggle it
+  return (allow && use_two_cta(M, N) && M >= 1024 && (sm_count() % 4 == 0)) ? 2 : 1;
+}
+
+// how many clusters of `ctas` CTAs of this kernel can be resident at once (the persistent
+// grid): asked from the driver once per kernel, 4-CTA clusters do not tile every GPC
+template <typename Kern>
+int max_clusters(Kern kern, int ctas, size_t smem) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(ctas * sm_count()));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = sm_count() / ctas;
+  }
+  return std::min(n, sm_count() / ctas);
+}
+
+int g_cluster4_resident = 0;  // resident 4-CTA clusters reported by the driver (gemm_run, first use)
+int cluster4_groups() { return g_cluster4_resident > 0 ? g_cluster4_resident : sm_count() / 4; }
+
 int plan_k_splits(int precision, long long M, long long N, long long K) {
   static const char* env = getenv("AB_GEMM_SPLITK");  // 0/1 = off, n = force n ranges
   const bool two = use_two_cta(M, N);
+  const int pairs = cluster_pairs(M, N);
   const long long block_n = two ? 256 : (N >= 256 ? 256 : (N >= 128 ? 128 : 64));
-  const long long tile_m = two ? 2 * BLOCK_M : BLOCK_M;
+  const long long tile_m = two ? 2 * BLOCK_M * pairs : BLOCK_M;
   const long long tiles = ((M + tile_m - 1) / tile_m) * ((N + block_n - 1) / block_n);
-  const long long groups = two ? sm_count() / 2 : sm_count();
+  const long long groups = two ? (pairs == 2 ? cluster4_groups() : sm_count() / 2) : sm_count();
   const long long k_elems = SW_BYTES / (precision == 2 ? 2 : 4);
   const long long num_kb = (K + k_elems - 1) / k_elems;
   if (env) {
@@ -341,7 +375,7 @@ int plan_k_splits(int precision, long long M, long long N, long long K) {
   };
   int best = 1;
   double best_score = eff(1);
-  for (int s = 2; s <= 4; ++s) {
+  for (int s = 2; s <= 8; ++s) {
     if (num_kb / s < 64) break;
     const double score = eff(s) * (1.0 - 0.01 * (s - 1));  // the partial planes are not free
     if (score > best_score * 1.05) { best = s; best_score = score; }
@@ -457,6 +491,7 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     p.b_tile_bytes = (p.block_n / 2) * SW_BYTES;  // this CTA's half of the B tile
     p.b_chunks = (p.block_n / 2) / p.mn_per_chunk;
   }
+  const int pairs = two_cta ? cluster_pairs(M, N) : 1;
   const int tile_m = two_cta ? 2 * BLOCK_M : BLOCK_M;
   const int stage_bytes = parts * (p.a_tile_bytes + p.b_tile_bytes);
   p.stages = std::max(2, std::min(8, (kMaxSmem - 1024) / stage_bytes));
@@ -508,48 +543,64 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     else rc = make_map(&ma[i], A.plane[i], bf16, K, M, A.pitch, BLOCK_M);
     if (rc) return rc;
     if (B.mn_major) rc = make_map(&mb[i], B.plane[i], bf16, N, K, B.pitch, p.k_elems_per_row);
-    else rc = make_map(&mb[i], B.plane[i], bf16, K, N, B.pitch, two_cta ? p.block_n / 2 : p.block_n);
+    else rc = make_map(&mb[i], B.plane[i], bf16, K, N, B.pitch,
+                       two_cta ? (pairs == 2 ? p.block_n / 4 : p.block_n / 2) : p.block_n);
     if (rc) return rc;
   }
   if (parts == 1) { ma[1] = ma[0]; mb[1] = mb[0]; }
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   if (two_cta) {
-    const long long tiles2 = ((N + p.block_n - 1) / p.block_n) * ((M + tile_m - 1) / tile_m) * p.k_splits;
-    const long long clusters = std::min<long long>(tiles2, sm_count() / 2);
+    const int ctas = 2 * pairs;
+    const long long cluster_m = (long long)tile_m * pairs;
+    const long long tiles2 = ((N + p.block_n - 1) / p.block_n) * ((M + cluster_m - 1) / cluster_m) * p.k_splits;
+    // resident clusters of this shape (asked once per variant; 4-CTA clusters do not tile every GPC)
+    static int resident[2][2] = {{0, 0}, {0, 0}};
+    int& res = resident[bf16 ? 1 : 0][pairs - 1];
+    if (!res) {
+      if (pairs == 2) {
+        if (bf16) {
+          AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+          res = max_clusters(gemm_tcgen05_2cta_kernel<1, 2>, ctas, smem);
+        } else {
+          AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+          res = max_clusters(gemm_tcgen05_2cta_kernel<0, 2>, ctas, smem);
+        }
+      } else {
+        if (bf16) AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        else AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        res = sm_count() / 2;
+      }
+      if (pairs == 2) g_cluster4_resident = res;
+    }
+    const long long clusters = std::min<long long>(tiles2, res);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.gridDim = dim3((unsigned)(ctas * clusters));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = ctas;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (ep) {
       cudaKernel_t kern;
-      if ((rc = fused_kernel(ep->module, bf16 ? "ab_gemm_ep_2cta_f16" : "ab_gemm_ep_2cta_tf32", &kern))) return rc;
+      const char* name = pairs == 2 ? (bf16 ? "ab_gemm_ep_4cta_f16" : "ab_gemm_ep_4cta_tf32")
+                                    : (bf16 ? "ab_gemm_ep_2cta_f16" : "ab_gemm_ep_2cta_tf32");
+      if ((rc = fused_kernel(ep->module, name, &kern))) return rc;
       void* args[] = {&ma[0], &ma[1], &mb[0], &mb[1], &p};
       AB_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kern, args));
       g_launches++;
       return AB_OK;
     }
-    if (bf16) {
-      static bool a1 = false;
-      if (!a1) {
-        AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        a1 = true;
-      }
-      AB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<1>, ma[0], ma[1], mb[0], mb[1], p));
+    if (pairs == 2) {
+      if (bf16) AB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<1, 2>, ma[0], ma[1], mb[0], mb[1], p));
+      else AB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<0, 2>, ma[0], ma[1], mb[0], mb[1], p));
     } else {
-      static bool a0 = false;
-      if (!a0) {
-        AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        a0 = true;
-      }
-      AB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<0>, ma[0], ma[1], mb[0], mb[1], p));
+      if (bf16) AB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<1, 1>, ma[0], ma[1], mb[0], mb[1], p));
+      else AB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<0, 1>, ma[0], ma[1], mb[0], mb[1], p));
     }
     g_launches++;
     return splitk_finish(p, st);

@@ -438,7 +438,35 @@ __device__ __forceinline__ void load_tile_2sm(uint8_t* dst, const CUtensorMap* m
 }
 // GemmParams here: block_n = 256 (the pair's N tile), b_tile_bytes = 128 rows * 128 B
 // (this CTA's half), b_chunks = chunks of the half, idesc encodes M = 256, N = 256.
-template <int KIND>
+//
+// PAIRS == 2: a cluster of FOUR CTAs = two such pairs stacked along M (a 512 x 256 cluster
+// tile) that share the B tile.  The 256 x 256 pair tile asks for 64 B/clk/SM from L2 at full
+// tensor rate while the chip delivers ~42 (6300 B/clk over 148 SMs): the mainloop of the
+// 2-CTA kernel is L2->SM bound (tensor pipe 72 % active, profiles/r01_gemm_bf16_v4*).  With
+// two pairs per cluster each CTA fetches its own 128 A rows and only a QUARTER of the B tile
+// (64 of the 256 N rows), which cp.async.bulk.tensor ... .multicast::cluster delivers to the
+// CTA of the same position in both pairs: 24 KB instead of 32 KB per CTA and k-block.
+//   * a CTA's shared-memory stage is now written by its own producer and by its twin in the
+//     other pair, so a stage is free only when BOTH pairs' MMAs have retired it: every
+//     leader's tcgen05.commit multicasts to the empty barriers of all four CTAs
+//     (count = PAIRS);
+//   * tmem_full / tmem_empty stay inside a pair.
+template <int PAIRS>
+__device__ __forceinline__ void load_b_2sm(uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int kc,
+                                           int n0, uint32_t pair, uint16_t mask, const GemmParams& p) {
+  if (PAIRS == 1) {
+    load_tile_2sm(dst, map, bar, kc, n0, p.b_mn, p.b_chunks, p);
+  } else if (!p.b_mn) {
+    // K-major: box {128 B of K, block_n / 4 rows}; this CTA's quarter lands behind the twin's
+    tma_load_2d_2sm_mc(dst + pair * (p.b_tile_bytes / 2), map, bar, kc, n0 + (int)pair * (p.block_n / 4), mask);
+  } else {
+    const int cpq = p.b_chunks / 2;  // chunks per quarter
+    for (int c = (int)pair * cpq; c < ((int)pair + 1) * cpq; ++c)
+      tma_load_2d_2sm_mc(dst + c * p.chunk_bytes, map, bar, n0 + c * p.mn_per_chunk, kc, mask);
+  }
+}
+
+template <int KIND, int PAIRS = 1>
 __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1,
                                                const CUtensorMap& map_b0, const CUtensorMap& map_b1,
                                                const GemmParams& p) {
@@ -453,21 +481,27 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u;   // position inside the CTA pair
+  const uint32_t pair = crank >> 1;   // which pair of the cluster
   const bool leader = rank == 0;
   const int stage_bytes = p.nparts * (p.a_tile_bytes + p.b_tile_bytes);
   const int num_k_blocks = (int)((p.K + p.k_elems_per_row - 1) / p.k_elems_per_row);
-  constexpr int TILE_M = 2 * BLOCK_M;
+  constexpr int TILE_M = 2 * BLOCK_M;        // rows of one pair
+  constexpr int CLUSTER_M = PAIRS * TILE_M;  // rows of the cluster tile
   const long long tiles_n = (p.N + p.block_n - 1) / p.block_n;
-  const long long num_tiles = ((p.M + TILE_M - 1) / TILE_M) * tiles_n;
+  const long long num_tiles = ((p.M + CLUSTER_M - 1) / CLUSTER_M) * tiles_n;
   const long long num_units = num_tiles * p.k_splits;
-  const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const long long cluster_id = blockIdx.x / (2 * PAIRS), n_clusters = gridDim.x / (2 * PAIRS);
   const uint32_t tmem_cols = (uint32_t)(p.acc_stages * p.block_n);
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
+  const uint16_t all_mask = (uint16_t)((1u << (2 * PAIRS)) - 1u);
+  const uint16_t twin_mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));  // same position, both pairs
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], PAIRS);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
@@ -496,7 +530,7 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
       uint32_t phase = 0;
       for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
         AB_UNIT_DECODE
-        const int m0 = (int)((tile / tiles_n) * TILE_M) + (int)rank * BLOCK_M;
+        const int m0 = (int)((tile / tiles_n) * CLUSTER_M) + (int)pair * TILE_M + (int)rank * BLOCK_M;
         const int n0 = (int)((tile % tiles_n) * p.block_n) + (int)rank * (p.block_n / 2);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -504,13 +538,13 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
           if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
           const int kc = kb * p.k_elems_per_row;
           load_tile_2sm(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
-          load_tile_2sm(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0,
-                        p.b_mn, p.b_chunks, p);
+          load_b_2sm<PAIRS>(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0, pair,
+                            twin_mask, p);
           if (p.nparts == 2) {
             load_tile_2sm(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn,
                           p.a_chunks, p);
-            load_tile_2sm(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc,
-                          n0, p.b_mn, p.b_chunks, p);
+            load_b_2sm<PAIRS>(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc,
+                              n0, pair, twin_mask, p);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -553,10 +587,10 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
                 umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
               }
             }
-            tcgen05_commit_2sm(&empty_bar[stage]);  // frees the stage in both CTAs
+            tcgen05_commit_2sm_mask(&empty_bar[stage], all_mask);  // frees the stage in every CTA it is written by
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit_2sm(&tmem_full_bar[as]);  // both CTAs' epilogues may fold the segment
+          tcgen05_commit_2sm_mask(&tmem_full_bar[as], pair_mask);  // both CTAs' epilogues may fold the segment
         }
       }
     }
@@ -571,7 +605,7 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
     uint32_t sit = 0;
     for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
         AB_UNIT_DECODE
-      const long long m0 = (tile / tiles_n) * TILE_M + (long long)rank * BLOCK_M;
+      const long long m0 = (tile / tiles_n) * CLUSTER_M + (long long)pair * TILE_M + (long long)rank * BLOCK_M;
       const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
       for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
         const uint32_t as = sit % (uint32_t)p.acc_stages;
@@ -620,4 +654,12 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1)
 ab_gemm_ep_2cta_f16(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                     const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
                     const __grid_constant__ GemmParams p) { gemm_2cta_body<1>(a0, a1, b0, b1, p); }
+extern "C" __global__ void __launch_bounds__(kThreads, 1)
+ab_gemm_ep_4cta_tf32(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
+                     const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
+                     const __grid_constant__ GemmParams p) { gemm_2cta_body<0, 2>(a0, a1, b0, b1, p); }
+extern "C" __global__ void __launch_bounds__(kThreads, 1)
+ab_gemm_ep_4cta_f16(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
+                    const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
+                    const __grid_constant__ GemmParams p) { gemm_2cta_body<1, 2>(a0, a1, b0, b1, p); }
 #endif

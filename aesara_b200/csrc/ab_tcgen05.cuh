@@ -143,6 +143,24 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same load delivered to every CTA of `mask` (same CTA-relative smem offset in each; the
+// complete_tx goes to the barrier at the same offset in the leader of each destination's pair)
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* map,
+                                                   uint64_t* leader_bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "

@@ -60,6 +60,40 @@ def test_gemm_fp32_faithful(K, m, n, k, layout):
     assert err < 1e-5, f"3xTF32 gemm normwise error {err}"
 
 
+@pytest.mark.parametrize("precision", [0, 2])
+@pytest.mark.parametrize("layout", ["nn", "tn", "nt", "tt"])
+@pytest.mark.parametrize("m,n,k", [(1024, 256, 192), (1500, 520, 1000), (4096, 1024, 512), (2300, 256, 4160)])
+def test_gemm_four_cta_cluster_multicast(K, m, n, k, layout, precision):
+    """M >= 1024 takes the 4-CTA cluster kernel (two CTA pairs sharing the B tile by TMA
+    multicast).  Its per-element arithmetic is the 2-CTA kernel's, so the result must be
+    BIT-IDENTICAL to the 2-CTA path (AB_GEMM_NO_CLUSTER4) for every operand layout (K-major and
+    MN-major B quarters), ragged cluster tiles (second pair partly or wholly out of range) and
+    both the 3xTF32 and bf16 policies; and inside tolerance of a float64 product."""
+    import os
+
+    rng = np.random.default_rng(m + n + k)
+    a = rng.standard_normal((m, k)).astype("float32")
+    b = rng.standard_normal((k, n)).astype("float32")
+    c0 = rng.standard_normal((m, n)).astype("float32")
+    A, B = _dev(a), _dev(b)
+    if layout[0] == "t":
+        A = _dev(np.ascontiguousarray(a.T)).dimshuffle([1, 0])
+    if layout[1] == "t":
+        B = _dev(np.ascontiguousarray(b.T)).dimshuffle([1, 0])
+    C4 = _dev(c0)
+    K.gemm(C4, 0.8, A, B, 0.4, precision=precision)
+    os.environ["AB_GEMM_NO_CLUSTER4"] = "1"
+    try:
+        C2 = _dev(c0)
+        K.gemm(C2, 0.8, A, B, 0.4, precision=precision)
+    finally:
+        del os.environ["AB_GEMM_NO_CLUSTER4"]
+    got = C4.to_numpy()
+    np.testing.assert_array_equal(got, C2.to_numpy())
+    want = 0.4 * c0.astype(np.float64) + 0.8 * (a.astype(np.float64) @ b.astype(np.float64))
+    assert _normwise(got, want) < (1e-5 if precision == 0 else 2e-2)
+
+
 @pytest.mark.parametrize("m,n,k", [(256, 256, 4096), (512, 256, 16384), (256, 512, 65536)])
 @pytest.mark.parametrize("layout", ["nn", "tn"])
 def test_gemm_long_k_accuracy(K, m, n, k, layout):
