@@ -422,9 +422,18 @@ struct EpilogueSpec {
   int nops = 0;
   const float* ptr[4] = {};
   long long rs[4] = {}, cs[4] = {};
-  void* shadow = nullptr;
-  long long shadow_pitch = 0;
+  int nout = 1;
+  float* out_ptr[3] = {};      // values 1.. (value 0 goes to C)
+  long long out_rs[3] = {};
+  void* shadow[3] = {};
+  long long shadow_pitch[3] = {};
+  double* colsum_ws = nullptr;
+  double* fullsum_ws = nullptr;
 };
+
+int fused_block_n(long long M, long long N) {
+  return use_two_cta(M, N) ? 256 : (N >= 256 ? 256 : (N >= 128 ? 128 : 64));
+}
 
 int fused_kernel(Module* m, const char* name, cudaKernel_t* out) {
   auto it = m->named.find(name);
@@ -532,9 +541,20 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
         return fail(AB_ERR_UNSUPPORTED, "fused-epilogue operand %d is not 16-byte aligned", k);
       p.ep_ptr[k] = ep->ptr[k]; p.ep_rs[k] = ep->rs[k]; p.ep_cs[k] = ep->cs[k];
     }
-    if (ep->shadow && ((reinterpret_cast<uintptr_t>(ep->shadow) & 7) || (ep->shadow_pitch & 3)))
-      return fail(AB_ERR_UNSUPPORTED, "bf16 shadow plane is not 8-byte aligned");
-    p.shadow = ep->shadow; p.shadow_pitch = ep->shadow_pitch;
+    if (ep->nout < 1 || ep->nout > 3) return fail(AB_ERR_INVALID, "fused epilogue yields 1..3 values");
+    for (int k = 0; k < 3; ++k) {
+      if (ep->shadow[k] && ((reinterpret_cast<uintptr_t>(ep->shadow[k]) & 7) || (ep->shadow_pitch[k] & 3)))
+        return fail(AB_ERR_UNSUPPORTED, "bf16 shadow plane is not 8-byte aligned");
+      if (ep->out_ptr[k] && ((reinterpret_cast<uintptr_t>(ep->out_ptr[k]) & 15) || (ep->out_rs[k] & 3)))
+        return fail(AB_ERR_UNSUPPORTED, "extra epilogue output %d is not 16-byte aligned", k);
+      p.shadow[k] = ep->shadow[k]; p.shadow_pitch[k] = ep->shadow_pitch[k];
+      p.out_ptr[k] = ep->out_ptr[k]; p.out_rs[k] = ep->out_rs[k];
+    }
+    p.colsum_ws = ep->colsum_ws;
+    p.fullsum_ws = ep->fullsum_ws;
+    p.fullsum_cols = 2 * ((N + p.block_n - 1) / p.block_n);
+  } else if (!C) {
+    return fail(AB_ERR_INVALID, "null output matrix");
   }
   CUtensorMap ma[2], mb[2];
   int rc;
@@ -717,11 +737,26 @@ extern "C" int ab_gemm_packed_fused(int precision, int64_t m, int64_t n, int64_t
     spec.rs[i] = ep->rs[i];
     spec.cs[i] = ep->cs[i];
   }
-  spec.shadow = ep->shadow_bf16;
-  spec.shadow_pitch = ep->shadow_pitch;
+  spec.nout = ep->n_outputs;
+  for (int i = 0; i < 3; ++i) {
+    spec.out_ptr[i] = static_cast<float*>(ep->out_f32[i]);
+    spec.out_rs[i] = ep->out_rs[i];
+    spec.shadow[i] = ep->shadow_bf16[i];
+    spec.shadow_pitch[i] = ep->shadow_pitch[i];
+  }
+  spec.colsum_ws = static_cast<double*>(ep->colsum_ws);
+  spec.fullsum_ws = static_cast<double*>(ep->fullsum_ws);
   return ab::gemm_run(precision, m, n, k, (float)alpha, pa, pb, (float)beta, static_cast<float*>(C),
                       c_rs, c_cs, ab::as_stream(stream), static_cast<const float*>(Cin), cin_rs,
                       cin_cs, nullptr, 0, &spec);
+}
+
+extern "C" int ab_gemm_fused_layout(int64_t m, int64_t n, int64_t* row_blocks, int64_t* fullsum_cols) {
+  if (!row_blocks || !fullsum_cols) return ab::fail(AB_ERR_INVALID, "null out pointer");
+  *row_blocks = (m + 31) / 32;
+  const int bn = ab::fused_block_n(m, n);
+  *fullsum_cols = 2 * ((n + bn - 1) / bn);
+  return AB_OK;
 }
 
 extern "C" int ab_gemm_packed_workspace_bytes(int precision, int64_t m, int64_t n, int64_t k,

@@ -36,8 +36,21 @@ struct GemmParams {
   // K-major operand plane for the GEMM that consumes it next
   const float* ep_ptr[4];
   long long ep_rs[4], ep_cs[4];
-  void* shadow;
-  long long shadow_pitch;
+  // the epilogue program yields AB_EP_NOUT values per element.  Value 0 goes to C (when C is
+  // not null), value k >= 1 to out_ptr[k] ([M, out_rs[k]] rows, unit column stride; null =
+  // not materialised); shadow[k] (optional) receives the bf16 copy of value k as a
+  // [M, shadow_pitch[k]] K-major operand plane for the GEMM that consumes it next.
+  float* out_ptr[3];
+  long long out_rs[3];
+  void* shadow[3];
+  long long shadow_pitch[3];
+  // reductions of one value each, accumulated in float64 like the reference's CAReduce
+  // (tensor/elemwise.py:1371-1385): colsum_ws[rb][col] = sum over the 32 rows of row block
+  // rb of value AB_EP_COLSUM; fullsum_ws[rb][cb] = sum of value AB_EP_FULLSUM over row block
+  // rb and column block cb (half a tile).  A second, deterministic pass adds the partials.
+  double* colsum_ws;
+  double* fullsum_ws;
+  long long fullsum_cols;
 };
 
 // one operand tile -> shared memory.  K-major: a single box {128 B of K, tile rows};
@@ -178,36 +191,6 @@ struct EpilogueOut {
 #pragma unroll
               for (int t = 0; t < 8; ++t) v[t] += p.beta * o[t];
             }
-#ifdef AB_EPILOGUE
-            {
-              float e[4][8];
-#pragma unroll
-              for (int k = 0; k < AB_EP_NOPS; ++k) {
-                const float* q = p.ep_ptr[k] + row * p.ep_rs[k] + (col0 + j) * p.ep_cs[k];
-                if (p.ep_cs[k] == 1) {
-                  ld8(q, e[k], ((reinterpret_cast<uintptr_t>(p.ep_ptr[k]) & 31) == 0) && ((p.ep_rs[k] & 7) == 0));
-                } else {
-#pragma unroll
-                  for (int t = 0; t < 8; ++t) e[k][t] = q[t * p.ep_cs[k]];
-                }
-              }
-#pragma unroll
-              for (int t = 0; t < 8; ++t) v[t] = AB_EP_CALL(v[t], t);
-              if (p.shadow) {
-                uint32_t h[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[t]) : "f"(v[2 * t + 1]), "f"(v[2 * t]));
-                uint16_t* sp = static_cast<uint16_t*>(p.shadow) + row * p.shadow_pitch + col0 + j;
-                if (((reinterpret_cast<uintptr_t>(p.shadow) & 15) == 0) && ((p.shadow_pitch & 7) == 0)) {
-                  *reinterpret_cast<uint4*>(sp) = make_uint4(h[0], h[1], h[2], h[3]);
-                } else {
-                  *reinterpret_cast<uint2*>(sp) = make_uint2(h[0], h[1]);
-                  *reinterpret_cast<uint2*>(sp + 4) = make_uint2(h[2], h[3]);
-                }
-              }
-            }
-#endif
             st8(crow + col0 + j, v, wide_out);
           }
         } else {
@@ -217,19 +200,6 @@ struct EpilogueOut {
             if (col < p.N) {
               float v = p.alpha * acc[c * 32 + j];
               if (p.beta != 0.0f) v += p.beta * irow[col * p.cin_cs];
-#ifdef AB_EPILOGUE
-              {
-                float e[4][1];
-#pragma unroll
-                for (int k = 0; k < AB_EP_NOPS; ++k) e[k][0] = p.ep_ptr[k][row * p.ep_rs[k] + col * p.ep_cs[k]];
-                v = AB_EP_CALL(v, 0);
-                if (p.shadow) {
-                  uint32_t b2;
-                  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b2) : "f"(0.0f), "f"(v));
-                  static_cast<uint16_t*>(p.shadow)[row * p.shadow_pitch + col] = (uint16_t)(b2 & 0xFFFFu);
-                }
-              }
-#endif
               crow[col * p.c_cs] = v;
             }
           }
@@ -237,6 +207,160 @@ struct EpilogueOut {
       }
     }
   }
+#ifdef AB_EPILOGUE
+  // ---- fused consumer region (codegen/gemm_epilogue.py) -------------------------------
+  // The generated AB_EP_EVAL(V, E, T, O) evaluates the region's scalar program on
+  // v = alpha*acc + beta*Cin and the memory operands E[k][T], leaving its AB_EP_NOUT values
+  // in O[0..][T].  Every lane of the warp stays in the function (rows beyond M contribute
+  // zeros and store nothing): the column sums are exchanged with warp shuffles.
+  __device__ __forceinline__ void put_outputs(const float (&o)[AB_EP_NOUT][8], long long row, long long col,
+                                              bool live) const {
+#pragma unroll
+    for (int k = 0; k < AB_EP_NOUT; ++k) {
+      float* dst = k == 0 ? p.C : p.out_ptr[k];
+      const long long rs = k == 0 ? p.c_rs : p.out_rs[k];
+      if (dst && live)
+        st8(dst + row * rs + col, o[k], ((rs & 7) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 31) == 0));
+      if (p.shadow[k] && live) {
+        uint32_t h[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[t]) : "f"(o[k][2 * t + 1]), "f"(o[k][2 * t]));
+        uint16_t* sp = static_cast<uint16_t*>(p.shadow[k]) + row * p.shadow_pitch[k] + col;
+        if (((reinterpret_cast<uintptr_t>(p.shadow[k]) & 15) == 0) && ((p.shadow_pitch[k] & 7) == 0)) {
+          *reinterpret_cast<uint4*>(sp) = make_uint4(h[0], h[1], h[2], h[3]);
+        } else {
+          *reinterpret_cast<uint2*>(sp) = make_uint2(h[0], h[1]);
+          *reinterpret_cast<uint2*>(sp + 4) = make_uint2(h[2], h[3]);
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void store_fused(float (&acc)[kAccRegs], long long row, long long n0,
+                                              int nchunks, int lane) const {
+    const bool live = row < p.M;
+    const long long rb = row >> 5;  // 32-row block of this warp (row - lane is a multiple of 32)
+    float* crow = p.C + (live ? row : 0) * p.c_rs;
+    const float* irow = p.Cin + (live ? row : 0) * p.cin_rs;
+    // extra outputs / shadows are row-contiguous by contract; C and Cin decide the vector path
+    const bool vec = (p.c_cs == 1 || !p.C) && (!p.C || (((p.c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0))) &&
+                     (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
+                                         ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
+#if AB_EP_FULLSUM >= 0
+    double fs = 0.0;
+#endif
+#pragma unroll
+    for (int c = 0; c < kAccRegs / 32; ++c) {
+      if (c < nchunks) {
+        const long long col0 = n0 + c * 32;
+        if (vec && col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = p.alpha * acc[c * 32 + j + t];
+            if (p.beta != 0.0f && live) {
+              float o[8];
+              ld8(irow + col0 + j, o, wide_in);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[t] += p.beta * o[t];
+            }
+            float e[4][8];
+#pragma unroll
+            for (int k = 0; k < AB_EP_NOPS; ++k) {
+              const float* q = p.ep_ptr[k] + (live ? row : 0) * p.ep_rs[k] + (col0 + j) * p.ep_cs[k];
+              if (p.ep_cs[k] == 1) {
+                ld8(q, e[k], ((reinterpret_cast<uintptr_t>(p.ep_ptr[k]) & 31) == 0) && ((p.ep_rs[k] & 7) == 0));
+              } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) e[k][t] = q[t * p.ep_cs[k]];
+              }
+            }
+            float o[AB_EP_NOUT][8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { AB_EP_EVAL(v[t], e, t, o); }
+            put_outputs(o, row, col0 + j, live);
+#if AB_EP_COLSUM >= 0
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[c * 32 + j + t] = live ? o[AB_EP_COLSUM][t] : 0.0f;
+#endif
+#if AB_EP_FULLSUM >= 0
+            if (live) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) fs += (double)o[AB_EP_FULLSUM][t];
+            }
+#endif
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long col = col0 + j;
+            const bool in = live && col < p.N;
+            float o[AB_EP_NOUT][8];
+            if (in) {
+              float v = p.alpha * acc[c * 32 + j];
+              if (p.beta != 0.0f) v += p.beta * irow[col * p.cin_cs];
+              float e[4][8];
+#pragma unroll
+              for (int k = 0; k < AB_EP_NOPS; ++k) e[k][0] = p.ep_ptr[k][row * p.ep_rs[k] + col * p.ep_cs[k]];
+              AB_EP_EVAL(v, e, 0, o);
+#pragma unroll
+              for (int k = 0; k < AB_EP_NOUT; ++k) {
+                if (k == 0) { if (p.C) crow[col * p.c_cs] = o[0][0]; }
+                else if (p.out_ptr[k]) p.out_ptr[k][row * p.out_rs[k] + col] = o[k][0];
+                if (p.shadow[k]) {
+                  uint32_t b2;
+                  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b2) : "f"(0.0f), "f"(o[k][0]));
+                  static_cast<uint16_t*>(p.shadow[k])[row * p.shadow_pitch[k] + col] = (uint16_t)(b2 & 0xFFFFu);
+                }
+              }
+            }
+#if AB_EP_COLSUM >= 0
+            acc[c * 32 + j] = in ? o[AB_EP_COLSUM][0] : 0.0f;
+#endif
+#if AB_EP_FULLSUM >= 0
+            if (in) fs += (double)o[AB_EP_FULLSUM][0];
+#endif
+          }
+        }
+#if AB_EP_COLSUM >= 0
+        {
+          // 32 x 32 transpose-reduce: after the step with distance h every lane keeps the half
+          // of its columns selected by bit h of its lane index; lane l ends with column col0 + l
+          double d[16];
+          {
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float keep = up ? acc[c * 32 + 16 + i] : acc[c * 32 + i];
+              const float send = up ? acc[c * 32 + i] : acc[c * 32 + 16 + i];
+              d[i] = (double)keep + (double)__shfl_xor_sync(0xffffffffu, send, 16);
+            }
+          }
+#pragma unroll
+          for (int h = 8; h >= 1; h >>= 1) {
+            const bool up = (lane & h) != 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i < h) {
+                const double keep = up ? d[h + i] : d[i];
+                const double send = up ? d[i] : d[h + i];
+                d[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+              }
+            }
+          }
+          if (rb * 32 < p.M && col0 + lane < p.N) p.colsum_ws[rb * p.N + col0 + lane] = d[0];
+        }
+#endif
+      }
+    }
+#if AB_EP_FULLSUM >= 0
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, h);
+    if (lane == 0 && rb * 32 < p.M) p.fullsum_ws[rb * p.fullsum_cols + n0 / (p.block_n >> 1)] = fs;
+#endif
+  }
+#endif  // AB_EPILOGUE
 };
 
 // work unit -> (tile, K range); consecutive units of a tile go to different CTAs
@@ -399,8 +523,12 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
                      : "memory");
       }
+#ifdef AB_EPILOGUE
+      eo.store_fused(acc, m0 + q * 32 + lane, n0, nchunks, lane);  // fused launches are never split along K
+#else
       if (split == 0) eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
       else eo.store_partial(acc, m0 + q * 32 + lane, n0, nchunks, split);
+#endif
     }
   }
   tcgen05_fence_before();
@@ -620,8 +748,12 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
                          smem_u32(&tmem_empty_bar[as]) & kPeerBitMask)
                      : "memory");
       }
+#ifdef AB_EPILOGUE
+      eo.store_fused(acc, m0 + q * 32 + lane, n0, nchunks, lane);  // fused launches are never split along K
+#else
       if (split == 0) eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
       else eo.store_partial(acc, m0 + q * 32 + lane, n0, nchunks, split);
+#endif
     }
   }
   tcgen05_fence_before();

@@ -338,17 +338,41 @@ def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision
                 ep.ptr[i] = a.ptr
                 ep.rs[i] = 0 if a.shape[0] == 1 else a.strides[0]
                 ep.cs[i] = 0 if a.shape[1] == 1 else a.strides[1]
-            shadow = None
-            if epilogue.want_shadow and C_.strides == (n, 1):
-                shadow = torch.empty(m * n * 2, dtype=torch.uint8, device=A.owner.device)
-                ep.shadow_bf16 = shadow.data_ptr()
-                ep.shadow_pitch = n
+            plan = epilogue.out_plan
+            ep.n_outputs = len(plan)
+            arrays, shadows = [], []
+            for i, (store, want_shadow) in enumerate(plan):
+                # value 0 lives in C_; a value that is not stored still gets its (unwritten)
+                # float32 buffer: it is what identifies the bf16 plane in the pack cache
+                arr = C_ if i == 0 else DeviceArray.empty((m, n), "float32")
+                arrays.append(arr)
+                if i >= 1 and store:
+                    ep.out_f32[i] = arr.ptr
+                    ep.out_rs[i] = arr.strides[0]
+                sh = None
+                if want_shadow and arr.strides == (n, 1):
+                    buf = torch.empty(m * n * 2, dtype=torch.uint8, device=A.owner.device)
+                    ep.shadow_bf16[i] = buf.data_ptr()
+                    ep.shadow_pitch[i] = n
+                    sh = (buf, n)
+                elif not store:
+                    raise _lib.AbError(5, "fused epilogue value is neither stored nor shadowed")
+                shadows.append(sh)
+            if epilogue.colsum or epilogue.fullsum:
+                rows, cols = C.c_int64(), C.c_int64()
+                _lib.check(lib.ab_gemm_fused_layout(m, n, C.byref(rows), C.byref(cols)))
+                if epilogue.colsum:
+                    epilogue.colsum_ws = DeviceArray.empty((rows.value, n), "float64")
+                    ep.colsum_ws = epilogue.colsum_ws.ptr
+                if epilogue.fullsum:
+                    epilogue.fullsum_ws = DeviceArray.empty((rows.value * cols.value,), "float64")
+                    ep.fullsum_ws = epilogue.fullsum_ws.ptr
+            c_ptr = C_.ptr if plan[0][0] else None
             _lib.check(lib.ab_gemm_packed_fused(precision, m, n, k, float(alpha), C.byref(opa), C.byref(opb),
-                                                float(beta), *cin_args, C_.ptr, C_.strides[0],
+                                                float(beta), *cin_args, c_ptr, C_.strides[0],
                                                 C_.strides[1], C.byref(ep), stream_handle()))
             epilogue.applied = True
-            if shadow is not None:
-                epilogue.shadow = (shadow, n)
+            epilogue.arrays, epilogue.shadows = arrays, shadows
             return
         need = C.c_size_t()
         _lib.check(lib.ab_gemm_packed_workspace_bytes(precision, m, n, k, C.byref(need)))

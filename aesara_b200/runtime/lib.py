@@ -141,6 +141,7 @@ SIGNATURES = {
         C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]
     ),
     "ab_gemm_tensorcore_eligible": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    "ab_gemm_fused_layout": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ab_softmax": (
         C.c_int,
         [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -191,8 +192,13 @@ class GemmEpilogue(C.Structure):
         ("ptr", C.c_void_p * 4),
         ("rs", C.c_int64 * 4),
         ("cs", C.c_int64 * 4),
-        ("shadow_bf16", C.c_void_p),
-        ("shadow_pitch", C.c_int64),
+        ("n_outputs", C.c_int32),
+        ("out_f32", C.c_void_p * 3),
+        ("out_rs", C.c_int64 * 3),
+        ("shadow_bf16", C.c_void_p * 3),
+        ("shadow_pitch", C.c_int64 * 3),
+        ("colsum_ws", C.c_void_p),
+        ("fullsum_ws", C.c_void_p),
     ]
 
 

@@ -370,37 +370,39 @@ class ProgramExecutor:
                         torch.cuda.current_stream().wait_event(ev)
             fusion = self._fusion_of.get(i)
             if fusion is not None:
-                if i != fusion.last:
-                    continue  # deferred to the region's last node
-                if events is not None:
-                    e0 = torch.cuda.Event(enable_timing=True)
-                    e1 = torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                try:
-                    done = fusion.run(self, env)
-                except Exception as exc:
-                    self.position_of_error = i
-                    raise NodeError(i, node, exc, [env.get(v) for v in node.inputs]) from exc
-                if not done:
-                    self._run_nodes(fusion.members, env)
-                else:
-                    self.fused_regions_run += 1
-                if events is not None:
-                    e1.record()
-                    inside = {v for m in fusion.members for v in nodes[m].outputs}
-                    ext = {v for m in fusion.members for v in nodes[m].inputs if v not in inside}
-                    nbytes = sum(touched_bytes(env.get(v)) for v in ext)
-                    nbytes += sum(touched_bytes(env.get(v)) for v in inside)
-                    events.append((i, e0, e1, nbytes))
-                if self.trace is not None:
-                    # values a fused region does not materialise are simply absent
-                    for m in fusion.members:
-                        vals = [env.get(v) for v in nodes[m].outputs]
-                        if all(v is not None for v in vals):
-                            self.trace[m] = [v.to_numpy() if isinstance(v, DeviceArray) else np.array(v, copy=True)
-                                             for v in vals]
-                for v in self._free_after[i]:
-                    env.pop(v, None)
+                # a region runs once, at its anchor (its last node unless the region says
+                # otherwise); the other member positions are skipped
+                if i == getattr(fusion, "anchor", fusion.last):
+                    if events is not None:
+                        e0 = torch.cuda.Event(enable_timing=True)
+                        e1 = torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                    try:
+                        done = fusion.run(self, env)
+                    except Exception as exc:
+                        self.position_of_error = i
+                        raise NodeError(i, node, exc, [env.get(v) for v in node.inputs]) from exc
+                    if not done:
+                        self._run_nodes(fusion.members, env)
+                    else:
+                        self.fused_regions_run += 1
+                    if events is not None:
+                        e1.record()
+                        inside = {v for m in fusion.members for v in nodes[m].outputs}
+                        ext = {v for m in fusion.members for v in nodes[m].inputs if v not in inside}
+                        nbytes = sum(touched_bytes(env.get(v)) for v in ext)
+                        nbytes += sum(touched_bytes(env.get(v)) for v in inside)
+                        events.append((i, e0, e1, nbytes))
+                    if self.trace is not None:
+                        # values a fused region does not materialise are simply absent
+                        for m in fusion.members:
+                            vals = [env.get(v) for v in nodes[m].outputs]
+                            if all(v is not None for v in vals):
+                                self.trace[m] = [v.to_numpy() if isinstance(v, DeviceArray) else np.array(v, copy=True)
+                                                 for v in vals]
+                if i == fusion.last:
+                    for v in self._free_after[i]:
+                        env.pop(v, None)
                 continue
             if events is not None:
                 e0 = torch.cuda.Event(enable_timing=True)

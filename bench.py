@@ -549,8 +549,9 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
 
     # per-kind device time and per-kernel HBM fractions from the per-node events
     prog = ex.program
-    fused_gemm = {fu.last for fu in ex._fusions if type(fu).__name__ == "GemmEpilogueFusion" and not fu.broken}
-    fused_any = {fu.last: fu for fu in ex._fusions}
+    fused_gemm = {getattr(fu, "anchor", fu.last) for fu in ex._fusions
+                  if type(fu).__name__ == "GemmEpilogueFusion" and not fu.broken}
+    fused_any = {getattr(fu, "anchor", fu.last): fu for fu in ex._fusions}
     gemm_ms = hbm_ms = other_ms = 0.0
     hbm_nodes = []
     for i, d in sorted(per_node.items()):

@@ -177,20 +177,33 @@ int ab_gemm_packed(int precision, int64_t m, int64_t n, int64_t k, double alpha,
                    int64_t c_cs, void* workspace, size_t workspace_bytes, void* stream);
 int ab_gemm_packed_workspace_bytes(int precision, int64_t m, int64_t n, int64_t k, size_t* bytes);
 
-/* Gemm/Dot22 followed by the Elemwise node that consumes it, in one kernel: `module` is
- * the NVRTC build of the tcgen05 kernels with that node's scalar expression as the
- * epilogue (aesara_b200/codegen/gemm_epilogue.py); C <- f(beta*Cin + alpha*A@B, e0..e3)
- * with e_i read at ptr[i][row*rs[i] + col*cs[i]] (stride 0 broadcasts).  `shadow_bf16`
- * (optional) receives the bf16 copy of the result as a [m, shadow_pitch] plane: the
- * packed operand of the next product (replaces ab_gemm_pack for that matrix). */
+/* Gemm/Dot22 followed by the Elemwise (and Sum) nodes that consume it, in one kernel:
+ * `module` is the NVRTC build of the tcgen05 kernels with the scalar program of those nodes
+ * as the epilogue (aesara_b200/codegen/gemm_epilogue.py).  Per element the program maps
+ * v = beta*Cin + alpha*A@B and the operands e_i = ptr[i][row*rs[i] + col*cs[i]] (stride 0
+ * broadcasts) to n_outputs values.  Value 0 is stored to C (C may be NULL: not stored),
+ * value k >= 1 to out_f32[k] ([m, out_rs[k]] rows, unit column stride; NULL: not stored).
+ * `shadow_bf16[k]` (optional) receives the bf16 copy of value k as a [m, shadow_pitch[k]]
+ * plane: the packed operand of the next product (replaces ab_gemm_pack for that matrix).
+ * Reductions the module was generated with (tensor/elemwise.py:1221 CAReduce{add}, float64
+ * accumulators like the reference): column sums of one value as partials per 32-row block,
+ * colsum_ws[row_blocks][n]; the sum of all elements of one value as partials
+ * fullsum_ws[row_blocks][fullsum_cols] (ab_gemm_fused_layout gives the extents).  The
+ * caller adds the partials (a deterministic second pass). */
 typedef struct {
   ab_module* module;
   int32_t n_operands;
   const void* ptr[4];
   int64_t rs[4], cs[4];
-  void* shadow_bf16;
-  int64_t shadow_pitch;
+  int32_t n_outputs;
+  void* out_f32[3];
+  int64_t out_rs[3];
+  void* shadow_bf16[3];
+  int64_t shadow_pitch[3];
+  void* colsum_ws;
+  void* fullsum_ws;
 } ab_gemm_epilogue;
+int ab_gemm_fused_layout(int64_t m, int64_t n, int64_t* row_blocks, int64_t* fullsum_cols);
 int ab_gemm_packed_fused(int precision, int64_t m, int64_t n, int64_t k, double alpha,
                          const ab_gemm_operand* A, const ab_gemm_operand* B, double beta,
                          const void* Cin, int64_t cin_rs, int64_t cin_cs, void* C, int64_t c_rs,

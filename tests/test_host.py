@@ -188,14 +188,34 @@ def test_fusion_regions_detected_on_the_committed_programs():
     prog, _, _ = load_case("cfg3_mlp")
     ex = ProgramExecutor(prog)
     kinds = sorted(type(f).__name__ for f in ex._fusions)
-    assert kinds == ["GemmEpilogueFusion"] * 3 + ["ReducePreFusion"]
-    for f in ex._fusions:
-        if type(f).__name__ == "GemmEpilogueFusion":
-            g, e = f.members
-            assert prog.nodes[g].op in ("Dot22", "Gemm") and prog.nodes[e].op == "Elemwise"
-            assert prog.nodes[e].inputs[f.acc_input] == prog.nodes[g].outputs[0]
-    shadows = [f.shadow_consumer for f in ex._fusions if type(f).__name__ == "GemmEpilogueFusion"]
-    assert shadows.count(True) == 2  # h and dpre feed later products; (h@W2 - Y) + b2 does not
+    assert kinds == ["GemmEpilogueFusion"] * 3  # Sqr -> Sum now lives inside the second region
+    regions = sorted((f for f in ex._fusions), key=lambda f: f.g)
+    ops = [[prog.nodes[i].op for i in f.members] for f in regions]
+    assert ops[0] == ["Dot22", "Elemwise"]                                   # tanh(X@W1 + b1)
+    assert sorted(ops[1]) == ["CAReduce", "CAReduce", "Elemwise", "Elemwise", "Elemwise", "Gemm"]
+    assert sorted(ops[2]) == ["CAReduce", "Dot22", "Elemwise"]               # dpre and its column sums
+    r2, r3 = regions[1], regions[2]
+    # diff is never stored; dout (stored and/or bf16 plane) carries the column sums, Sqr(diff) the total
+    assert len(r2.out_vars) == 2 and r2.out_vars[1] is None and r2.colsum == 0 and r2.fullsum == 1
+    assert r3.colsum == 0 and r3.fullsum == -1
+    # the second region waits for the 1/n factor computed after the Gemm node and runs before
+    # the first product that reads dout
+    assert r2.g < r2.anchor < min(c for v in r2.out_vars if v is not None for c in r2._consumers[v])
+    assert regions[0].anchor == regions[0].g  # nothing to wait for: runs at the GEMM position
+    for f in regions:
+        assert f.anchor in f.members and f.last == max(f.members)
+    shadows = [f.shadow_consumer for f in regions]
+    assert shadows == [True, True, True]  # h, dout and dpre feed later products
+
+    import os
+    os.environ["AB_GEMM_FUSE_SINGLE"] = "1"
+    try:
+        ex1 = ProgramExecutor(prog)
+    finally:
+        del os.environ["AB_GEMM_FUSE_SINGLE"]
+    kinds = sorted(type(f).__name__ for f in ex1._fusions)
+    assert kinds == ["GemmEpilogueFusion"] * 3 + ["ReducePreFusion"]         # round-1 regions
+    assert all(len(f.members) == 2 for f in ex1._fusions)
 
     for name in ("softmax_classifier", "blas_dot22_layouts", "cfg4_lstm", "cfg1_readme"):
         prog, _, _ = load_case(name)
