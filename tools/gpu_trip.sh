@@ -1,0 +1,34 @@
+#!/bin/bash
+# One validation trip on a B200 (run under gpurun): the sections are independent, each under
+# its own timeout, risky kernels last.  usage: tools/gpu_trip.sh <section>...
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+export PYTHONPATH=$PWD
+for sec in "$@"; do
+case $sec in
+  newtests)
+    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_function.py -m gpu -q -p no:cacheprovider -k "big or cuda_graph or launch_counts or matches_reference or epilogue_fusion" > gpurun_out/pytest_new.log 2>&1; echo "newtests rc=$?"; tail -5 gpurun_out/pytest_new.log | cut -c1-400;;
+  alltests)
+    timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1; echo "alltests rc=$?"; tail -8 gpurun_out/pytest_all.log | cut -c1-400;;
+  c4test)
+    timeout 300 python -m pytest tests/test_gpu_blas.py -m gpu -q -p no:cacheprovider -x -k "four_cta" > gpurun_out/pytest_c4.log 2>&1; echo "c4 rc=$?"; tail -12 gpurun_out/pytest_c4.log | cut -c1-300;;
+  blas)
+    timeout 600 python -m pytest tests/test_gpu_blas.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_blas.log 2>&1; echo "blas rc=$?"; tail -8 gpurun_out/pytest_blas.log | cut -c1-300;;
+  bench)
+    timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_default.err; cut -c1-2500 gpurun_out/bench_default.json;;
+  bench_quick)
+    timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench_quick rc=$?"; tail -3 gpurun_out/bench_quick.err; cut -c1-1800 gpurun_out/bench_quick.json;;
+  bench_noc4)
+    AB_GEMM_NO_CLUSTER4=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_noc4.json 2> gpurun_out/bench_noc4.err; echo "bench_noc4 rc=$?"; tail -3 gpurun_out/bench_noc4.err; cut -c1-1800 gpurun_out/bench_noc4.json;;
+  bench_single)
+    AB_GEMM_FUSE_SINGLE=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_single.json 2> gpurun_out/bench_single.err; echo "bench_single rc=$?"; tail -3 gpurun_out/bench_single.err; cut -c1-1800 gpurun_out/bench_single.json;;
+  reference)
+    timeout 500 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"; tail -2 gpurun_out/bench_reference.err; cut -c1-1200 gpurun_out/bench_reference.json;;
+  smoke)
+    timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3;;
+  launches)
+    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-also --no-cpu --no-e2e --graph 0 > gpurun_out/launches.log 2>&1; echo "launches rc=$?"; tail -2 gpurun_out/launches.log | cut -c1-300;;
+  *) echo "unknown section $sec";;
+esac
+done
