@@ -81,7 +81,7 @@ class B200VM:
         if self.time_thunks and hasattr(executor, "time_nodes"):
             executor.time_nodes = True
         self._replay = None
-        if linker.cuda_graph and not self.time_thunks:
+        if linker.cuda_graph and not self.time_thunks and linker.shard is None:
             from .runtime.graph import GraphReplay
 
             self._replay = GraphReplay(executor)
@@ -165,11 +165,21 @@ class B200Linker(LocalLinker):
     """Link an optimised ``FunctionGraph`` to hand-written sm_100a kernels."""
 
     def __init__(self, allow_gc=True, precision="fp32", device_outputs=False, schedule=None,
-                 cuda_graph=False):
+                 cuda_graph=False, shard=None, shard_inputs=None, gather=False):
         super().__init__(allow_gc=allow_gc, scheduler=schedule)
         self.fgraph = None
         self.precision = precision
         self.device_outputs = device_outputs
+        # shard="rows": each rank of the torch.distributed job gets its row block of the
+        # sharded inputs (found by shardplan.infer_sharded_inputs, or named by shard_inputs =
+        # {input position: axis}); how the outputs combine is derived from the graph
+        # (shardplan.analyse, SURVEY 8e); a graph that is not a batch map raises ReplicasOnly
+        if shard not in (None, "rows"):
+            raise ValueError("shard must be None or 'rows'")
+        self.shard = shard
+        self.shard_inputs = shard_inputs
+        self.gather = gather
+        self.shard_plan = None
         # replay each evaluation as ONE CUDA graph (runtime/graph.py) once the argument
         # addresses and shapes repeat: removes the per-node host cost, which is what the C
         # twin of the reference VM exists for (lazylinker_c.c).  Off by default because a
@@ -185,8 +195,9 @@ class B200Linker(LocalLinker):
         if self.fgraph is not None and self.fgraph is not fgraph:
             # a linker instance is bound to one graph (pattern of link/basic.py:300-326)
             return type(self)(allow_gc=self.allow_gc, precision=self.precision,
-                              device_outputs=self.device_outputs,
-                              cuda_graph=self.cuda_graph).accept(fgraph, no_recycling, profile)
+                              device_outputs=self.device_outputs, cuda_graph=self.cuda_graph,
+                              shard=self.shard, shard_inputs=self.shard_inputs,
+                              gather=self.gather).accept(fgraph, no_recycling, profile)
         self.fgraph = fgraph
         self.no_recycling = no_recycling
         self.profile = profile
@@ -209,6 +220,18 @@ class B200Linker(LocalLinker):
         self.program = lower_fgraph(fgraph, order=order)
         prec = {"fp32": 0, "tf32": 1, "bf16": 2}.get(self.precision, self.precision)
         executor = ProgramExecutor(self.program, precision=prec, host_outputs=False)
+        if self.shard == "rows":
+            from . import shardplan
+            from .shard import ShardedExecutor
+
+            if self.shard_inputs is None:
+                self.shard_plan = shardplan.infer_sharded_inputs(self.program)
+            else:
+                spec = [None] * len(self.program.inputs)
+                for k, ax in dict(self.shard_inputs).items():
+                    spec[int(k)] = int(ax)
+                self.shard_plan = shardplan.analyse(self.program, spec)
+            executor = ShardedExecutor(executor, self.shard_plan, gather=self.gather)
         fn = B200VM(self, fgraph, order, executor, input_storage, output_storage, storage_map)
         return (
             fn,
@@ -219,13 +242,15 @@ class B200Linker(LocalLinker):
         )
 
 
-def mode(precision="fp32", device_outputs=False, optimizer=None, cuda_graph=False):
+def mode(precision="fp32", device_outputs=False, optimizer=None, cuda_graph=False, shard=None,
+         shard_inputs=None, gather=False):
     """An Aesara ``Mode`` using this backend with the ``fast_run`` rewrites the
-    C-linker gets."""
+    C-linker gets.  ``shard="rows"``: see :class:`B200Linker`."""
     if optimizer is None:
         optimizer = RewriteDatabaseQuery(include=["fast_run"])
     return Mode(B200Linker(precision=precision, device_outputs=device_outputs,
-                           cuda_graph=cuda_graph), optimizer)
+                           cuda_graph=cuda_graph, shard=shard, shard_inputs=shard_inputs,
+                           gather=gather), optimizer)
 
 
 def register():

@@ -213,6 +213,20 @@ class ProgramExecutor:
                     self._free_after[f.last].extend(self._free_after[i])
                     self._free_after[i] = []
         self.fused_regions_run = 0
+        # output hook (shard.ShardedExecutor): called as hook(k, value) right after the node
+        # (or region) that produces function output k has been launched, so that a collective
+        # on a finished gradient overlaps the rest of the evaluation
+        self.output_hook = None
+        producer = {v: i for i, n in enumerate(program.nodes) for v in n.outputs}
+        self._outputs_of_node = {}
+        for k, v in enumerate(program.outputs):
+            i = producer.get(v)
+            if i is None:
+                continue
+            f = self._fusion_of.get(i)
+            if f is not None:
+                i = getattr(f, "anchor", f.last)
+            self._outputs_of_node.setdefault(i, []).append((k, v))
         self.prepare()
 
     # ------------------------------------------------------------------
@@ -400,6 +414,9 @@ class ProgramExecutor:
                             if all(v is not None for v in vals):
                                 self.trace[m] = [v.to_numpy() if isinstance(v, DeviceArray) else np.array(v, copy=True)
                                                  for v in vals]
+                    if self.output_hook is not None:
+                        for k, v in self._outputs_of_node.get(i, ()):
+                            self.output_hook(k, env[v])
                 if i == fusion.last:
                     for v in self._free_after[i]:
                         env.pop(v, None)
@@ -434,6 +451,9 @@ class ProgramExecutor:
                 d = env.get(node.inputs[pos])
                 if isinstance(d, DeviceArray):
                     self.pack_cache.invalidate(d.owner)
+            if self.output_hook is not None:
+                for k, v in self._outputs_of_node.get(i, ()):
+                    self.output_hook(k, env[v])
             if self.trace is not None:
                 vals = [env[v] for v in node.outputs]
                 self.trace[i] = [v.to_numpy() if isinstance(v, DeviceArray)

@@ -134,3 +134,214 @@ def _c(shape):
     from .runtime.device import c_strides
 
     return c_strides(shape)
+
+
+# ---------------------------------------------------------------------------------------------
+# Sharding behind the linker: ``aesara_b200.mode(shard="rows")``
+# ---------------------------------------------------------------------------------------------
+SMALL_OUTPUT_BYTES = 1 << 16  # outputs below this are packed into one exchange at the end
+
+
+class ShardedExecutor:
+    """One rank of a row-sharded evaluation.
+
+    ``plan`` (``shardplan.analyse`` / ``infer_sharded_inputs``) says which function inputs are
+    this rank's row block and how each output combines — decided from the graph, SURVEY §8e's
+    rule, not by the caller.  The wrapped executor runs the unchanged program on the local
+    rows; batch reductions (``sum`` / ``mean`` outputs: cost, gradients) are all-reduced over
+    NCCL, each rank's contribution weighted by its share of the rows for ``mean``.  A large
+    reduction output is handed to NCCL on a side stream as soon as the node that produces it
+    has been launched (``ProgramExecutor.output_hook``), so the exchange of an early gradient
+    overlaps the rest of the backward pass; the small ones travel packed in one buffer at the
+    end.  ``concat`` outputs stay sharded (this rank's rows) unless ``gather=True`` asks for the
+    north star's all-gather."""
+
+    def __init__(self, executor, plan, group=None, gather=False, overlap=True):
+        import torch.distributed as dist
+
+        self.ex = executor
+        self.plan = plan
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.gather = gather
+        self.overlap = overlap
+        prog = executor.program
+        consumed = {v for n in prog.nodes for v in n.inputs}
+        # outputs nobody else reads may be reduced in place as soon as they exist
+        self._early_ok = [prog.outputs[k] not in consumed and prog.outputs[k] not in prog.inputs
+                          and prog.outputs.count(prog.outputs[k]) == 1 for k in range(len(prog.outputs))]
+        self._side = None
+        self._mul = None
+        self.early_issued = 0      # collectives issued before the evaluation finished (last call)
+        self.exchanges = 0         # collectives of the last call
+
+    # forwarded attributes the VM / profiler / debugger consult
+    def __getattr__(self, name):
+        return getattr(self.ex, name)
+
+    @property
+    def time_nodes(self):
+        return self.ex.time_nodes
+
+    @time_nodes.setter
+    def time_nodes(self, v):
+        self.ex.time_nodes = v
+
+    @property
+    def trace(self):
+        return self.ex.trace
+
+    @trace.setter
+    def trace(self, v):
+        self.ex.trace = v
+
+    def _weight(self, args):
+        """Device scalar n_r / N (float32, shape [1]) for the ``mean`` outputs, computed on the
+        device: a one-element all-reduce of the local row count, no host synchronisation."""
+        import torch
+
+        from .runtime.device import DeviceArray
+
+        n_local = None
+        for a, ax in zip(args, self.plan.sharded_inputs):
+            if ax is not None:
+                n_local = int(np.shape(a)[ax] if not isinstance(a, DeviceArray) else a.shape[ax])
+                break
+        if n_local is None:
+            raise ValueError("sharded evaluation without a sharded input")
+        t = torch.full((1,), float(n_local), dtype=torch.float64, device="cuda")
+        tot = t.clone()
+        self.dist.all_reduce(tot, op=self.dist.ReduceOp.SUM, group=self.group)
+        w = (t / tot).to(torch.float32)
+        return DeviceArray.from_torch(w)
+
+    def _scale_inplace(self, arr, w):
+        from .runtime import kernels as K
+
+        if self._mul is None:
+            dt = "float32"
+            self._mul = K.ElemwiseKernel.get({
+                "inputs": [dt, dt], "out_dtypes": [dt], "outputs": ["t0"], "name": "shard_weight",
+                "stmts": [{"op": "mul", "args": ["i0", "i1"], "dtype": dt, "in_dtypes": [dt, dt]}]})
+        wv = w.view((1,) * arr.ndim, (0,) * arr.ndim) if arr.ndim else w.view((), ())
+        self._mul.launch(arr.shape, [arr, wv], [arr])
+
+    def __call__(self, *args, output_subset=None):
+        import torch
+
+        from .runtime import kernels as K
+        from .runtime.device import DeviceArray
+
+        if self.world == 1:
+            return self.ex(*args, output_subset=output_subset)
+        modes = self.plan.outputs
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        need_w = any(m[0] == "mean" for m in modes)
+        side.wait_stream(cur)
+        w = w_ready = None
+        if need_w:
+            with torch.cuda.stream(side):
+                w = self._weight(args)
+                w_ready = torch.cuda.Event()
+                w_ready.record(side)
+        works, done = [], set()
+        self.early_issued = self.exchanges = 0
+
+        def reduce_now(k, val):
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                if modes[k][0] == "mean":
+                    self._scale_inplace(val, w)
+                t = val.owner.view(torch.float32)[: val.size]
+                works.append((self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group,
+                                                   async_op=True), val))
+            self.exchanges += 1
+
+        def hook(k, val):
+            if (modes[k][0] in ("sum", "mean") and self._early_ok[k] and isinstance(val, DeviceArray)
+                    and val.dtype == np.float32 and val.is_c_contiguous()
+                    and val.nbytes >= SMALL_OUTPUT_BYTES and (output_subset is None or k in output_subset)):
+                reduce_now(k, val)
+                done.add(k)
+                self.early_issued += 1
+
+        host_out, self.ex.host_outputs = self.ex.host_outputs, False
+        self.ex.output_hook = hook if self.overlap else None
+        try:
+            outs = list(self.ex(*args, output_subset=output_subset))
+        finally:
+            self.ex.output_hook = None
+            self.ex.host_outputs = host_out
+        # the rest: large ones individually, small ones packed into one buffer
+        small = []
+        for k, (o, m) in enumerate(zip(outs, modes)):
+            if o is None or k in done or m[0] not in ("sum", "mean"):
+                continue
+            if not isinstance(o, DeviceArray):
+                o = DeviceArray.from_numpy(np.asarray(o))
+            if o.dtype != np.float32:
+                raise TypeError(f"output {k}: batch reductions are combined in float32, got {o.dtype}")
+            if not o.is_c_contiguous() or not self._early_ok[k]:
+                o = K.contiguous_copy(o)
+            outs[k] = o
+            if o.nbytes >= SMALL_OUTPUT_BYTES:
+                reduce_now(k, o)
+            else:
+                small.append(k)
+        if small:
+            layout = pack_layout([outs[k].shape for k in small])
+            flat = DeviceArray.empty((layout.total,), "float32")
+            for k, off in zip(small, layout.offsets):
+                o = outs[k]
+                seg = flat.view(o.shape, _c(o.shape), off)
+                K.copy_into(seg, o)
+                if modes[k][0] == "mean":
+                    if w_ready is not None:
+                        cur.wait_event(w_ready)  # only the weight, not the exchanges queued behind it
+                        w_ready = None
+                    self._scale_inplace(seg, w)
+                outs[k] = seg
+            t = flat.owner.view(torch.float32)[: layout.total]
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.exchanges += 1
+        if self.gather:
+            for k, (o, m) in enumerate(zip(outs, modes)):
+                if o is not None and m[0] == "concat":
+                    outs[k] = self._all_gather_rows(o, m[1])
+        for work, _val in works:
+            work.wait()      # the current stream waits for the collective
+        cur.wait_stream(side)
+        if host_out:
+            got = DeviceArray.download_all([o for o in outs if o is not None])
+            it = iter(got)
+            outs = [None if o is None else next(it) for o in outs]
+        return outs
+
+    def _all_gather_rows(self, o, axis):
+        """Equal row blocks only (``all_gather_into_tensor``); the rows move to axis 0 and back."""
+        import torch
+
+        from .runtime import kernels as K
+        from .runtime.device import DeviceArray
+
+        if axis != 0:
+            order = [axis] + [d for d in range(o.ndim) if d != axis]
+            o = o.dimshuffle(order)
+        o = o if o.is_c_contiguous() else K.contiguous_copy(o)
+        out = DeviceArray.empty((self.world * o.shape[0],) + o.shape[1:], o.dtype)
+        nb = o.nbytes
+        self.dist.all_gather_into_tensor(out.owner[: self.world * nb], o.owner[:nb], group=self.group)
+        self.exchanges += 1
+        if axis != 0:
+            inv = [0] * out.ndim
+            for pos, d in enumerate([axis] + [d for d in range(out.ndim) if d != axis]):
+                inv[d] = pos
+            out = out.dimshuffle(inv)
+        return out

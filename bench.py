@@ -197,6 +197,11 @@ def compile_b200(spec, precision, device_outputs, cuda_graph, shard=None):
     aesara = front_end()
     if aesara is None:
         pc = ProgramCallable(spec, PRECISIONS[precision], device_outputs, cuda_graph)
+        if shard is not None:
+            from aesara_b200 import shardplan
+            from aesara_b200.shard import ShardedExecutor
+
+            pc.executor = ShardedExecutor(pc.executor, shardplan.infer_sharded_inputs(pc.executor.program))
         return pc, pc.executor, "lowered program (no front-end importable)"
     import aesara_b200.linker as L
 
@@ -463,19 +468,15 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
     from aesara_b200.runtime.device import DeviceArray
 
     L = lib.load()
-    f, ex, boundary = compile_b200(spec, precision, device_outputs=True, cuda_graph=use_graph)
+    # N > 1: the row sharding and the combination of the outputs are the linker's
+    # (mode(shard="rows")): derived from the graph, one process per GPU, NCCL all-reduces
+    f, ex, boundary = compile_b200(spec, precision, device_outputs=True,
+                                   cuda_graph=use_graph and world == 1,
+                                   shard="rows" if world > 1 else None)
     dev_in, keep = make_inputs_device(spec, seed=seed + rank)
-    combiner = None
-    if world > 1:
-        from aesara_b200.shard import OutputCombiner
-
-        combiner = OutputCombiner(world, mode="mean")
 
     def step():
-        outs = f(*dev_in)
-        if combiner is not None:
-            outs = combiner(outs)
-        return outs
+        return f(*dev_in)
 
     def barrier():
         if dist is not None:
@@ -496,6 +497,10 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
         return t.item() / n
 
     res = {"boundary": boundary}
+    if world > 1:
+        plan = getattr(ex, "plan", None)
+        res["shard_plan"] = None if plan is None else {
+            "sharded_inputs": plan.sharded_inputs, "outputs": [list(o) for o in plan.outputs]}
     for _ in range(max(warmup, 3)):
         step()
     barrier()
@@ -546,6 +551,10 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
     clk = clocks.stop()
     res.update(ms_per_step_eager=ms_eager, gpu_launches=int(launches), clocks=clk,
                fused_regions_run=ex.fused_regions_run)
+    if world > 1:
+        res["exchange"] = {"collectives_per_step": getattr(ex, "exchanges", None),
+                           "issued_before_the_evaluation_finished": getattr(ex, "early_issued", None)}
+        ex = getattr(ex, "ex", ex)  # the wrapped ProgramExecutor for the per-node statistics
 
     # per-kind device time and per-kernel HBM fractions from the per-node events
     prog = ex.program
@@ -618,6 +627,60 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
     gc.collect()
     torch.cuda.empty_cache()
     return res
+
+
+def sharded_parity(spec, precision, rank, world, dist, rows_per_rank=2048):
+    """Pre-flight of an N-GPU run: the combined outputs of the row-sharded function equal ONE
+    GPU's evaluation of the concatenated batch (rank 0 gathers the shards and evaluates the
+    unsharded function).  Reduced row count, full width.  Returns the worst norm-wise error."""
+    import copy
+
+    import torch
+
+    from aesara_b200.runtime.device import DeviceArray
+
+    small = copy.deepcopy(spec)
+    if spec["rows"] is None:
+        return None
+    small[spec["rows"]] = rows_per_rank
+    fs, exs, _ = compile_b200(small, precision, device_outputs=True, cuda_graph=False, shard="rows")
+    dev_in, keep = make_inputs_device(small, seed=777 + rank)
+    outs = fs(*dev_in)
+    outs = outs if isinstance(outs, (list, tuple)) else [outs]
+    plan = exs.plan
+    # gather every rank's sharded inputs on every rank (small), concatenate along the axis
+    full_in = []
+    ti = iter(keep)
+    for a, ax in zip(dev_in, plan.sharded_inputs):
+        if not isinstance(a, DeviceArray):
+            full_in.append(a)
+            continue
+        t = next(ti)
+        if ax is None:
+            full_in.append(a)
+            continue
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t.contiguous())
+        full_in.append(DeviceArray.from_torch(torch.cat(parts, dim=ax).contiguous()))
+    err, checked = 0.0, 0
+    if rank == 0:
+        f1, _, _ = compile_b200(small, precision, device_outputs=True, cuda_graph=False)
+        want = f1(*full_in)
+        want = want if isinstance(want, (list, tuple)) else [want]
+        for k, (g, w_, m) in enumerate(zip(outs, want, plan.outputs)):
+            if m[0] not in ("sum", "mean", "rep"):
+                continue
+            g = np.asarray(g.to_numpy() if isinstance(g, DeviceArray) else g, np.float64)
+            w_ = np.asarray(w_.to_numpy() if isinstance(w_, DeviceArray) else w_, np.float64)
+            err = max(err, float(np.max(np.abs(g - w_)) / max(np.max(np.abs(w_)), 1e-30)))
+            checked += 1
+    t = torch.tensor([err], device="cuda", dtype=torch.float64)
+    dist.broadcast(t, src=0)
+    torch.cuda.synchronize()
+    return {"vs": f"one GPU evaluating the concatenated batch ({rows_per_rank} rows per rank x {world})",
+            "normwise_err": float(t.item()), "outputs_checked": checked,
+            "tolerance": TOLERANCE[precision] if spec["n_gemm"] else 1e-5,
+            "combine": [list(o) for o in plan.outputs]}
 
 
 def roofline_of(spec, precision, m, peaks):
@@ -700,6 +763,11 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = measured_peaks()
+    parity = None
+    if world > 1:
+        parity = sharded_parity(spec, args.precision, rank, world, dist)
+        if parity is not None and not parity["normwise_err"] <= 4 * parity["tolerance"]:
+            raise SystemExit(f"sharded evaluation disagrees with the single-GPU one: {parity}")
     m = measure(spec, args.precision, args.steps, args.warmup, rank, world, dist,
                 use_graph=bool(args.graph), e2e_steps=0 if args.no_e2e else max(2, min(args.steps, 5)))
     ms_step = m["ms_per_step"]
@@ -770,6 +838,10 @@ def main():
             "cpu_baseline": cb, "e2e": m.get("e2e"), "gpu_launches": m["gpu_launches"],
             "clocks": m["clocks"], "also": also,
         }
+        if world > 1:
+            line["parity_sharded"] = parity
+            line["shard_plan"] = m.get("shard_plan")
+            line["exchange"] = m.get("exchange")
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

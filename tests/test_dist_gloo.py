@@ -96,3 +96,60 @@ def test_sharded_logreg_matches_unsharded_gloo():
         assert p.exitcode == 0
     for full, comb in res:
         np.testing.assert_allclose(comb, full, rtol=2e-5, atol=1e-6)
+
+
+def _worker_plan(rank, world, port, case, n_rows, q):
+    """The combination rule comes from the graph (shardplan), not from the caller."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from aesara_b200 import shardplan
+    from oracle.program_np import run_program
+    from tests._cases import load_case
+
+    prog, _, _ = load_case(case)
+    plan = shardplan.infer_sharded_inputs(prog)
+    rng = np.random.default_rng(11)
+    H = 24
+    ins = [rng.standard_normal((n_rows, H)).astype("float32"), rng.standard_normal((n_rows, H)).astype("float32"),
+           (rng.standard_normal((H, H)) / 5).astype("float32"), (rng.standard_normal(H) * 0.1).astype("float32"),
+           (rng.standard_normal((H, H)) / 5).astype("float32"), (rng.standard_normal(H) * 0.1).astype("float32")]
+    a, b = row_block(n_rows, world, rank)
+    local = [x[a:b] if ax == 0 else x for x, ax in zip(ins, plan.sharded_inputs)]
+    outs = run_program(prog, local)
+    n_local = torch.tensor([float(b - a)], dtype=torch.float64)
+    n_tot = n_local.clone()
+    dist.all_reduce(n_tot)
+    w = float(n_local / n_tot)
+    combined = []
+    for o, mode in zip(outs, plan.outputs):
+        t = torch.from_numpy(np.array(o, dtype=np.float32).reshape(-1).copy())
+        if mode[0] == "mean":
+            t *= w
+        assert mode[0] in ("mean", "sum")
+        dist.all_reduce(t)
+        combined.append(t.numpy())
+    if rank == 0:
+        full = run_program(prog, ins)
+        q.put([(np.asarray(f, "float32").reshape(-1).tolist(), c.tolist()) for f, c in zip(full, combined)])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_mlp_combines_by_the_plan_gloo():
+    """cfg3 over 2 ranks with UNEQUAL row blocks (33 rows): the analysis says `mean` for the loss
+    and every gradient; weighting each rank by its share of the rows reproduces the unsharded
+    evaluation."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_plan, args=(r, 2, port, "cfg3_mlp", 33, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=100)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for full, comb in res:
+        np.testing.assert_allclose(comb, full, rtol=3e-5, atol=1e-6)
