@@ -43,7 +43,7 @@ def _worker(rank, world, port, q):
     res = {}
     for name, build, inputs in (("cfg3", G.cfg3_mlp, lambda: G.cfg3_inputs(1100, 256)),
                                 ("cfg5", G.cfg5_logreg, lambda: G.cfg5_inputs(3001, 64)),
-                                ("cfg2", G.cfg2_fused_elemwise, lambda: G.cfg2_inputs(70000))  # even: equal blocks for the gather):
+                                ("cfg2", G.cfg2_fused_elemwise, lambda: G.cfg2_inputs(70000))):  # even: equal blocks for the gather
         i, o = build()
         f = aesara.function(i, o, mode=L.mode(shard="rows", gather=True), on_unused_input="ignore")
         plan = f.maker.linker.shard_plan
