@@ -459,8 +459,41 @@ GEMM_OPS = ("Dot22", "Gemm", "Dot22Scalar", "Scan", "Dot", "BatchedDot")
 HBM_OPS = ("Elemwise", "CAReduce", "Gemv", "Ger", "Softmax", "MaxAndArgmax")
 
 
+def truth_check(spec, precision, outs, keep):
+    """Measured error of THIS run's outputs against a float64 evaluation of the same inputs
+    (tests/_truth.py: torch.float64 on the GPU, a checker outside every timed region)."""
+    import torch
+
+    from tests._truth import logreg_truth, mlp_truth, nerr
+
+    outs = outs if isinstance(outs, (list, tuple)) else [outs]
+    host = [np.asarray(o.to_numpy() if hasattr(o, "to_numpy") else o) for o in outs]
+    if spec["name"] == "mlp":
+        H = spec["H"]
+        blocks = [(0, 0), (H // 2, max(H // 2 - 128, 0))] if H >= 256 else []
+        t = mlp_truth(*keep, blocks)
+        loss, dW1, db1, dW2, db2 = host
+        err = {"loss": abs(float(loss) - float(t["loss"])) / abs(float(t["loss"])),
+               "db1": nerr(db1, t["db1"]), "db2": nerr(db2, t["db2"])}
+        for nm, dev, tr in (("dW1", dW1, t["dW1"]), ("dW2", dW2, t["dW2"])):
+            scale = float(np.max(np.abs(dev)))
+            err[nm + "_blocks"] = max([float(np.max(np.abs(dev[r:r + 128, c:c + 128].astype(np.float64) - b.cpu().numpy()))) / scale
+                                       for (r, c), b in zip(blocks, tr)] or [0.0])
+        tol = TOLERANCE[precision]
+    else:
+        X, y, w = keep
+        t = logreg_truth(X, y, w, 0.0)
+        cost, gw, gb = host
+        err = {"cost": abs(float(cost) - float(t["cost"])) / abs(float(t["cost"])), "grad_w": nerr(gw, t["grad_w"]),
+               "grad_b": abs(float(gb) - float(t["grad_b"])) / max(abs(float(t["grad_b"])), float(t["grad_w"].abs().max()))}
+        tol = 1e-5
+    torch.cuda.synchronize()
+    return {"vs": "float64 evaluation of the same inputs (torch.float64 checker, tests/_truth.py); norm-wise",
+            "err": err, "max_err": max(err.values()), "stated_tolerance": tol, "within": max(err.values()) <= tol}
+
+
 def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_graph=True,
-            node_region=True, e2e_steps=0, seed=1234):
+            node_region=True, e2e_steps=0, seed=1234, check_truth=False):
     """One workload on this rank's GPU.  Returns a dict of measurements (see main())."""
     import torch
 
@@ -497,6 +530,8 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
         return t.item() / n
 
     res = {"boundary": boundary}
+    if check_truth and world == 1 and spec["name"] in ("mlp", "logreg"):
+        res["parity"] = truth_check(spec, precision, step(), keep)
     if world > 1:
         plan = getattr(ex, "plan", None)
         res["shard_plan"] = None if plan is None else {
@@ -740,6 +775,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the one-liners of the other configs")
+    ap.add_argument("--no-truth", action="store_true", help="skip the float64 parity check of the headline run")
     args = ap.parse_args()
     spec = workload_spec(args.workload, args.batch, args.hidden, args.n, args.steps_t)
     if args.precision is None:
@@ -769,7 +805,8 @@ def main():
         if parity is not None and not parity["normwise_err"] <= 4 * parity["tolerance"]:
             raise SystemExit(f"sharded evaluation disagrees with the single-GPU one: {parity}")
     m = measure(spec, args.precision, args.steps, args.warmup, rank, world, dist,
-                use_graph=bool(args.graph), e2e_steps=0 if args.no_e2e else max(2, min(args.steps, 5)))
+                use_graph=bool(args.graph), e2e_steps=0 if args.no_e2e else max(2, min(args.steps, 5)),
+                check_truth=not args.no_truth)
     ms_step = m["ms_per_step"]
     value = world * 1e3 / ms_step  # every rank evaluates its shard once per step
     roofline = roofline_of(spec, args.precision, m, peaks)
@@ -798,14 +835,15 @@ def main():
                 ("readme_cfg1", workload_spec("readme"), "fp32", 50)]
         for key, sp, prec, k in todo:
             try:
-                mm = measure(sp, prec, k, 3, use_graph=True)
+                mm = measure(sp, prec, k, 3, use_graph=True, check_truth=not args.no_truth)
                 rr = roofline_of(sp, prec, mm, peaks)
                 also[key] = {"workload": sp["desc"], "ms_per_step": mm["ms_per_step"],
                              "value": 1e3 / mm["ms_per_step"], "steps": k, "executor": mm["executor"],
                              "bound": rr["bound"], "achieved": rr["achieved"], "unit": rr["unit"],
                              "frac": rr.get("frac"), "kernel": rr["kernel"],
                              "frac_of_3xtf32_ceiling": rr.get("frac_of_3xtf32_ceiling"),
-                             "gpu_launches": mm["gpu_launches"]}
+                             "gpu_launches": mm["gpu_launches"],
+                             "parity_max_err": (mm.get("parity") or {}).get("max_err")}
             except Exception as e:  # an auxiliary line must not take the headline down
                 also[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
@@ -836,7 +874,7 @@ def main():
             "hbm_kernels": [dict(n, frac=n["gbs"] / peaks["hbm"]) for n in m["hbm_nodes"]],
             "device_ms": m["device_ms"], "ms_per_step_eager": m["ms_per_step_eager"],
             "cpu_baseline": cb, "e2e": m.get("e2e"), "gpu_launches": m["gpu_launches"],
-            "clocks": m["clocks"], "also": also,
+            "clocks": m["clocks"], "parity": m.get("parity"), "also": also,
         }
         if world > 1:
             line["parity_sharded"] = parity
