@@ -165,7 +165,7 @@ class B200Linker(LocalLinker):
     """Link an optimised ``FunctionGraph`` to hand-written sm_100a kernels."""
 
     def __init__(self, allow_gc=True, precision="fp32", device_outputs=False, schedule=None,
-                 cuda_graph=False, shard=None, shard_inputs=None, gather=False):
+                 cuda_graph=False, shard=None, shard_inputs=None, gather=False, host_chunks=0):
         super().__init__(allow_gc=allow_gc, scheduler=schedule)
         self.fgraph = None
         self.precision = precision
@@ -180,6 +180,10 @@ class B200Linker(LocalLinker):
         self.shard_inputs = shard_inputs
         self.gather = gather
         self.shard_plan = None
+        # host_chunks=K: NumPy arguments of a batch-map graph are uploaded and evaluated in K
+        # row blocks, the upload of one overlapping the evaluation of the previous
+        # (shard.ChunkedHostExecutor); graphs that are not batch maps are evaluated whole
+        self.host_chunks = int(host_chunks or 0)
         # replay each evaluation as ONE CUDA graph (runtime/graph.py) once the argument
         # addresses and shapes repeat: removes the per-node host cost, which is what the C
         # twin of the reference VM exists for (lazylinker_c.c).  Off by default because a
@@ -197,7 +201,7 @@ class B200Linker(LocalLinker):
             return type(self)(allow_gc=self.allow_gc, precision=self.precision,
                               device_outputs=self.device_outputs, cuda_graph=self.cuda_graph,
                               shard=self.shard, shard_inputs=self.shard_inputs,
-                              gather=self.gather).accept(fgraph, no_recycling, profile)
+                              gather=self.gather, host_chunks=self.host_chunks).accept(fgraph, no_recycling, profile)
         self.fgraph = fgraph
         self.no_recycling = no_recycling
         self.profile = profile
@@ -232,6 +236,16 @@ class B200Linker(LocalLinker):
                     spec[int(k)] = int(ax)
                 self.shard_plan = shardplan.analyse(self.program, spec)
             executor = ShardedExecutor(executor, self.shard_plan, gather=self.gather)
+        elif self.host_chunks >= 2:
+            from . import shardplan
+            from .shard import ChunkedHostExecutor
+
+            try:
+                self.shard_plan = shardplan.infer_sharded_inputs(self.program)
+                if all(a in (None, 0) for a in self.shard_plan.sharded_inputs):
+                    executor = ChunkedHostExecutor(executor, self.shard_plan, self.host_chunks)
+            except shardplan.ReplicasOnly:
+                self.shard_plan = None  # not a batch map: evaluated whole
         fn = B200VM(self, fgraph, order, executor, input_storage, output_storage, storage_map)
         return (
             fn,
@@ -243,14 +257,14 @@ class B200Linker(LocalLinker):
 
 
 def mode(precision="fp32", device_outputs=False, optimizer=None, cuda_graph=False, shard=None,
-         shard_inputs=None, gather=False):
+         shard_inputs=None, gather=False, host_chunks=0):
     """An Aesara ``Mode`` using this backend with the ``fast_run`` rewrites the
     C-linker gets.  ``shard="rows"``: see :class:`B200Linker`."""
     if optimizer is None:
         optimizer = RewriteDatabaseQuery(include=["fast_run"])
     return Mode(B200Linker(precision=precision, device_outputs=device_outputs,
                            cuda_graph=cuda_graph, shard=shard, shard_inputs=shard_inputs,
-                           gather=gather), optimizer)
+                           gather=gather, host_chunks=host_chunks), optimizer)
 
 
 def register():

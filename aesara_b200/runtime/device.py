@@ -91,19 +91,24 @@ class DeviceArray:
         src = a if a.flags.c_contiguous else np.array(a, order="C")
         if not src.flags.writeable:
             src = src.copy()
-        out = DeviceArray.empty(src.shape, src.dtype)
         if not src.size:
-            return out, None
+            return DeviceArray.empty(src.shape, src.dtype), None
         hb = torch.from_numpy(src.reshape(-1).view(np.uint8))
         if not hb.is_pinned():
+            out = DeviceArray.empty(src.shape, src.dtype)
             out.owner[: hb.numel()].copy_(hb)
             return out, None
-        # the block may still be in use by earlier work of the consumer stream
-        copy_stream.wait_stream(consumer_stream)
+        # The destination is allocated ON the copy stream: the caching allocator then orders its
+        # reuse against earlier copy-stream work only, and the copy need not wait for whatever
+        # the consumer stream still has queued (an upload of row block i+1 overlaps the
+        # evaluation of row block i, shard.ChunkedHostExecutor).  record_stream keeps the block
+        # from being recycled while the consumer stream uses it.
         with torch.cuda.stream(copy_stream):
+            out = DeviceArray.empty(src.shape, src.dtype)
             out.owner[: hb.numel()].copy_(hb, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
+        out.owner.record_stream(consumer_stream)
         return out, (ev, hb)  # the caller keeps ``hb`` alive until the event has completed
 
     @staticmethod

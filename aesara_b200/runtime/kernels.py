@@ -355,8 +355,6 @@ def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision
                     ep.shadow_bf16[i] = buf.data_ptr()
                     ep.shadow_pitch[i] = n
                     sh = (buf, n)
-                elif not store:
-                    raise _lib.AbError(5, "fused epilogue value is neither stored nor shadowed")
                 shadows.append(sh)
             if epilogue.colsum or epilogue.fullsum:
                 rows, cols = C.c_int64(), C.c_int64()

@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
 TOLERANCE = {"fp32": 1e-5, "tf32": 2e-3, "bf16": 2e-2}
+E2E_CHUNKS = int(os.environ.get("AB_E2E_CHUNKS", "8"))
 
 
 # ----------------------------------------------------------------------------- workloads
@@ -191,7 +192,7 @@ class ProgramCallable:
         return (self.replay or self.executor)(*args)
 
 
-def compile_b200(spec, precision, device_outputs, cuda_graph, shard=None):
+def compile_b200(spec, precision, device_outputs, cuda_graph, shard=None, host_chunks=0):
     """-> (callable, executor, boundary).  The callable is an ``aesara`` ``Function`` linked
     by ``B200Linker`` when a front-end is available."""
     aesara = front_end()
@@ -209,6 +210,8 @@ def compile_b200(spec, precision, device_outputs, cuda_graph, shard=None):
     kw = {}
     if shard is not None:
         kw["shard"] = shard
+    if host_chunks:
+        kw["host_chunks"] = host_chunks
     f = aesara.function(i, o, mode=L.mode(precision=precision, device_outputs=device_outputs,
                                           cuda_graph=cuda_graph, **kw), on_unused_input="ignore")
     if device_outputs:
@@ -597,12 +600,15 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
                   if type(fu).__name__ == "GemmEpilogueFusion" and not fu.broken}
     fused_any = {getattr(fu, "anchor", fu.last): fu for fu in ex._fusions}
     gemm_ms = hbm_ms = other_ms = 0.0
-    hbm_nodes = []
+    hbm_nodes, gemm_nodes = [], []
     for i, d in sorted(per_node.items()):
         op = "Gemm" if i in fused_gemm else prog.nodes[i].op
         t = float(np.mean(d["ms"]))
         if op in GEMM_OPS:
             gemm_ms += t
+            gemm_nodes.append({"node": i, "label": (prog.nodes[i].label or prog.nodes[i].op)[:60],
+                               "fused_members": len(fused_any[i].members) if i in fused_any else 1,
+                               "ms": round(t, 4)})
         elif op in HBM_OPS:
             hbm_ms += t
             label = prog.nodes[i].label or prog.nodes[i].op
@@ -613,7 +619,8 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
                                   "gbs": d["bytes"] / (t * 1e-3) / 1e9})
         else:
             other_ms += t
-    res.update(device_ms={"gemm": gemm_ms, "elemwise_careduce": hbm_ms, "other": other_ms}, hbm_nodes=hbm_nodes)
+    res.update(device_ms={"gemm": gemm_ms, "elemwise_careduce": hbm_ms, "other": other_ms}, hbm_nodes=hbm_nodes,
+               gemm_nodes=gemm_nodes)
 
     # end to end through the public call: pinned host inputs, H2D + eval + D2H of every output
     if e2e_steps and world == 1:
@@ -631,7 +638,8 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
 
         gc.collect()
         torch.cuda.empty_cache()
-        f2, _, _ = compile_b200(spec, precision, device_outputs=False, cuda_graph=False)
+        f2, ex2, _ = compile_b200(spec, precision, device_outputs=False, cuda_graph=False,
+                                  host_chunks=E2E_CHUNKS)
         it = iter(host_in)
         host_args = [slot if slot is not None else next(it).numpy() for slot in template]
 
@@ -651,7 +659,12 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
         e2e_ms = a.elapsed_time(b) / e2e_steps
         res["e2e"] = {"value": 1e3 / e2e_ms, "unit": "graph-evals/s", "h2d_bytes_per_step": h2d,
                       "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                      "call": "Function.__call__ with page-locked host ndarrays in, host ndarrays out"}
+                      "call": "Function.__call__ with page-locked host ndarrays in, host ndarrays out",
+                      "row_chunks": getattr(ex2, "chunks_run", 1),
+                      "pipeline": ("mode(host_chunks=%d): rows uploaded and evaluated in blocks, the upload of one "
+                                   "overlapping the evaluation of the previous (batch map proven by shardplan)"
+                                   % E2E_CHUNKS) if getattr(ex2, "chunks_run", 1) > 1 else "whole batch"}
+        del ex2
         del f2, host_args, host_in
     else:
         del keep[:]
@@ -872,6 +885,7 @@ def main():
                        "per_gpu": {k: spec[k] for k in ("B", "H", "n", "N", "D", "T") if k in spec}},
             "roofline": roofline,
             "hbm_kernels": [dict(n, frac=n["gbs"] / peaks["hbm"]) for n in m["hbm_nodes"]],
+            "gemm_nodes": m["gemm_nodes"],
             "device_ms": m["device_ms"], "ms_per_step_eager": m["ms_per_step_eager"],
             "cpu_baseline": cb, "e2e": m.get("e2e"), "gpu_launches": m["gpu_launches"],
             "clocks": m["clocks"], "parity": m.get("parity"), "also": also,

@@ -23,6 +23,12 @@ case $sec in
     AB_GEMM_NO_CLUSTER4=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_noc4.json 2> gpurun_out/bench_noc4.err; echo "bench_noc4 rc=$?"; tail -3 gpurun_out/bench_noc4.err; cut -c1-1800 gpurun_out/bench_noc4.json;;
   bench_single)
     AB_GEMM_FUSE_SINGLE=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_single.json 2> gpurun_out/bench_single.err; echo "bench_single rc=$?"; tail -3 gpurun_out/bench_single.err; cut -c1-1800 gpurun_out/bench_single.json;;
+  bench_single_noc4)
+    AB_GEMM_NO_CLUSTER4=1 AB_GEMM_FUSE_SINGLE=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_single_noc4.json 2> gpurun_out/bench_single_noc4.err; echo "bench_single_noc4 rc=$?"; tail -3 gpurun_out/bench_single_noc4.err; cut -c1-400 gpurun_out/bench_single_noc4.json;;
+  fullsize)
+    timeout 900 python -m pytest tests/test_gpu_fullsize.py -m gpu -q -s -p no:cacheprovider > gpurun_out/pytest_fullsize.log 2>&1; echo "fullsize rc=$?"; grep -a "cfg\|passed\|failed\|Error" gpurun_out/pytest_fullsize.log | cut -c1-300 | tail -20;;
+  e2e)
+    timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu > gpurun_out/bench_e2e.json 2> gpurun_out/bench_e2e.err; echo "bench_e2e rc=$?"; tail -3 gpurun_out/bench_e2e.err; python -c "import json;d=json.load(open('gpurun_out/bench_e2e.json'));print(d['ms_per_step'], d['e2e'], d.get('parity'))";;
   reference)
     timeout 500 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"; tail -2 gpurun_out/bench_reference.err; cut -c1-1200 gpurun_out/bench_reference.json;;
   smoke)
