@@ -542,6 +542,15 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
       p.ep_ptr[k] = ep->ptr[k]; p.ep_rs[k] = ep->rs[k]; p.ep_cs[k] = ep->cs[k];
     }
     if (ep->nout < 1 || ep->nout > 3) return fail(AB_ERR_INVALID, "fused epilogue yields 1..3 values");
+    // the fused epilogue moves 8 columns at a time (ab_gemm_tcgen05_kernel.cuh, fused_chunk)
+    if (N % 8) return fail(AB_ERR_UNSUPPORTED, "fused epilogue needs N %% 8 == 0");
+    if (C && (c_cs != 1 || (c_rs & 3) || (reinterpret_cast<uintptr_t>(C) & 15)))
+      return fail(AB_ERR_UNSUPPORTED, "fused epilogue needs a row-contiguous, 16-byte aligned C");
+    if (beta != 0.0f && (p.cin_cs != 1 || (p.cin_rs & 3) || (reinterpret_cast<uintptr_t>(p.Cin) & 15)))
+      return fail(AB_ERR_UNSUPPORTED, "fused epilogue needs a row-contiguous, 16-byte aligned Cin");
+    for (int k = 0; k < 3; ++k)
+      if (ep->shadow[k] && ((reinterpret_cast<uintptr_t>(ep->shadow[k]) & 15) || (ep->shadow_pitch[k] & 7)))
+        return fail(AB_ERR_UNSUPPORTED, "bf16 shadow plane rows are not 16-byte aligned");
     for (int k = 0; k < 3; ++k) {
       if (ep->shadow[k] && ((reinterpret_cast<uintptr_t>(ep->shadow[k]) & 7) || (ep->shadow_pitch[k] & 3)))
         return fail(AB_ERR_UNSUPPORTED, "bf16 shadow plane is not 8-byte aligned");

@@ -211,154 +211,165 @@ struct EpilogueOut {
   // ---- fused consumer region (codegen/gemm_epilogue.py) -------------------------------
   // The generated AB_EP_EVAL(V, E, T, O) evaluates the region's scalar program on
   // v = alpha*acc + beta*Cin and the memory operands E[k][T], leaving its AB_EP_NOUT values
-  // in O[0..][T].  Every lane of the warp stays in the function (rows beyond M contribute
-  // zeros and store nothing): the column sums are exchanged with warp shuffles.
-  __device__ __forceinline__ void put_outputs(const float (&o)[AB_EP_NOUT][8], long long row, long long col,
-                                              bool live) const {
+  // in O[0..][T].  Contract (gemm_run refuses the fused launch otherwise): N % 8 == 0, every
+  // matrix that is read or written 8 columns at a time (C, Cin, extra outputs, operands with
+  // unit column stride) has 16-byte aligned rows.
+  //
+  // The work is organised per 32-column chunk of one accumulator row (`fused_chunk`), so that
+  // the body exists ONCE in the instruction stream: an epilogue unrolled over all 128
+  // columns of a thread (tanh, IEEE division, float64 sums per element) is several hundred KB
+  // of SASS, which every warp re-fetches from L2 for every tile (measured: the region with
+  // two values and two reductions ran 1.5 ms slower than its five separate kernels).
+  struct FusedScalars { float v[4]; bool is[4]; };
+  __device__ __forceinline__ FusedScalars load_scalars() const {
+    FusedScalars s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s.is[k] = k < AB_EP_NOPS && p.ep_rs[k] == 0 && p.ep_cs[k] == 0;  // a [1,1] operand
+      s.v[k] = s.is[k] ? p.ep_ptr[k][0] : 0.0f;
+    }
+    return s;
+  }
+  __device__ __forceinline__ void put_outputs(const float (&o)[AB_EP_NOUT][8], long long row, long long col) const {
 #pragma unroll
     for (int k = 0; k < AB_EP_NOUT; ++k) {
       float* dst = k == 0 ? p.C : p.out_ptr[k];
       const long long rs = k == 0 ? p.c_rs : p.out_rs[k];
-      if (dst && live)
+      if (dst)
         st8(dst + row * rs + col, o[k], ((rs & 7) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 31) == 0));
-      if (p.shadow[k] && live) {
+      if (p.shadow[k]) {
         uint32_t h[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t)
           asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[t]) : "f"(o[k][2 * t + 1]), "f"(o[k][2 * t]));
         uint16_t* sp = static_cast<uint16_t*>(p.shadow[k]) + row * p.shadow_pitch[k] + col;
-        if (((reinterpret_cast<uintptr_t>(p.shadow[k]) & 15) == 0) && ((p.shadow_pitch[k] & 7) == 0)) {
-          *reinterpret_cast<uint4*>(sp) = make_uint4(h[0], h[1], h[2], h[3]);
-        } else {
-          *reinterpret_cast<uint2*>(sp) = make_uint2(h[0], h[1]);
-          *reinterpret_cast<uint2*>(sp + 4) = make_uint2(h[2], h[3]);
-        }
+        *reinterpret_cast<uint4*>(sp) = make_uint4(h[0], h[1], h[2], h[3]);
       }
     }
   }
-  __device__ __forceinline__ void store_fused(float (&acc)[kAccRegs], long long row, long long n0,
-                                              int nchunks, int lane) const {
-    const bool live = row < p.M;
-    const long long rb = row >> 5;  // 32-row block of this warp (row - lane is a multiple of 32)
-    float* crow = p.C + (live ? row : 0) * p.c_rs;
-    const float* irow = p.Cin + (live ? row : 0) * p.cin_rs;
-    // extra outputs / shadows are row-contiguous by contract; C and Cin decide the vector path
-    const bool vec = (p.c_cs == 1 || !p.C) && (!p.C || (((p.c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0))) &&
-                     (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
-                                         ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
-#if AB_EP_FULLSUM >= 0
-    double fs = 0.0;
-#endif
+  // x[32]: raw accumulator values of columns col0 .. col0+31 of `row`; on return (AB_EP_COLSUM
+  // builds) they have been replaced and reduced: the column sums of the warp's 32 rows are
+  // written to colsum_ws.  `fs` accumulates the AB_EP_FULLSUM value of this thread.
+  __device__ __forceinline__ void fused_chunk(float (&x)[32], long long row, long long col0, bool live,
+                                              int lane, const FusedScalars& sc, double& fs) const {
+    const long long r = live ? row : 0;
 #pragma unroll
-    for (int c = 0; c < kAccRegs / 32; ++c) {
-      if (c < nchunks) {
-        const long long col0 = n0 + c * 32;
-        if (vec && col0 + 32 <= p.N) {
+    for (int j = 0; j < 32; j += 8) {
+      const long long col = col0 + j;
+      if (live && col < p.N) {  // N % 8 == 0: a group of 8 columns is inside or outside as a whole
+        float v[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float v[8];
+        for (int t = 0; t < 8; ++t) v[t] = p.alpha * x[j + t];
+        if (p.beta != 0.0f) {
+          float ci[8];
+          ld8(p.Cin + r * p.cin_rs + col, ci, wide_in);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = p.alpha * acc[c * 32 + j + t];
-            if (p.beta != 0.0f && live) {
-              float o[8];
-              ld8(irow + col0 + j, o, wide_in);
+          for (int t = 0; t < 8; ++t) v[t] += p.beta * ci[t];
+        }
+        float e[4][8];
 #pragma unroll
-              for (int t = 0; t < 8; ++t) v[t] += p.beta * o[t];
-            }
-            float e[4][8];
+        for (int k = 0; k < AB_EP_NOPS; ++k) {
+          if (sc.is[k]) {
 #pragma unroll
-            for (int k = 0; k < AB_EP_NOPS; ++k) {
-              const float* q = p.ep_ptr[k] + (live ? row : 0) * p.ep_rs[k] + (col0 + j) * p.ep_cs[k];
-              if (p.ep_cs[k] == 1) {
-                ld8(q, e[k], ((reinterpret_cast<uintptr_t>(p.ep_ptr[k]) & 31) == 0) && ((p.ep_rs[k] & 7) == 0));
-              } else {
+            for (int t = 0; t < 8; ++t) e[k][t] = sc.v[k];
+          } else if (p.ep_cs[k] == 1) {
+            ld8(p.ep_ptr[k] + r * p.ep_rs[k] + col, e[k],
+                ((reinterpret_cast<uintptr_t>(p.ep_ptr[k]) & 31) == 0) && ((p.ep_rs[k] & 7) == 0));
+          } else {
+            const float* q = p.ep_ptr[k] + r * p.ep_rs[k] + col * p.ep_cs[k];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) e[k][t] = q[t * p.ep_cs[k]];
-              }
-            }
-            float o[AB_EP_NOUT][8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) { AB_EP_EVAL(v[t], e, t, o); }
-            put_outputs(o, row, col0 + j, live);
-#if AB_EP_COLSUM >= 0
-#pragma unroll
-            for (int t = 0; t < 8; ++t) acc[c * 32 + j + t] = live ? o[AB_EP_COLSUM][t] : 0.0f;
-#endif
-#if AB_EP_FULLSUM >= 0
-            if (live) {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) fs += (double)o[AB_EP_FULLSUM][t];
-            }
-#endif
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long col = col0 + j;
-            const bool in = live && col < p.N;
-            float o[AB_EP_NOUT][8];
-            if (in) {
-              float v = p.alpha * acc[c * 32 + j];
-              if (p.beta != 0.0f) v += p.beta * irow[col * p.cin_cs];
-              float e[4][8];
-#pragma unroll
-              for (int k = 0; k < AB_EP_NOPS; ++k) e[k][0] = p.ep_ptr[k][row * p.ep_rs[k] + col * p.ep_cs[k]];
-              AB_EP_EVAL(v, e, 0, o);
-#pragma unroll
-              for (int k = 0; k < AB_EP_NOUT; ++k) {
-                if (k == 0) { if (p.C) crow[col * p.c_cs] = o[0][0]; }
-                else if (p.out_ptr[k]) p.out_ptr[k][row * p.out_rs[k] + col] = o[k][0];
-                if (p.shadow[k]) {
-                  uint32_t b2;
-                  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b2) : "f"(0.0f), "f"(o[k][0]));
-                  static_cast<uint16_t*>(p.shadow[k])[row * p.shadow_pitch[k] + col] = (uint16_t)(b2 & 0xFFFFu);
-                }
-              }
-            }
-#if AB_EP_COLSUM >= 0
-            acc[c * 32 + j] = in ? o[AB_EP_COLSUM][0] : 0.0f;
-#endif
-#if AB_EP_FULLSUM >= 0
-            if (in) fs += (double)o[AB_EP_FULLSUM][0];
-#endif
+            for (int t = 0; t < 8; ++t) e[k][t] = q[t * p.ep_cs[k]];
           }
         }
+        float o[AB_EP_NOUT][8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { AB_EP_EVAL(v[t], e, t, o); }
+        put_outputs(o, r, col);
 #if AB_EP_COLSUM >= 0
-        {
-          // 32 x 32 transpose-reduce: after the step with distance h every lane keeps the half
-          // of its columns selected by bit h of its lane index; lane l ends with column col0 + l
-          double d[16];
-          {
-            const bool up = (lane & 16) != 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float keep = up ? acc[c * 32 + 16 + i] : acc[c * 32 + i];
-              const float send = up ? acc[c * 32 + i] : acc[c * 32 + 16 + i];
-              d[i] = (double)keep + (double)__shfl_xor_sync(0xffffffffu, send, 16);
-            }
-          }
+        for (int t = 0; t < 8; ++t) x[j + t] = o[AB_EP_COLSUM][t];
+#endif
+#if AB_EP_FULLSUM >= 0
 #pragma unroll
-          for (int h = 8; h >= 1; h >>= 1) {
-            const bool up = (lane & h) != 0;
+        for (int t = 0; t < 8; ++t) fs += (double)o[AB_EP_FULLSUM][t];
+#endif
+      } else {
+#if AB_EP_COLSUM >= 0
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i < h) {
-                const double keep = up ? d[h + i] : d[i];
-                const double send = up ? d[i] : d[h + i];
-                d[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-              }
-            }
-          }
-          if (rb * 32 < p.M && col0 + lane < p.N) p.colsum_ws[rb * p.N + col0 + lane] = d[0];
-        }
+        for (int t = 0; t < 8; ++t) x[j + t] = 0.0f;
 #endif
       }
     }
+#if AB_EP_COLSUM >= 0
+    {
+      // 32 x 32 transpose-reduce over the warp's rows in float64 (the reference's CAReduce
+      // accumulates float32 sums in float64, tensor/elemwise.py:1371-1385): after the step
+      // with distance h every lane keeps the half of its columns selected by bit h of its lane
+      // index; lane l ends with the sum of column col0 + l
+      double d[16];
+      {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float keep = up ? x[16 + i] : x[i];
+          const float send = up ? x[i] : x[16 + i];
+          d[i] = (double)keep + (double)__shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+#define AB_COLSUM_STEP(H)                                                      \
+      {                                                                        \
+        const bool up = (lane & (H)) != 0;                                     \
+        _Pragma("unroll") for (int i = 0; i < (H); ++i) {                      \
+          const double keep = up ? d[(H) + i] : d[i];                          \
+          const double send = up ? d[i] : d[(H) + i];                          \
+          d[i] = keep + __shfl_xor_sync(0xffffffffu, send, (H));               \
+        }                                                                      \
+      }
+      AB_COLSUM_STEP(8) AB_COLSUM_STEP(4) AB_COLSUM_STEP(2) AB_COLSUM_STEP(1)
+#undef AB_COLSUM_STEP
+      const long long rb = row >> 5;  // row - lane is a multiple of 32
+      if (rb * 32 < p.M && col0 + lane < p.N) p.colsum_ws[rb * p.N + col0 + lane] = d[0];
+    }
+#endif
+  }
+  __device__ __forceinline__ void finish_fullsum(double fs, long long row, long long n0, int lane) const {
 #if AB_EP_FULLSUM >= 0
 #pragma unroll
     for (int h = 16; h >= 1; h >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, h);
+    const long long rb = row >> 5;
     if (lane == 0 && rb * 32 < p.M) p.fullsum_ws[rb * p.fullsum_cols + n0 / (p.block_n >> 1)] = fs;
 #endif
+  }
+  // accumulator already folded into registers (several K segments: the fp32-faithful mode)
+  __device__ __forceinline__ void store_fused(float (&acc)[kAccRegs], long long row, long long n0,
+                                              int nchunks, int lane) const {
+    const bool live = row < p.M;
+    const FusedScalars sc = load_scalars();
+    double fs = 0.0;
+#pragma unroll
+    for (int c = 0; c < kAccRegs / 32; ++c) {
+      if (c < nchunks)
+        fused_chunk(*reinterpret_cast<float(*)[32]>(&acc[c * 32]), row, n0 + c * 32, live, lane, sc, fs);
+    }
+    finish_fullsum(fs, row, n0, lane);
+  }
+  // the whole K range sits in one TMEM accumulator (bf16 / tf32 policies): 32 columns at a
+  // time straight from TMEM in a rolled loop -- 32 live accumulator registers instead of 128
+  __device__ __forceinline__ void store_fused_tmem(uint32_t t_acc, long long row, long long n0, int nchunks,
+                                                   int lane) const {
+    const bool live = row < p.M;
+    const FusedScalars sc = load_scalars();
+    double fs = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+      fused_chunk(x, row, n0 + c * 32, live, lane, sc, fs);
+    }
+    finish_fullsum(fs, row, n0, lane);
   }
 #endif  // AB_EPILOGUE
 };
@@ -510,6 +521,23 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
         AB_UNIT_DECODE
       const long long m0 = (tile / tiles_n) * BLOCK_M;
       const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
+#ifdef AB_EPILOGUE
+      if (KIND == 1 || kb_end - kb_begin <= p.seg_kblocks) {  // bf16 products are never segmented
+        // one segment: the epilogue reads TMEM chunk by chunk, then frees the stage
+        const uint32_t as = sit % (uint32_t)p.acc_stages;
+        const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+        ++sit;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tcgen05_fence_after();
+        const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
+                               ((uint32_t)(q * 32) << 16);
+        eo.store_fused_tmem(t_acc, m0 + q * 32 + lane, n0, nchunks, lane);
+        tcgen05_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
+                     : "memory");
+        continue;
+      }
+#endif
       for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
         const uint32_t as = sit % (uint32_t)p.acc_stages;
         const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
@@ -735,6 +763,23 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
         AB_UNIT_DECODE
       const long long m0 = (tile / tiles_n) * CLUSTER_M + (long long)pair * TILE_M + (long long)rank * BLOCK_M;
       const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
+#ifdef AB_EPILOGUE
+      if (KIND == 1 || kb_end - kb_begin <= p.seg_kblocks) {  // bf16 products are never segmented
+        const uint32_t as = sit % (uint32_t)p.acc_stages;
+        const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+        ++sit;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tcgen05_fence_after();
+        const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
+                               ((uint32_t)(q * 32) << 16);
+        eo.store_fused_tmem(t_acc, m0 + q * 32 + lane, n0, nchunks, lane);
+        tcgen05_fence_before();
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(
+                         smem_u32(&tmem_empty_bar[as]) & kPeerBitMask)
+                     : "memory");
+        continue;
+      }
+#endif
       for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
         const uint32_t as = sit % (uint32_t)p.acc_stages;
         const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;

@@ -48,6 +48,7 @@ class ScanRunner:
 
             self.lstm = LstmMatch(self.inner)
         self.used_fast_path = False
+        self.direct_writes = 0
 
     def run(self, args):
         info = self.info
@@ -113,14 +114,25 @@ class ScanRunner:
                     inner_in.append(bufs[idx].index(((pos[idx] + t) % store_steps[idx],)))
             inner_in += shared_vals
             inner_in += non_seqs
-            inner_out = self.inner(*inner_in)
+            # sit-sot / mit-sot results go straight into their ring rows when the row does not
+            # overlap anything this step still reads (scan_perform.pyx copies, op.py:2005-2040)
+            k0 = sum(len(self.mm_out[g]) for g in range(self.n_mit_mot))
+            want = {}
+            for j in range(self.n_mit_mot, n_outs):
+                row = bufs[j].index((pos[j],))
+                if row.is_c_contiguous() and not any(_overlaps(row, a) for a in inner_in):
+                    want[k0 + j - self.n_mit_mot] = row
+            inner_out = self.inner(*inner_in, out_storage=want)
             k = 0
             for g in range(self.n_mit_mot):
                 for out_slice in self.mm_out[g]:
                     K.copy_into(bufs[g].index((out_slice + pos[g],)), _d(inner_out[k]))
                     k += 1
             for j in range(self.n_mit_mot, n_outs):
-                K.copy_into(bufs[j].index((pos[j],)), _d(inner_out[k]))
+                if inner_out[k] is not want.get(k):
+                    K.copy_into(bufs[j].index((pos[j],)), _d(inner_out[k]))
+                else:
+                    self.direct_writes += 1
                 k += 1
             for j in range(n_nit):
                 val = _d(inner_out[k])
@@ -156,6 +168,27 @@ class ScanRunner:
                 if i < n_steps:
                     allb[idx] = b.index((slice(0, st - (n_steps - i)),))
         return allb + shared_vals
+
+
+def _overlaps(a, b):
+    """Conservative byte-range overlap of two device arrays (host values never overlap)."""
+    if not isinstance(a, DeviceArray) or not isinstance(b, DeviceArray) or a.owner is not b.owner:
+        return False
+
+    def span(x):
+        lo = hi = 0
+        for n, s in zip(x.shape, x.strides):
+            if n == 0:
+                return x.ptr, x.ptr
+            if s >= 0:
+                hi += (n - 1) * s
+            else:
+                lo += (n - 1) * s
+        return x.ptr + lo * x.itemsize, x.ptr + (hi + 1) * x.itemsize
+
+    a0, a1 = span(a)
+    b0, b1 = span(b)
+    return a0 < b1 and b0 < a1
 
 
 def _d(v):

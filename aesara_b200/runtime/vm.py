@@ -217,6 +217,7 @@ class ProgramExecutor:
         # (or region) that produces function output k has been launched, so that a collective
         # on a finished gradient overlaps the rest of the evaluation
         self.output_hook = None
+        self._out_storage = None
         producer = {v: i for i, n in enumerate(program.nodes) for v in n.outputs}
         self._outputs_of_node = {}
         for k, v in enumerate(program.outputs):
@@ -315,8 +316,15 @@ class ProgramExecutor:
         self._subset_cache[key] = (needed, key)
         return needed, key
 
-    def __call__(self, *inputs, output_subset=None):
+    def __call__(self, *inputs, output_subset=None, out_storage=None):
+        """``out_storage`` ({output position: DeviceArray}): where the caller would like those
+        outputs to be written (a Scan step hands the rows of its output buffers,
+        runtime/scan.py); honoured by the node that allocates the output when shape, dtype and
+        layout agree — the caller checks identity and copies otherwise."""
         prog = self.program
+        self._out_storage = None
+        if out_storage:
+            self._out_storage = {prog.outputs[k]: a for k, a in out_storage.items()}
         if len(inputs) != len(prog.inputs):
             raise TypeError(f"expected {len(prog.inputs)} inputs, got {len(inputs)}")
         needed = None
@@ -561,7 +569,12 @@ def _elemwise(ex, i, node, args):
         else:
             if order is None:
                 order = K.elemwise_out_order(ins, shape)
-            outs.append(DeviceArray.empty(shape, dt, order=order))
+            want = ex._out_storage.get(node.outputs[k]) if ex._out_storage else None
+            if (want is not None and want.shape == tuple(shape) and want.dtype == dt and order == "C"
+                    and want.is_c_contiguous()):
+                outs.append(want)  # the caller's buffer (a row of a Scan output ring)
+            else:
+                outs.append(DeviceArray.empty(shape, dt, order=order))
     if all(n != 0 for n in shape) or not shape:
         kern.launch(shape, ins, outs)
     return outs[0] if n_out == 1 else outs

@@ -29,6 +29,8 @@ case $sec in
     timeout 900 python -m pytest tests/test_gpu_fullsize.py -m gpu -q -s -p no:cacheprovider > gpurun_out/pytest_fullsize.log 2>&1; echo "fullsize rc=$?"; grep -a "cfg\|passed\|failed\|Error" gpurun_out/pytest_fullsize.log | cut -c1-300 | tail -20;;
   e2e)
     timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu > gpurun_out/bench_e2e.json 2> gpurun_out/bench_e2e.err; echo "bench_e2e rc=$?"; tail -3 gpurun_out/bench_e2e.err; python -c "import json;d=json.load(open('gpurun_out/bench_e2e.json'));print(d['ms_per_step'], d['e2e'], d.get('parity'))";;
+  e2e_probe)
+    timeout 600 python tools/e2e_probe.py 2>&1 | grep -v Warn | tail -12;;
   reference)
     timeout 500 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"; tail -2 gpurun_out/bench_reference.err; cut -c1-1200 gpurun_out/bench_reference.json;;
   smoke)
