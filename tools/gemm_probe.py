@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Per-shape timing of the bf16 tcgen05 GEMM (the three operand layouts of cfg3), 4-CTA
+multicast clusters on/off, back to back in one process; sustained (many iterations)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+from aesara_b200.runtime import kernels as K
+from aesara_b200.runtime import lib
+from aesara_b200.runtime.device import DeviceArray
+
+lib.check(lib.load().ab_init(0))
+torch.cuda.set_device(0)
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+B, H = 65536, 4096
+g = torch.Generator(device="cuda").manual_seed(0)
+X = torch.randn(B, H, device="cuda", generator=g)
+D = torch.randn(B, H, device="cuda", generator=g)
+W = torch.randn(H, H, device="cuda", generator=g) / 64
+dX, dD, dW = DeviceArray.from_torch(X), DeviceArray.from_torch(D), DeviceArray.from_torch(W)
+shapes = {
+    "fwd  X[B,H] @ W[H,H]      (A K-major, B MN-major)": (dX, dW, (B, H)),
+    "dh   D[B,H] @ W.T         (A K-major, B K-major)": (dD, dW.dimshuffle([1, 0]), (B, H)),
+    "dW   X.T[H,B] @ D[B,H]    (A MN-major, B MN-major, K=65536)": (dX.dimshuffle([1, 0]), dD, (H, H)),
+}
+res = {}
+for name, (A, Bm, oshape) in shapes.items():
+    C = DeviceArray.empty(oshape, "float32")
+    for variant in ("cluster4", "2cta"):
+        if variant == "2cta":
+            os.environ["AB_GEMM_NO_CLUSTER4"] = "1"
+        else:
+            os.environ.pop("AB_GEMM_NO_CLUSTER4", None)
+        cache = K.PackCache()
+        for _ in range(3):
+            K.gemm(C, 1.0, A, Bm, 0.0, precision=2, cache=cache)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            K.gemm(C, 1.0, A, Bm, 0.0, precision=2, cache=cache)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        tf = 2.0 * B * H * H / ms / 1e9
+        res[f"{name} | {variant}"] = {"ms": ms, "tflops": tf}
+        print(f"{name:70s} {variant:9s} {ms:7.3f} ms  {tf:7.1f} TF/s", flush=True)
+# cuBLAS through torch as the yardstick of the box at this moment (checker only)
+a = X.bfloat16()
+w = W.bfloat16()
+for _ in range(3):
+    torch.matmul(a, w)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters):
+    torch.matmul(a, w)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / iters
+print(f"{'cuBLAS bf16 (torch.matmul) same fwd shape, bf16 out':70s} {'':9s} {ms:7.3f} ms  {2.0*B*H*H/ms/1e9:7.1f} TF/s")
+res["cublas_fwd"] = {"ms": ms, "tflops": 2.0 * B * H * H / ms / 1e9}
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "gemm_probe.json"), "w"), indent=1)

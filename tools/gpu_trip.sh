@@ -31,6 +31,10 @@ case $sec in
     timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu > gpurun_out/bench_e2e.json 2> gpurun_out/bench_e2e.err; echo "bench_e2e rc=$?"; tail -3 gpurun_out/bench_e2e.err; python -c "import json;d=json.load(open('gpurun_out/bench_e2e.json'));print(d['ms_per_step'], d['e2e'], d.get('parity'))";;
   e2e_probe)
     timeout 600 python tools/e2e_probe.py 2>&1 | grep -v Warn | tail -12;;
+  gemm_probe)
+    timeout 600 python tools/gemm_probe.py 30 2>&1 | tail -9;;
+  gemm_ncu)
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 6 -c 2 -o gpurun_out/gemm_prof -f python tools/gemm_probe.py 2 > gpurun_out/gemm_ncu.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/gemm_ncu.log | cut -c1-300; ls -la gpurun_out/gemm_prof.ncu-rep;;
   reference)
     timeout 500 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"; tail -2 gpurun_out/bench_reference.err; cut -c1-1200 gpurun_out/bench_reference.json;;
   smoke)
