@@ -46,8 +46,9 @@ class RowFusion:
 
     # ------------------------------------------------------------------ analysis
     @staticmethod
-    def detect(program):
-        """All fusable regions of ``program`` (normally zero or one)."""
+    def detect(program, destroys=None):
+        """All fusable regions of ``program`` (normally zero or one).  ``destroys[i]``: input
+        positions node i rewrites in place (the executor's destroy map)."""
         if os.environ.get("AB_NO_ROWFUSE"):
             return []
         producer = {}
@@ -63,10 +64,28 @@ class RowFusion:
             if n.op != "Gemv" or i in taken:
                 continue
             f = RowFusion._grow(program, i, producer, consumers)
+            if f is not None and not RowFusion._schedule_ok(program, f, consumers, destroys):
+                f = None
             if f is not None and not (set(f.members) & taken):
                 found.append(f)
                 taken.update(f.members)
         return found
+
+    @staticmethod
+    def _schedule_ok(program, f, consumers, destroys):
+        """The members are deferred to ``f.last``: no node in between may read a value the
+        region produces (it would not exist yet), nor rewrite memory in place (X, w or an
+        operand vector could change under the deferred kernel) — ADVICE r1."""
+        members = set(f.members)
+        outs = {v for m in f.members for v in program.nodes[m].outputs}
+        for i in range(f.first + 1, f.last):
+            if i in members:
+                continue
+            if any(v in outs for v in program.nodes[i].inputs):
+                return False
+            if destroys is not None and destroys[i]:
+                return False
+        return True
 
     @staticmethod
     def _is_fresh_gemv(program, node, producer):

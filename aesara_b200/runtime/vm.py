@@ -197,7 +197,7 @@ class ProgramExecutor:
 
         from .gemmfuse import GemmEpilogueFusion
 
-        self._fusions = RowFusion.detect(program)
+        self._fusions = RowFusion.detect(program, self._destroys)
         taken = {i for f in self._fusions for i in f.members}
         self._fusions += GemmEpilogueFusion.detect(program, self._destroys, taken)
         from .redfuse import ReducePreFusion

@@ -261,7 +261,8 @@ int ab_cumulative(int dtype, int mul, const void* x, void* out, int64_t outer, i
  * hbuf / cbuf are the Scan's circular output buffers [sh|sc, B, H] (contiguous); the row
  * before pos_h / pos_c holds the initial state; step t writes row (pos + t) % s.
  * x is [T, B, 4H] with element strides (x_ts, x_rs, 1); U is [H, 4H] with strides
- * (u_rs, u_cs).  One cooperative launch; steps are ordered by a device-wide barrier. */
+ * (u_rs, u_cs).  One cooperative launch; there is no barrier between steps: a step-t+1
+ * tile waits only for the step-t tiles of its own 256-row block (per-row-block counters). */
 int ab_lstm_scan_supported(int64_t t, int64_t b, int64_t h);
 int ab_lstm_scan_workspace_bytes(int64_t b, int64_t h, size_t* bytes);
 int ab_lstm_scan(int64_t T, int64_t B, int64_t H, const void* x, int64_t x_ts, int64_t x_rs,
