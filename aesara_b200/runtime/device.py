@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 PINNED_MIN_BYTES = 1 << 16  # device->host copies at least this big use page-locked memory
+SMALL_STAGE_BYTES = 1 << 20  # host->device copies up to this size are staged through page-locked memory
 _TORCH_BYTES = torch.uint8
 
 
@@ -78,6 +79,15 @@ class DeviceArray:
         out = DeviceArray.empty(src.shape, src.dtype, device=device)
         if src.size:
             hb = torch.from_numpy(src.reshape(-1).view(np.uint8))
+            if not hb.is_pinned() and hb.numel() <= SMALL_STAGE_BYTES:
+                # A copy from pageable memory is synchronous: issued behind queued kernels it
+                # blocks the host until they have run (a hidden device synchronisation per
+                # staged scalar).  Small values go through a page-locked staging block of
+                # torch's caching host allocator instead, which the allocator keeps alive until
+                # the stream has consumed it.
+                st = torch.empty(hb.numel(), dtype=_TORCH_BYTES, pin_memory=True)
+                st.copy_(hb)
+                hb = st
             out.owner[: hb.numel()].copy_(hb, non_blocking=hb.is_pinned())
         return out
 

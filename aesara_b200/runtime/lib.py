@@ -161,6 +161,14 @@ SIGNATURES = {
         [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
          C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p],
     ),
+    "ab_cell_scan_supported": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64]),
+    "ab_cell_scan_workspace_bytes": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]),
+    "ab_cell_scan": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+         C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+         C.POINTER(C.c_int64), C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
     "ab_lstm_scan_supported": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "ab_lstm_scan_workspace_bytes": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]),
     "ab_lstm_scan": (

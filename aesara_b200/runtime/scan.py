@@ -38,16 +38,19 @@ class ScanRunner:
         self.n_shared = info["n_shared_outs"]
         self.n_seqs = info["n_seqs"]
         self.mintaps = [min(t) for t in self.tap_array] + [0] * self.n_nit_sot
-        # fast path: LSTM-cell recurrence -> one persistent kernel (runtime/scan_lstm.py)
-        self.lstm = None
-        if (self.n_seqs == 1 and not self.mm_in and self.tap_array == [[-1], [-1]]
+        # fast path: "one Gemm with a loop-invariant matrix + Elemwise on its column slices"
+        # (LSTM, tanh-RNN, gated units) -> one persistent kernel (runtime/scan_cell.py)
+        self.cell = None
+        if (self.n_seqs == 1 and not self.mm_in and 1 <= len(self.tap_array) <= 3
+                and all(list(t) == [-1] for t in self.tap_array)
                 and self.n_nit_sot == 0 and self.n_shared == 0 and info["n_non_seqs"] == 1
                 and not info["as_while"] and parent.precision == 0
                 and not os.environ.get("AB_SCAN_NO_FAST")):
-            from .scan_lstm import LstmMatch
+            from .scan_cell import CellMatch
 
-            self.lstm = LstmMatch(self.inner)
+            self.cell = CellMatch(self.inner, len(self.tap_array))
         self.used_fast_path = False
+        self.fast_path_kind = None   # "lstm" (ahead-of-time cell) or "jit" (generated cell)
         self.direct_writes = 0
 
     def run(self, args):
@@ -96,14 +99,23 @@ class ScanRunner:
         pos = [(-self.mintaps[idx]) % store_steps[idx] for idx in range(n_outs + n_nit)]
         i, cond = 0, True
         self.used_fast_path = False
-        if self.lstm is not None and len(non_seqs) == 1:
-            from . import scan_lstm
+        self.fast_path_kind = None
+        if self.cell is not None and len(non_seqs) == 1:
+            from . import scan_cell
 
             U = dev(non_seqs[0], len(args) - 1)
-            hb, cb = bufs[0], bufs[1]
-            if (scan_lstm.eligible(seqs[0], U, hb, cb, n_steps)
-                    and self.lstm.match(hb.shape[1], hb.shape[2])):
-                scan_lstm.run_lstm(n_steps, seqs[0], U, hb, cb, pos[0], pos[1])
+            H = bufs[0].shape[2] if bufs[0].ndim == 3 else 0
+            gates = U.shape[1] // H if (U.ndim == 2 and H and U.shape[1] % H == 0) else 0
+            spec = None
+            if gates and scan_cell.eligible(seqs[0], U, bufs, n_steps, gates):
+                spec = self.cell.match(bufs[0].shape[1], H, gates)
+            if spec is not None:
+                if spec.is_lstm and not os.environ.get("AB_SCAN_JIT"):
+                    scan_cell.run_lstm(n_steps, seqs[0], U, bufs[0], bufs[1], pos[0], pos[1])
+                    self.fast_path_kind = "lstm"
+                else:
+                    scan_cell.run_cell(spec, n_steps, seqs[0], U, bufs, pos[:n_outs])
+                    self.fast_path_kind = "jit"
                 i = n_steps
                 pos = [(p + n_steps) % s for p, s in zip(pos, store_steps)]
                 self.used_fast_path = True

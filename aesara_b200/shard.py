@@ -429,12 +429,18 @@ class ChunkedHostExecutor:
         host_out, self.ex.host_outputs = self.ex.host_outputs, False
         acc = [None] * len(modes)
         mul, fma = self._kernels()
+        # every block's weight (and a 1 for `sum` outputs) goes to the device in ONE small copy
+        # before anything is queued: a pageable-memory copy is synchronous, and issued between
+        # blocks it would wait for the previous block's kernels — no overlap at all
+        blocks = [row_block(rows, n, c) for c in range(n)]
+        wall = DeviceArray.from_numpy(np.asarray([(b0 - a0) / float(rows) for a0, b0 in blocks] + [1.0], "float32"))
+        one = wall.index((slice(n, n + 1),))
         try:
             for c in range(n):
-                a0, b0 = row_block(rows, n, c)
+                a0, b0 = blocks[c]
                 local = [a[a0:b0] if ax == 0 else a for a, ax in zip(args, axes)]
                 outs = self.ex(*local)
-                w = DeviceArray.from_numpy(np.asarray([(b0 - a0) / float(rows)], "float32"))
+                w = wall.index((slice(c, c + 1),))
                 for k, (o, m) in enumerate(zip(outs, modes)):
                     if m[0] in ("sum", "mean"):
                         o = o if isinstance(o, DeviceArray) else DeviceArray.from_numpy(np.asarray(o))
@@ -448,8 +454,8 @@ class ChunkedHostExecutor:
                                 acc[k] = DeviceArray.empty(o.shape, "float32")
                                 mul.launch(o.shape, [o, wv.view((1,) * o.ndim, (0,) * o.ndim)], [acc[k]])
                         else:
-                            one = wv if wv is not None else DeviceArray.from_numpy(np.ones(1, "float32"))
-                            fma.launch(o.shape, [acc[k], o, one.view((1,) * o.ndim, (0,) * o.ndim)], [acc[k]])
+                            sc = wv if wv is not None else one
+                            fma.launch(o.shape, [acc[k], o, sc.view((1,) * o.ndim, (0,) * o.ndim)], [acc[k]])
                     elif m[0] == "concat":
                         ax = m[1]
                         if acc[k] is None:

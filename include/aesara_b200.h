@@ -270,6 +270,21 @@ int ab_lstm_scan(int64_t T, int64_t B, int64_t H, const void* x, int64_t x_ts, i
                  void* cbuf, int64_t sc, int64_t pos_c, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* The same persistent kernel for the whole family "one Gemm(x_t, 1, s_hs, U, 1) + Elemwise
+ * nodes on its column slices" (aesara/scan/op.py:1673-2160 runs such an inner function step
+ * by step): pre = x[t] + s_hs[t-1] @ U is [B, gates*H]; the cell maps the `gates` column
+ * blocks of pre and the `states` previous states to the new states.  `module` is the NVRTC
+ * build of csrc/ab_scan_cell_kernel.cuh with the cell generated from the inner graph's scalar
+ * expressions (aesara_b200/codegen/scan_cell.py).  state_bufs[k] is the Scan's output ring
+ * [state_lens[k], B, H] of state k (row state_pos[k] - 1 holds the initial value); x is
+ * [T, B, gates*H] with strides (x_ts, x_rs, 1); U is [H, gates*H] with strides (u_rs, u_cs). */
+int ab_cell_scan_supported(int gates, int states, int64_t t, int64_t b, int64_t h);
+int ab_cell_scan_workspace_bytes(int gates, int64_t b, int64_t h, size_t* bytes);
+int ab_cell_scan(ab_module* module, int gates, int states, int hs, int64_t T, int64_t B, int64_t H,
+                 const void* x, int64_t x_ts, int64_t x_rs, const void* U, int64_t u_rs, int64_t u_cs,
+                 void* const* state_bufs, const int64_t* state_lens, const int64_t* state_pos,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* number of kernels this library has launched since load (bench.py reports it) */
 uint64_t ab_launch_count(void);
 

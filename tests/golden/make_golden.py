@@ -815,6 +815,44 @@ def _():
     return [x0, limit], [vs, vs[-1], vs.shape[0]], [rnd(2000, "float32", 0, 1), np.float32(300.0)]
 
 
+# ---------------------------------------------------------------- Scan cell family (one Gemm + Elemwise)
+@case("scan_rnn_tanh_cell")
+def _():
+    """tanh-RNN with pre-projected inputs: h_t = tanh(x_t + h_{t-1} @ U): 1 gate, 1 state."""
+    x = at.ftensor3("x")
+    h0, U = at.fmatrix("h0"), at.fmatrix("U")
+    hs, _ = aesara.scan(lambda x_t, h, U_: at.tanh(x_t + at.dot(h, U_)), sequences=[x], outputs_info=[h0],
+                        non_sequences=[U])
+    T, B, H = 5, 256, 64
+    r = np.random.default_rng(21)
+    return [x, h0, U], [hs[-1], hs.sum(axis=0)], [r.standard_normal((T, B, H)).astype("float32"),
+                                                  (r.standard_normal((B, H)) * 0.1).astype("float32"),
+                                                  (r.standard_normal((H, H)) / np.sqrt(H)).astype("float32")]
+
+
+@case("scan_gated_unit_cell")
+def _():
+    """A minimal gated unit on one product (3 gates, 1 state):
+    pre = x_t + h @ U;  z = sigmoid(pre_0), r = sigmoid(pre_1), n = tanh(pre_2 * r);  h' = (1 - z) * h + z * n."""
+    x = at.ftensor3("x")
+    h0, U = at.fmatrix("h0"), at.fmatrix("U")
+
+    def step(x_t, h, U_):
+        H = h.shape[1]
+        pre = x_t + at.dot(h, U_)
+        z = at.sigmoid(pre[:, :H])
+        r = at.sigmoid(pre[:, H : 2 * H])
+        n = at.tanh(pre[:, 2 * H :] * r)
+        return (1.0 - z) * h + z * n
+
+    hs, _ = aesara.scan(step, sequences=[x], outputs_info=[h0], non_sequences=[U])
+    T, B, H = 6, 256, 64
+    r = np.random.default_rng(22)
+    return [x, h0, U], [hs[-1], hs], [r.standard_normal((T, B, 3 * H)).astype("float32"),
+                                      (r.standard_normal((B, H)) * 0.1).astype("float32"),
+                                      (r.standard_normal((H, 3 * H)) / np.sqrt(H)).astype("float32")]
+
+
 PY_LINKER_CASES = {"indexing_embedding", "adv_index_pairs", "classifier_int_labels", "cumsum_cumprod", "batched_dot_ifelse"}
 
 

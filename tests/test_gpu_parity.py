@@ -513,6 +513,73 @@ def test_gemm_full_size_tile_independence(rt):
     assert rel < 2e-2
 
 
+@pytest.mark.parametrize("name,gates", [("scan_rnn_tanh_cell", 1), ("scan_gated_unit_cell", 3)])
+def test_scan_cell_family_runs_as_one_persistent_kernel(rt, name, gates):
+    """Scan inner graphs "one Gemm(x_t, 1, h, U, 1) + Elemwise on its column slices" other than
+    the LSTM get a generated cell in the persistent kernel (runtime/scan_cell.py): reference
+    outputs reproduced, the general per-step loop agrees, and far fewer launches."""
+    import os
+
+    from aesara_b200.runtime import lib
+    from oracle.program_np import run_program
+
+    prog, ins, want = load_case(name)
+    ex = rt(prog)
+    before = lib.load().ab_launch_count()
+    got = ex(*[np.array(a) for a in ins])
+    fast_launches = lib.load().ab_launch_count() - before
+    scan = [st["runner"] for st in ex._state if "runner" in st][0]
+    assert scan.used_fast_path and scan.fast_path_kind == "jit"
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert_matches(g, w, blas=True, what=f"{name} output {k} vs the reference")
+    os.environ["AB_SCAN_NO_FAST"] = "1"
+    try:
+        ex_gen = rt(prog)
+        before = lib.load().ab_launch_count()
+        general = ex_gen(*[np.array(a) for a in ins])
+        slow_launches = lib.load().ab_launch_count() - before
+    finally:
+        del os.environ["AB_SCAN_NO_FAST"]
+    assert not [st["runner"] for st in ex_gen._state if "runner" in st][0].used_fast_path
+    for k, (g, e) in enumerate(zip(got, general)):
+        assert_matches(g, e, blas=True, what=f"{name} output {k}: persistent kernel vs general loop")
+    assert fast_launches < slow_launches
+    # larger, ragged shapes against the oracle (second 2-CTA tile partly empty; 1-CTA kernel)
+    rng = np.random.default_rng(gates)
+    for T, B, H in ((9, 384, 128), (4, 200, 64)):
+        vals = [rng.standard_normal((T, B, gates * H)).astype("float32"),
+                (rng.standard_normal((B, H)) * 0.1).astype("float32"),
+                (rng.standard_normal((H, gates * H)) / np.sqrt(H)).astype("float32")]
+        o = run_program(prog, [np.array(a) for a in vals])
+        g = rt(prog)(*vals)
+        for k, (a, b) in enumerate(zip(g, o)):
+            assert_matches(a, b, blas=True, what=f"{name} at T={T}, B={B}, H={H} output {k} vs oracle")
+
+
+def test_lstm_generated_cell_equals_the_ahead_of_time_cell(rt):
+    """The LSTM through the generated-cell path (AB_SCAN_JIT) is BIT-identical to the
+    ahead-of-time kernel: same skeleton, the cell emitted from the inner graph's expressions."""
+    import os
+
+    prog, _, _ = load_case("cfg4_lstm")
+    rng = np.random.default_rng(8)
+    T, B, H = 7, 512, 128
+    ins = [rng.standard_normal((T, B, 4 * H)).astype("float32"), np.zeros((B, H), "float32"),
+           np.zeros((B, H), "float32"), (rng.standard_normal((H, 4 * H)) / np.sqrt(H)).astype("float32")]
+    ex = rt(prog)
+    aot = ex(*ins)
+    assert [st["runner"] for st in ex._state if "runner" in st][0].fast_path_kind == "lstm"
+    os.environ["AB_SCAN_JIT"] = "1"
+    try:
+        ex2 = rt(prog)
+        jit = ex2(*ins)
+    finally:
+        del os.environ["AB_SCAN_JIT"]
+    assert [st["runner"] for st in ex2._state if "runner" in st][0].fast_path_kind == "jit"
+    for a, b in zip(aot, jit):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_zz_launch_counts_are_recorded():
     """Writes the per-fixture launch counts next to the run (gpurun_out/) for the record."""
     import json

@@ -143,20 +143,24 @@ def _scan_runner(name):
     return ex._state[idx]["runner"]
 
 
-def test_lstm_fast_path_matcher_accepts_the_cfg4_inner_graph():
+def test_cell_matcher_accepts_the_cfg4_inner_graph_as_the_lstm_member():
     """The matcher traces the inner program with address-only stand-ins (no GPU needed)."""
     r = _scan_runner("cfg4_lstm")
-    assert r.lstm is not None
-    assert r.lstm.match(256, 128) is True
-    assert r.lstm.match(8192, 1024) is True
+    assert r.cell is not None
+    for B, H in ((256, 128), (8192, 1024)):
+        spec = r.cell.match(B, H, 4)
+        assert spec is not None and spec.is_lstm and (spec.gates, spec.states, spec.hs) == (4, 2, 0)
+    assert r.cell.match(256, 128, 3) is None      # U would not be [H, 4H]
 
 
-def test_lstm_fast_path_matcher_rejects_other_recurrences():
+def test_cell_matcher_family_and_rejections():
     import copy
 
-    assert _scan_runner("scan_cumsum_allsteps").lstm is None
-    assert _scan_runner("scan_two_taps_nitsot").lstm is None
-    # same structure but a different cell (tanh on the output gate replaced by sigmoid)
+    # no loop-invariant product: not the family
+    assert _scan_runner("scan_cumsum_allsteps").cell is None
+    assert _scan_runner("scan_two_taps_nitsot").cell is None
+    # the same structure with another cell (tanh on the output gate replaced by sigmoid) is still
+    # a member of the family, but no longer the ahead-of-time LSTM: it gets a generated cell
     r = _scan_runner("cfg4_lstm")
     inner = r.inner.program
     for n in inner.nodes:
@@ -165,7 +169,23 @@ def test_lstm_fast_path_matcher_rejects_other_recurrences():
             for s in n.params["expr"]["stmts"]:
                 if s["op"] == "tanh":
                     s["op"] = "sigmoid"
-    assert r.lstm.match(256, 128) is False
+    spec = r.cell.match(256, 128, 4)
+    assert spec is not None and not spec.is_lstm
+    assert "ab_cell_body" in spec.source() and "AB_CELL_GATES 4" in spec.source()
+    # tanh-RNN (1 gate, 1 state) and a gated unit (3 gates, 1 state), from the reference
+    for name, gates, states in (("scan_rnn_tanh_cell", 1, 1), ("scan_gated_unit_cell", 3, 1)):
+        r = _scan_runner(name)
+        assert r.cell is not None, name
+        spec = r.cell.match(256, 64, gates)
+        assert spec is not None and not spec.is_lstm and (spec.gates, spec.states, spec.hs) == (gates, states, 0)
+
+
+def test_generated_scan_cells_compile_for_sm100a():
+    """NVRTC (no GPU): the persistent Scan kernel with cells generated from inner graphs."""
+    for name, gates in (("scan_rnn_tanh_cell", 1), ("scan_gated_unit_cell", 3), ("cfg4_lstm", 4)):
+        spec = _scan_runner(name).cell.match(256, 64, gates)
+        assert spec is not None
+        spec.compile()
 
 
 # ---------------------------------------------------------------- executor-level regions
