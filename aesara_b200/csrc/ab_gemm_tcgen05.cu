@@ -324,7 +324,11 @@ bool use_two_cta(long long M, long long N) {
 // 4-CTA clusters (two CTA pairs stacked along M sharing the B tile by TMA multicast, see
 // gemm_2cta_body<KIND, 2>) for problems with at least two full cluster tiles of rows
 int cluster_pairs(long long M, long long N) {
-  const bool allow = getenv("AB_GEMM_NO_CLUSTER4") == nullptr;  // read per call: tests toggle it
+  // Off by default: measured on B200 (tools/gemm_probe.py, profiles/r02_gemm_probe.json) the
+  // 4-CTA multicast variant is 1-18 % SLOWER than plain CTA pairs on all three operand layouts
+  // of cfg3 (the smaller multicast boxes cost more than the saved L2 reads; the 2-CTA mainloop
+  // is not L2-bound after all).  AB_GEMM_CLUSTER4=1 enables it (kept, tested bit-exact).
+  const bool allow = getenv("AB_GEMM_CLUSTER4") != nullptr && getenv("AB_GEMM_NO_CLUSTER4") == nullptr;
   return (allow && use_two_cta(M, N) && M >= 1024 && (sm_count() % 4 == 0)) ? 2 : 1;
 }
 

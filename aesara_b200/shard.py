@@ -14,6 +14,7 @@ world_size-2 tests on CPU); ``OutputCombiner`` is the device path.
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Sequence, Tuple
 
@@ -435,11 +436,27 @@ class ChunkedHostExecutor:
         blocks = [row_block(rows, n, c) for c in range(n)]
         wall = DeviceArray.from_numpy(np.asarray([(b0 - a0) / float(rows) for a0, b0 in blocks] + [1.0], "float32"))
         one = wall.index((slice(n, n + 1),))
+        trace = [] if os.environ.get("AB_CHUNK_TRACE") else None
+        if trace is not None:
+            import time
+
+            import torch
+
+            t_origin = time.perf_counter()
+            e_origin = torch.cuda.Event(enable_timing=True)
+            e_origin.record()
         try:
             for c in range(n):
                 a0, b0 = blocks[c]
                 local = [a[a0:b0] if ax == 0 else a for a, ax in zip(args, axes)]
+                if trace is not None:
+                    t0 = time.perf_counter() - t_origin
                 outs = self.ex(*local)
+                if trace is not None:
+                    e_done = torch.cuda.Event(enable_timing=True)
+                    e_done.record()
+                    ups = [ev for ev, _ in self.ex._inflight]
+                    trace.append((c, t0, time.perf_counter() - t_origin, ups, e_done))
                 w = wall.index((slice(c, c + 1),))
                 for k, (o, m) in enumerate(zip(outs, modes)):
                     if m[0] in ("sum", "mean"):
@@ -468,6 +485,11 @@ class ChunkedHostExecutor:
                     elif acc[k] is None:
                         acc[k] = o
             self.chunks_run = n
+            if trace is not None:
+                torch.cuda.synchronize()
+                print("[chunk trace] block: host enters / host leaves the evaluation (ms) | device: compute done (ms)")
+                for c, t0, t1, ups, e_done in trace:
+                    print(f"  {c:2d}: {1e3 * t0:7.2f} / {1e3 * t1:7.2f} | {e_origin.elapsed_time(e_done):7.2f}")
         finally:
             self.ex.host_outputs = host_out
         if host_out:

@@ -64,8 +64,8 @@ def test_gemm_fp32_faithful(K, m, n, k, layout):
 @pytest.mark.parametrize("layout", ["nn", "tn", "nt", "tt"])
 @pytest.mark.parametrize("m,n,k", [(1024, 256, 192), (1500, 520, 1000), (4096, 1024, 512), (2300, 256, 4160)])
 def test_gemm_four_cta_cluster_multicast(K, m, n, k, layout, precision):
-    """M >= 1024 takes the 4-CTA cluster kernel (two CTA pairs sharing the B tile by TMA
-    multicast).  Its per-element arithmetic is the 2-CTA kernel's, so the result must be
+    """With AB_GEMM_CLUSTER4 set, M >= 1024 takes the 4-CTA cluster kernel (two CTA pairs sharing
+    the B tile by TMA multicast).  Its per-element arithmetic is the 2-CTA kernel's, so the result must be
     BIT-IDENTICAL to the 2-CTA path (AB_GEMM_NO_CLUSTER4) for every operand layout (K-major and
     MN-major B quarters), ragged cluster tiles (second pair partly or wholly out of range) and
     both the 3xTF32 and bf16 policies; and inside tolerance of a float64 product."""
@@ -80,14 +80,14 @@ def test_gemm_four_cta_cluster_multicast(K, m, n, k, layout, precision):
         A = _dev(np.ascontiguousarray(a.T)).dimshuffle([1, 0])
     if layout[1] == "t":
         B = _dev(np.ascontiguousarray(b.T)).dimshuffle([1, 0])
-    C4 = _dev(c0)
-    K.gemm(C4, 0.8, A, B, 0.4, precision=precision)
-    os.environ["AB_GEMM_NO_CLUSTER4"] = "1"
+    os.environ["AB_GEMM_CLUSTER4"] = "1"   # the variant is off by default (slower, see cluster_pairs)
     try:
-        C2 = _dev(c0)
-        K.gemm(C2, 0.8, A, B, 0.4, precision=precision)
+        C4 = _dev(c0)
+        K.gemm(C4, 0.8, A, B, 0.4, precision=precision)
     finally:
-        del os.environ["AB_GEMM_NO_CLUSTER4"]
+        del os.environ["AB_GEMM_CLUSTER4"]
+    C2 = _dev(c0)
+    K.gemm(C2, 0.8, A, B, 0.4, precision=precision)
     got = C4.to_numpy()
     np.testing.assert_array_equal(got, C2.to_numpy())
     want = 0.4 * c0.astype(np.float64) + 0.8 * (a.astype(np.float64) @ b.astype(np.float64))

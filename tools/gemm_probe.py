@@ -31,10 +31,10 @@ res = {}
 for name, (A, Bm, oshape) in shapes.items():
     C = DeviceArray.empty(oshape, "float32")
     for variant in ("cluster4", "2cta"):
-        if variant == "2cta":
-            os.environ["AB_GEMM_NO_CLUSTER4"] = "1"
+        if variant == "cluster4":
+            os.environ["AB_GEMM_CLUSTER4"] = "1"
         else:
-            os.environ.pop("AB_GEMM_NO_CLUSTER4", None)
+            os.environ.pop("AB_GEMM_CLUSTER4", None)
         cache = K.PackCache()
         for _ in range(3):
             K.gemm(C, 1.0, A, Bm, 0.0, precision=2, cache=cache)

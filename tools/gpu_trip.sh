@@ -35,6 +35,10 @@ case $sec in
     timeout 600 python tools/gemm_probe.py 30 2>&1 | tail -9;;
   gemm_ncu)
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 6 -c 2 -o gpurun_out/gemm_prof -f python tools/gemm_probe.py 2 > gpurun_out/gemm_ncu.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/gemm_ncu.log | cut -c1-300; ls -la gpurun_out/gemm_prof.ncu-rep;;
+  scantests)
+    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -q -p no:cacheprovider -k "lstm or scan or cfg4" > gpurun_out/pytest_scan.log 2>&1; echo "scantests rc=$?"; tail -6 gpurun_out/pytest_scan.log | cut -c1-300;;
+  bench_lstm)
+    timeout 600 python bench.py --workload lstm --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_lstm.json 2> gpurun_out/bench_lstm.err; echo "bench_lstm rc=$?"; tail -2 gpurun_out/bench_lstm.err; python -c "import json;d=json.load(open('gpurun_out/bench_lstm.json'));print(d['ms_per_step'], d['roofline'])";;
   reference)
     timeout 500 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"; tail -2 gpurun_out/bench_reference.err; cut -c1-1200 gpurun_out/bench_reference.json;;
   smoke)
