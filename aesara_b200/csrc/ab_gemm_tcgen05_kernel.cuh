@@ -434,7 +434,7 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a0)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b0)) : "memory");
       int stage = 0;
@@ -462,7 +462,7 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t sit = 0;  // accumulator segments issued by this CTA
@@ -681,7 +681,7 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
 
   if (warp == 0) {
     // ================= TMA producer (one per CTA) =================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
@@ -708,7 +708,7 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t sit = 0;

@@ -134,7 +134,7 @@ __device__ __forceinline__ void cell_scan_body(const CUtensorMap& map_h00, const
     int stage = 0;
     uint32_t phase = 0;
     uint32_t it = 0;
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
       // ================= TMA producer (one per CTA) =================
       for (long long t = 0; t < p.T; ++t) {
         const int set = (int)(t & 1);  // planes read this step; the other set is written
@@ -181,7 +181,7 @@ __device__ __forceinline__ void cell_scan_body(const CUtensorMap& map_h00, const
         }
         }
       }
-    } else if (warp == 1 && leader && lane == 0) {
+    } else if (warp == 1 && leader && elect_one()) {
       // ================= MMA issuer (the leader CTA of a pair) =================
       for (long long t = 0; t < p.T; ++t) {
         for (long long tile = group_id; tile < num_tiles; tile += n_groups) {

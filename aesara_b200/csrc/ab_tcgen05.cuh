@@ -28,6 +28,18 @@ constexpr int kMaxSmem = 200 * 1024;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// one lane of the (converged) warp; code under `if (elect_one())` keeps warp-uniform values in
+// uniform registers, which tcgen05.mma / cp.async.bulk.tensor take their operands from — under
+// `if (lane == 0)` the compiler moves every descriptor through an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY loop (measured: ~120 SASS instructions per k-block on the MMA-issuing thread, the
+// tensor pipe 74 % active with the issue thread never waiting for data)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

@@ -73,3 +73,12 @@ for chunks in (0, 8):
         os.environ["AB_CHUNK_TRACE"] = "1"
         f(*args)
         del os.environ["AB_CHUNK_TRACE"]
+        import cProfile
+        import pstats
+
+        pr = cProfile.Profile()
+        pr.enable()
+        f(*args)
+        pr.disable()
+        torch.cuda.synchronize()
+        pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
