@@ -192,6 +192,27 @@ int make_map(CUtensorMap* map, const void* base, bool bf16, long long inner, lon
   return AB_OK;
 }
 
+// MN-major plane [k rows, pitch] as a 3-D tensor {128 B of MN, k, MN chunks}: box = {128 B, box_k
+// rows, chunks} lands as `chunks` consecutive [box_k x 128 B] blocks in shared memory — the
+// canonical MN-major SWIZZLE_128B tile — with one bulk copy.  Needs mn % (128 B of elements) == 0.
+int make_map_mn3d(CUtensorMap* map, const void* base, bool bf16, long long mn, long long k,
+                  long long pitch_elems, int box_k, int chunks) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(AB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const int es = bf16 ? 2 : 4;
+  const long long per = SW_BYTES / es;
+  cuuint64_t dims[3] = {(cuuint64_t)per, (cuuint64_t)k, (cuuint64_t)(mn / per)};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch_elems * es, (cuuint64_t)SW_BYTES};
+  cuuint32_t box[3] = {(cuuint32_t)per, (cuuint32_t)box_k, (cuuint32_t)chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AB_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with code %d", (int)r);
+  return AB_OK;
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 bool eligible(long long M, long long N, long long K) {
@@ -571,11 +592,16 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   }
   CUtensorMap ma[2], mb[2];
   int rc;
+  const bool allow_3d = getenv("AB_GEMM_NO_MN3D") == nullptr;  // read per call: tests toggle it
+  p.a_mn3d = (allow_3d && A.mn_major && M % p.mn_per_chunk == 0 && p.a_chunks > 1) ? 1 : 0;
+  p.b_mn3d = (allow_3d && B.mn_major && N % p.mn_per_chunk == 0 && p.b_chunks > 1 && pairs == 1) ? 1 : 0;
   for (int i = 0; i < parts; ++i) {
-    if (A.mn_major) rc = make_map(&ma[i], A.plane[i], bf16, M, K, A.pitch, p.k_elems_per_row);
+    if (p.a_mn3d) rc = make_map_mn3d(&ma[i], A.plane[i], bf16, M, K, A.pitch, p.k_elems_per_row, p.a_chunks);
+    else if (A.mn_major) rc = make_map(&ma[i], A.plane[i], bf16, M, K, A.pitch, p.k_elems_per_row);
     else rc = make_map(&ma[i], A.plane[i], bf16, K, M, A.pitch, BLOCK_M);
     if (rc) return rc;
-    if (B.mn_major) rc = make_map(&mb[i], B.plane[i], bf16, N, K, B.pitch, p.k_elems_per_row);
+    if (p.b_mn3d) rc = make_map_mn3d(&mb[i], B.plane[i], bf16, N, K, B.pitch, p.k_elems_per_row, p.b_chunks);
+    else if (B.mn_major) rc = make_map(&mb[i], B.plane[i], bf16, N, K, B.pitch, p.k_elems_per_row);
     else rc = make_map(&mb[i], B.plane[i], bf16, K, N, B.pitch,
                        two_cta ? (pairs == 2 ? p.block_n / 4 : p.block_n / 2) : p.block_n);
     if (rc) return rc;

@@ -25,6 +25,10 @@ struct GemmParams {
   int k_elems_per_row;    // K elements per stage = per 128-byte K-major row: 32 (tf32) / 64 (bf16)
   int a_tile_bytes, b_tile_bytes;
   int a_mn, b_mn;         // operand is MN-major
+  int a_mn3d, b_mn3d;     // ... and its tensor map is 3-D {128 B of MN, K rows, MN chunks}: the
+                          // whole tile arrives with ONE bulk copy instead of one per chunk
+                          // (measured: every extra cp.async.bulk.tensor per k-block costs the
+                          // 2-CTA mainloop ~0.1 ms of a 2.2 TFLOP product)
   int a_chunks, b_chunks; // MN-major: 128-byte MN chunks per tile (tile_rows * elem_size / 128)
   int chunk_bytes;        // MN-major: k_elems_per_row rows * 128 B
   int mn_per_chunk;       // MN-major: elements per chunk (128 / elem_size)
@@ -57,9 +61,11 @@ struct GemmParams {
 // MN-major: one box {128 B of MN, BLOCK_K rows} per chunk.
 __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
                                           int kc, int mn0, int mn_major, int chunks,
-                                          const GemmParams& p) {
+                                          const GemmParams& p, int mn3d = 0) {
   if (!mn_major) {
     tma_load_2d(dst, map, bar, kc, mn0);
+  } else if (mn3d) {
+    tma_load_3d(dst, map, bar, 0, kc, mn0 / p.mn_per_chunk);
   } else {
     for (int c = 0; c < chunks; ++c)
       tma_load_2d(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
@@ -448,13 +454,13 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
           uint8_t* sbase = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           const int kc = kb * p.k_elems_per_row;
-          load_tile(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
+          load_tile(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p, p.a_mn3d);
           load_tile(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0, p.b_mn,
-                    p.b_chunks, p);
+                    p.b_chunks, p, p.b_mn3d);
           if (p.nparts == 2) {
-            load_tile(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
+            load_tile(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p, p.a_mn3d);
             load_tile(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc, n0,
-                      p.b_mn, p.b_chunks, p);
+                      p.b_mn, p.b_chunks, p, p.b_mn3d);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -584,9 +590,11 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
 //   * all 256 epilogue threads arrive on the leader's tmem_empty barrier.
 __device__ __forceinline__ void load_tile_2sm(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
                                               int kc, int mn0, int mn_major, int chunks,
-                                              const GemmParams& p) {
+                                              const GemmParams& p, int mn3d = 0) {
   if (!mn_major) {
     tma_load_2d_2sm(dst, map, bar, kc, mn0);
+  } else if (mn3d) {
+    tma_load_3d_2sm(dst, map, bar, 0, kc, mn0 / p.mn_per_chunk);
   } else {
     for (int c = 0; c < chunks; ++c)
       tma_load_2d_2sm(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
@@ -611,7 +619,7 @@ template <int PAIRS>
 __device__ __forceinline__ void load_b_2sm(uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int kc,
                                            int n0, uint32_t pair, uint16_t mask, const GemmParams& p) {
   if (PAIRS == 1) {
-    load_tile_2sm(dst, map, bar, kc, n0, p.b_mn, p.b_chunks, p);
+    load_tile_2sm(dst, map, bar, kc, n0, p.b_mn, p.b_chunks, p, p.b_mn3d);
   } else if (!p.b_mn) {
     // K-major: box {128 B of K, block_n / 4 rows}; this CTA's quarter lands behind the twin's
     tma_load_2d_2sm_mc(dst + pair * (p.b_tile_bytes / 2), map, bar, kc, n0 + (int)pair * (p.block_n / 4), mask);
@@ -693,12 +701,12 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
           uint8_t* sbase = smem + (size_t)stage * stage_bytes;
           if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
           const int kc = kb * p.k_elems_per_row;
-          load_tile_2sm(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p);
+          load_tile_2sm(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p, p.a_mn3d);
           load_b_2sm<PAIRS>(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0, pair,
                             twin_mask, p);
           if (p.nparts == 2) {
             load_tile_2sm(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn,
-                          p.a_chunks, p);
+                          p.a_chunks, p, p.a_mn3d);
             load_b_2sm<PAIRS>(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc,
                               n0, pair, twin_mask, p);
           }

@@ -94,6 +94,38 @@ def test_gemm_four_cta_cluster_multicast(K, m, n, k, layout, precision):
     assert _normwise(got, want) < (1e-5 if precision == 0 else 2e-2)
 
 
+@pytest.mark.parametrize("layout", ["tn", "nt", "tt"])
+@pytest.mark.parametrize("m,n,k", [(512, 768, 640), (1024, 256, 200), (320, 576, 4160), (300, 520, 512)])
+def test_gemm_mn_major_tiles_as_one_bulk_copy(K, m, n, k, layout):
+    """bf16 MN-major operands (a matrix used transposed) arrive through a 3-D tensor map, one
+    cp.async.bulk.tensor per tile, when the MN extent is a multiple of 64; bit-identical to the
+    one-copy-per-chunk path (AB_GEMM_NO_MN3D), ragged extents keep that path."""
+    import os
+
+    rng = np.random.default_rng(m + n + k)
+    a = rng.standard_normal((m, k)).astype("float32")
+    b = rng.standard_normal((k, n)).astype("float32")
+    A, B = _dev(a), _dev(b)
+    if layout[0] == "t":
+        A = _dev(np.ascontiguousarray(a.T)).dimshuffle([1, 0])
+    if layout[1] == "n":
+        pass  # B [k, n] row-major is MN-major as it stands
+    else:
+        B = _dev(np.ascontiguousarray(b.T)).dimshuffle([1, 0])
+    C3 = _dev(np.zeros((m, n), "float32"))
+    K.gemm(C3, 1.0, A, B, 0.0, precision=2)
+    os.environ["AB_GEMM_NO_MN3D"] = "1"
+    try:
+        C2 = _dev(np.zeros((m, n), "float32"))
+        K.gemm(C2, 1.0, A, B, 0.0, precision=2)
+    finally:
+        del os.environ["AB_GEMM_NO_MN3D"]
+    got = C3.to_numpy()
+    np.testing.assert_array_equal(got, C2.to_numpy())
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    assert _normwise(got, want) < 2e-2
+
+
 @pytest.mark.parametrize("m,n,k", [(256, 256, 4096), (512, 256, 16384), (256, 512, 65536)])
 @pytest.mark.parametrize("layout", ["nn", "tn"])
 def test_gemm_long_k_accuracy(K, m, n, k, layout):
