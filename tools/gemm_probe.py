@@ -28,41 +28,61 @@ shapes = {
     "dW   X.T[H,B] @ D[B,H]    (A MN-major, B MN-major, K=65536)": (dX.dimshuffle([1, 0]), dD, (H, H)),
 }
 res = {}
-for name, (A, Bm, oshape) in shapes.items():
-    C = DeviceArray.empty(oshape, "float32")
-    for variant in ("cluster4", "2cta"):
-        if variant == "cluster4":
-            os.environ["AB_GEMM_CLUSTER4"] = "1"
-        else:
-            os.environ.pop("AB_GEMM_CLUSTER4", None)
-        cache = K.PackCache()
-        for _ in range(3):
-            K.gemm(C, 1.0, A, Bm, 0.0, precision=2, cache=cache)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            K.gemm(C, 1.0, A, Bm, 0.0, precision=2, cache=cache)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
-        tf = 2.0 * B * H * H / ms / 1e9
-        res[f"{name} | {variant}"] = {"ms": ms, "tflops": tf}
-        print(f"{name:70s} {variant:9s} {ms:7.3f} ms  {tf:7.1f} TF/s", flush=True)
-# cuBLAS through torch as the yardstick of the box at this moment (checker only)
-a = X.bfloat16()
-w = W.bfloat16()
-for _ in range(3):
-    torch.matmul(a, w)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(iters):
-    torch.matmul(a, w)
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / iters
-print(f"{'cuBLAS bf16 (torch.matmul) same fwd shape, bf16 out':70s} {'':9s} {ms:7.3f} ms  {2.0*B*H*H/ms/1e9:7.1f} TF/s")
+VARIANTS = {
+    "2cta": {},
+    "2cta, one copy per MN chunk": {"AB_GEMM_NO_MN3D": "1"},
+    "cluster4": {"AB_GEMM_CLUSTER4": "1"},
+}
+KNOBS = ("AB_GEMM_NO_MN3D", "AB_GEMM_CLUSTER4")
+
+
+def cublas_ms():
+    a = X.bfloat16()
+    w = W.bfloat16()
+    for _ in range(3):
+        torch.matmul(a, w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(a, w)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+print(f"cuBLAS bf16 (torch.matmul) fwd shape at the start: {cublas_ms():.3f} ms", flush=True)
+# variants interleaved, three rounds, best of each: box-to-box and minute-to-minute drift of
+# this power-capped part is larger (10-15 %) than the differences being measured
+best = {}
+for rnd in range(3):
+    for name, (A, Bm, oshape) in shapes.items():
+        C = DeviceArray.empty(oshape, "float32")
+        for variant, env in VARIANTS.items():
+            for k in KNOBS:
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            cache = K.PackCache()
+            for _ in range(2):
+                K.gemm(C, 1.0, A, Bm, 0.0, precision=2, cache=cache)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                K.gemm(C, 1.0, A, Bm, 0.0, precision=2, cache=cache)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            key = f"{name} | {variant}"
+            best[key] = min(best.get(key, 1e9), ms)
+for k in KNOBS:
+    os.environ.pop(k, None)
+for key, ms in best.items():
+    tf = 2.0 * B * H * H / ms / 1e9
+    res[key] = {"ms": ms, "tflops": tf}
+    print(f"{key:100s} {ms:7.3f} ms  {tf:7.1f} TF/s", flush=True)
+ms = cublas_ms()
+print(f"cuBLAS bf16 (torch.matmul) fwd shape at the end:   {ms:.3f} ms  {2.0*B*H*H/ms/1e9:7.1f} TF/s")
 res["cublas_fwd"] = {"ms": ms, "tflops": 2.0 * B * H * H / ms / 1e9}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "gemm_probe.json"), "w"), indent=1)

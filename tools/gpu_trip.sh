@@ -30,9 +30,9 @@ case $sec in
   e2e)
     timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu > gpurun_out/bench_e2e.json 2> gpurun_out/bench_e2e.err; echo "bench_e2e rc=$?"; tail -3 gpurun_out/bench_e2e.err; python -c "import json;d=json.load(open('gpurun_out/bench_e2e.json'));print(d['ms_per_step'], d['e2e'], d.get('parity'))";;
   e2e_probe)
-    timeout 600 python tools/e2e_probe.py 2>&1 | grep -v Warn | tail -12;;
+    timeout 600 python tools/e2e_probe.py > gpurun_out/e2e_probe.log 2>&1; grep -a "host_chunks\|GB/s" gpurun_out/e2e_probe.log | tail -8;;
   gemm_probe)
-    timeout 600 python tools/gemm_probe.py 30 2>&1 | tail -9;;
+    timeout 600 python tools/gemm_probe.py 20 > gpurun_out/gemm_probe.log 2>&1; tail -16 gpurun_out/gemm_probe.log;;
   gemm_ncu)
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 6 -c 2 -o gpurun_out/gemm_prof -f python tools/gemm_probe.py 2 > gpurun_out/gemm_ncu.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/gemm_ncu.log | cut -c1-300; ls -la gpurun_out/gemm_prof.ncu-rep;;
   scantests)
