@@ -434,6 +434,22 @@ class ChunkedHostExecutor:
         # before anything is queued: a pageable-memory copy is synchronous, and issued between
         # blocks it would wait for the previous block's kernels — no overlap at all
         blocks = [row_block(rows, n, c) for c in range(n)]
+        # replicated host tensors (weights) cross the bus ONCE, not once per block
+        import torch
+
+        cur = torch.cuda.current_stream()
+        args = list(args)
+        keep_alive = []
+        for k, (a, ax) in enumerate(zip(args, axes)):
+            if ax is None and isinstance(a, np.ndarray) and a.size > 64:
+                for ev, _ in self.ex._inflight:     # sources of the previous call's uploads
+                    ev.synchronize()
+                self.ex._inflight = []
+                d, tok = DeviceArray.upload(a, self.ex._copy_stream_for(cur), cur)
+                if tok is not None:
+                    cur.wait_event(tok[0])
+                    keep_alive.append(tok)
+                args[k] = d
         wall = DeviceArray.from_numpy(np.asarray([(b0 - a0) / float(rows) for a0, b0 in blocks] + [1.0], "float32"))
         one = wall.index((slice(n, n + 1),))
         trace = [] if os.environ.get("AB_CHUNK_TRACE") else None
@@ -485,6 +501,8 @@ class ChunkedHostExecutor:
                     elif acc[k] is None:
                         acc[k] = o
             self.chunks_run = n
+            for ev, _ in keep_alive:  # the page-locked sources stay alive until the copies ran
+                ev.synchronize()
             if trace is not None:
                 torch.cuda.synchronize()
                 print("[chunk trace] block: host enters / host leaves the evaluation (ms) | device: compute done (ms)")
