@@ -592,7 +592,9 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   }
   CUtensorMap ma[2], mb[2];
   int rc;
-  const bool allow_3d = getenv("AB_GEMM_NO_MN3D") == nullptr;  // read per call: tests toggle it
+  // Off by default: measured neutral for a B operand and 20 % slower for an MN-major A with a
+  // long K (profiles/r02_gemm_probe_variants.json); AB_GEMM_MN3D=1 enables it (kept, tested).
+  const bool allow_3d = getenv("AB_GEMM_MN3D") != nullptr && getenv("AB_GEMM_NO_MN3D") == nullptr;
   p.a_mn3d = (allow_3d && A.mn_major && M % p.mn_per_chunk == 0 && p.a_chunks > 1) ? 1 : 0;
   p.b_mn3d = (allow_3d && B.mn_major && N % p.mn_per_chunk == 0 && p.b_chunks > 1 && pairs == 1) ? 1 : 0;
   for (int i = 0; i < parts; ++i) {

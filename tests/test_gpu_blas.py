@@ -97,9 +97,9 @@ def test_gemm_four_cta_cluster_multicast(K, m, n, k, layout, precision):
 @pytest.mark.parametrize("layout", ["tn", "nt", "tt"])
 @pytest.mark.parametrize("m,n,k", [(512, 768, 640), (1024, 256, 200), (320, 576, 4160), (300, 520, 512)])
 def test_gemm_mn_major_tiles_as_one_bulk_copy(K, m, n, k, layout):
-    """bf16 MN-major operands (a matrix used transposed) arrive through a 3-D tensor map, one
-    cp.async.bulk.tensor per tile, when the MN extent is a multiple of 64; bit-identical to the
-    one-copy-per-chunk path (AB_GEMM_NO_MN3D), ragged extents keep that path."""
+    """With AB_GEMM_MN3D set, bf16 MN-major operands (a matrix used transposed) arrive through a
+    3-D tensor map, one cp.async.bulk.tensor per tile, when the MN extent is a multiple of 64;
+    bit-identical to the default one-copy-per-chunk path, ragged extents keep that path."""
     import os
 
     rng = np.random.default_rng(m + n + k)
@@ -112,14 +112,14 @@ def test_gemm_mn_major_tiles_as_one_bulk_copy(K, m, n, k, layout):
         pass  # B [k, n] row-major is MN-major as it stands
     else:
         B = _dev(np.ascontiguousarray(b.T)).dimshuffle([1, 0])
-    C3 = _dev(np.zeros((m, n), "float32"))
-    K.gemm(C3, 1.0, A, B, 0.0, precision=2)
-    os.environ["AB_GEMM_NO_MN3D"] = "1"
+    os.environ["AB_GEMM_MN3D"] = "1"   # off by default (measured slower for MN-major A operands)
     try:
-        C2 = _dev(np.zeros((m, n), "float32"))
-        K.gemm(C2, 1.0, A, B, 0.0, precision=2)
+        C3 = _dev(np.zeros((m, n), "float32"))
+        K.gemm(C3, 1.0, A, B, 0.0, precision=2)
     finally:
-        del os.environ["AB_GEMM_NO_MN3D"]
+        del os.environ["AB_GEMM_MN3D"]
+    C2 = _dev(np.zeros((m, n), "float32"))
+    K.gemm(C2, 1.0, A, B, 0.0, precision=2)
     got = C3.to_numpy()
     np.testing.assert_array_equal(got, C2.to_numpy())
     want = a.astype(np.float64) @ b.astype(np.float64)

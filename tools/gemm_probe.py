@@ -30,10 +30,10 @@ shapes = {
 res = {}
 VARIANTS = {
     "2cta": {},
-    "2cta, one copy per MN chunk": {"AB_GEMM_NO_MN3D": "1"},
+    "2cta, MN-major tiles by one 3-D copy": {"AB_GEMM_MN3D": "1"},
     "cluster4": {"AB_GEMM_CLUSTER4": "1"},
 }
-KNOBS = ("AB_GEMM_NO_MN3D", "AB_GEMM_CLUSTER4")
+KNOBS = ("AB_GEMM_MN3D", "AB_GEMM_CLUSTER4")
 
 
 def cublas_ms():
