@@ -468,7 +468,7 @@ int fused_kernel(Module* m, const char* name, cudaKernel_t* out) {
     cudaGetLastError();
     return fail(AB_ERR_INVALID, "fused GEMM module has no kernel %s", name);
   }
-  cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemGemm);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return fail(AB_ERR_CUDA, "cannot raise the dynamic shared memory limit of %s: %s", name, cudaGetErrorString(e));
@@ -528,7 +528,9 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   const int pairs = two_cta ? cluster_pairs(M, N) : 1;
   const int tile_m = two_cta ? 2 * BLOCK_M : BLOCK_M;
   const int stage_bytes = parts * (p.a_tile_bytes + p.b_tile_bytes);
-  p.stages = std::max(2, std::min(8, (kMaxSmem - 1024) / stage_bytes));
+  p.stages = std::max(2, std::min(8, (kMaxSmemGemm - 1024) / stage_bytes));
+  if (const char* st_env = getenv("AB_GEMM_STAGES"))  // probing knob (tools/gemm_probe.py)
+    p.stages = std::max(2, std::min(p.stages, atoi(st_env)));
   p.acc_stages = 2;  // 2 x block_n <= 512 TMEM columns
   {
     // K segments (see "segments" above): 4 k-blocks = 128 K elements for the fp32-faithful
@@ -620,15 +622,15 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     if (!res) {
       if (pairs == 2) {
         if (bf16) {
-          AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+          AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemGemm));
           res = max_clusters(gemm_tcgen05_2cta_kernel<1, 2>, ctas, smem);
         } else {
-          AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+          AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemGemm));
           res = max_clusters(gemm_tcgen05_2cta_kernel<0, 2>, ctas, smem);
         }
       } else {
-        if (bf16) AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        else AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        if (bf16) AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemGemm));
+        else AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemGemm));
         res = sm_count() / 2;
       }
       if (pairs == 2) g_cluster4_resident = res;
@@ -679,14 +681,14 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   if (bf16) {
     static bool attr1 = false;
     if (!attr1) {
-      AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemGemm));
       attr1 = true;
     }
     gemm_tcgen05_kernel<1><<<grid, kThreads, smem, st>>>(ma[0], ma[1], mb[0], mb[1], p);
   } else {
     static bool attr0 = false;
     if (!attr0) {
-      AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      AB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemGemm));
       attr0 = true;
     }
     gemm_tcgen05_kernel<0><<<grid, kThreads, smem, st>>>(ma[0], ma[1], mb[0], mb[1], p);

@@ -22,7 +22,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int SW_BYTES = 128;  // swizzle span = smem row pitch of every operand tile
 constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
-constexpr int kMaxSmem = 200 * 1024;
+constexpr int kMaxSmem = 200 * 1024;       // dynamic shared memory the Scan kernels ask for
+constexpr int kMaxSmemGemm = 226 * 1024;   // GEMM: 7 stages of 32 KB (227 KB is the per-block limit)
 
 // ----------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -32,8 +32,10 @@ VARIANTS = {
     "2cta": {},
     "2cta, MN-major tiles by one 3-D copy": {"AB_GEMM_MN3D": "1"},
     "cluster4": {"AB_GEMM_CLUSTER4": "1"},
+    "2cta, 6 stages": {"AB_GEMM_STAGES": "6"},
+    "2cta, 4 stages": {"AB_GEMM_STAGES": "4"},
 }
-KNOBS = ("AB_GEMM_MN3D", "AB_GEMM_CLUSTER4")
+KNOBS = ("AB_GEMM_MN3D", "AB_GEMM_CLUSTER4", "AB_GEMM_STAGES")
 
 
 def cublas_ms():

@@ -41,6 +41,14 @@ case $sec in
     timeout 600 python bench.py --workload lstm --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_lstm.json 2> gpurun_out/bench_lstm.err; echo "bench_lstm rc=$?"; tail -2 gpurun_out/bench_lstm.err; python -c "import json;d=json.load(open('gpurun_out/bench_lstm.json'));print(d['ms_per_step'], d['roofline'])";;
   bench_ncu)
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ab_gemm_ep|gemm_tcgen05" -s 8 -c 5 -o gpurun_out/bench_prof -f python bench.py --steps 1 --warmup 1 --no-also --no-cpu --no-e2e --no-truth --graph 0 > gpurun_out/bench_ncu.log 2>&1; echo "bench_ncu rc=$?"; tail -2 gpurun_out/bench_ncu.log | cut -c1-200; ls -la gpurun_out/bench_prof.ncu-rep;;
+  multitest)
+    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -p no:cacheprovider -x > gpurun_out/pytest_multi.log 2>&1; echo "multitest rc=$?"; tail -6 gpurun_out/pytest_multi.log | cut -c1-300;;
+  scale_mlp)
+    N=$(nvidia-smi -L | wc -l)
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_mlp_n$N.json 2> gpurun_out/bench_mlp_n$N.err; echo "scale_mlp N=$N rc=$?"; tail -3 gpurun_out/bench_mlp_n$N.err | cut -c1-300; python -c "import json;d=json.load(open('gpurun_out/bench_mlp_n$N.json'));print(d['n_gpus'], d['value'], d['ms_per_step'], d.get('parity_sharded'), d.get('exchange'))";;
+  scale_logreg)
+    N=$(nvidia-smi -L | wc -l)
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --workload logreg --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_logreg_n$N.json 2> gpurun_out/bench_logreg_n$N.err; echo "scale_logreg N=$N rc=$?"; tail -3 gpurun_out/bench_logreg_n$N.err | cut -c1-300; python -c "import json;d=json.load(open('gpurun_out/bench_logreg_n$N.json'));print(d['n_gpus'], d['value'], d['ms_per_step'], d.get('parity_sharded'), d.get('exchange'))";;
   reference)
     timeout 500 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"; tail -2 gpurun_out/bench_reference.err; cut -c1-1200 gpurun_out/bench_reference.json;;
   smoke)
