@@ -533,6 +533,10 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     p.stages = std::max(2, std::min(p.stages, atoi(st_env)));
   p.acc_stages = 2;  // 2 x block_n <= 512 TMEM columns
   {
+    const char* gm_env = getenv("AB_GEMM_GROUP_M");  // probing knob; 1 = rows-then-columns order
+    p.group_m = gm_env ? std::max(1, atoi(gm_env)) : 8;
+  }
+  {
     // K segments (see "segments" above): 4 k-blocks = 128 K elements for the fp32-faithful
     // mode; AB_GEMM_SEG_KB overrides (0 = never fold, the whole K loop stays in TMEM)
     static const char* seg_env = getenv("AB_GEMM_SEG_KB");

@@ -17,7 +17,8 @@ struct GemmParams {
   int acc_stages;         // TMEM accumulator stages (2 -> epilogue overlaps the next segment)
   int seg_kblocks;        // k-blocks accumulated inside the tensor core before the epilogue
                           // folds the partial sum into its FP32 registers (see "segments")
-  int k_splits;           // split-K: work unit = (tile, K range); unit u -> tile u / k_splits
+  int group_m;            // tile rows per group of the grouped unit order (AB_UNIT_DECODE)
+  int k_splits;           // split-K: work unit = (K range, tile)
   int kb_per_split;       // k-blocks per K range
   float* partial;         // [k_splits - 1][M][N] alpha * (A@B over K range s), s >= 1
   int stages;
@@ -259,6 +260,30 @@ struct EpilogueOut {
   __device__ __forceinline__ void fused_chunk(float (&x)[32], long long row, long long col0, bool live,
                                               int lane, const FusedScalars& sc, double& fs) const {
     const long long r = live ? row : 0;
+    // Matrix-shaped reads of the whole chunk are issued up front: the loads of all four column
+    // groups are in flight together (one DRAM latency per chunk).  Loaded group by group right
+    // before their use, an epilogue that reads a [M, N] operand (the Gemm's z, or h in
+    // g * (1 - h^2)) is latency-bound: 16 dependent round trips per tile, tensor pipe 52-66 %
+    // active against 71-74 % without such a read (profiles/r02_bench_step_ncu.txt).
+#if AB_EP_CIN
+    float cin_pre[32];
+    if (live && p.beta != 0.0f) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        if (col0 + j < p.N) ld8(p.Cin + r * p.cin_rs + col0 + j, *reinterpret_cast<float(*)[8]>(&cin_pre[j]), wide_in);
+    }
+#endif
+#if AB_EP_PRE_OP >= 0
+    float op_pre[32];
+    const bool pre_ok = live && !sc.is[AB_EP_PRE_OP] && p.ep_cs[AB_EP_PRE_OP] == 1;
+    if (pre_ok) {
+      const bool wide = ((reinterpret_cast<uintptr_t>(p.ep_ptr[AB_EP_PRE_OP]) & 31) == 0) && ((p.ep_rs[AB_EP_PRE_OP] & 7) == 0);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        if (col0 + j < p.N)
+          ld8(p.ep_ptr[AB_EP_PRE_OP] + r * p.ep_rs[AB_EP_PRE_OP] + col0 + j, *reinterpret_cast<float(*)[8]>(&op_pre[j]), wide);
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       const long long col = col0 + j;
@@ -267,14 +292,26 @@ struct EpilogueOut {
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[t] = p.alpha * x[j + t];
         if (p.beta != 0.0f) {
+#if AB_EP_CIN
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] += p.beta * cin_pre[j + t];
+#else
           float ci[8];
           ld8(p.Cin + r * p.cin_rs + col, ci, wide_in);
 #pragma unroll
           for (int t = 0; t < 8; ++t) v[t] += p.beta * ci[t];
+#endif
         }
         float e[4][8];
 #pragma unroll
         for (int k = 0; k < AB_EP_NOPS; ++k) {
+#if AB_EP_PRE_OP >= 0
+          if (k == AB_EP_PRE_OP && pre_ok) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) e[k][t] = op_pre[j + t];
+            continue;
+          }
+#endif
           if (sc.is[k]) {
 #pragma unroll
             for (int t = 0; t < 8; ++t) e[k][t] = sc.v[k];
@@ -381,12 +418,25 @@ struct EpilogueOut {
 };
 
 // work unit -> (tile, K range); consecutive units of a tile go to different CTAs
+// Work unit -> (K range, tile).  Units are K-range major and, inside a K range, follow a grouped
+// order (groups of p.group_m tile rows, columns outer, rows inner): the ~74 units in flight
+// then form a compact block of the tile grid over ONE K range, so they share ~8 A panels and
+// ~9 B panels in L2.  With rows-then-columns order the cfg3 weight-gradient products
+// (4096 x 4096 x 65536) re-read their B operand for every tile row: 5.5-5.9 GB of DRAM reads
+// per launch against 1 GB of operands (profiles/r02_bench_step_ncu.txt).
 #define AB_UNIT_DECODE                                                          \
-  const long long tile = unit / p.k_splits;                                     \
-  const int split = (int)(unit - tile * p.k_splits);                            \
+  const int split = (int)(unit / num_tiles);                                    \
+  const long long tile_lin = unit - (long long)split * num_tiles;               \
+  const long long tiles_m_ = num_tiles / tiles_n;                               \
+  const long long gsz_ = (long long)p.group_m * tiles_n;                        \
+  const long long first_m_ = (tile_lin / gsz_) * p.group_m;                     \
+  const long long gm_ = min((long long)p.group_m, tiles_m_ - first_m_);         \
+  const long long loc_ = tile_lin % gsz_;                                       \
+  const long long tile_m = first_m_ + loc_ % gm_;                               \
+  const long long tile_n = loc_ / gm_;                                          \
   const int kb_begin = split * p.kb_per_split;                                  \
   const int kb_end = min(kb_begin + p.kb_per_split, num_k_blocks);              \
-  (void)split;
+  (void)split; (void)tile_m; (void)tile_n;
 
 template <int KIND>
 __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1,
@@ -447,8 +497,8 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
       uint32_t phase = 0;
       for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         AB_UNIT_DECODE
-        const int m0 = (int)((tile / tiles_n) * BLOCK_M);
-        const int n0 = (int)((tile % tiles_n) * p.block_n);
+        const int m0 = (int)(tile_m * BLOCK_M);
+        const int n0 = (int)(tile_n * p.block_n);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sbase = smem + (size_t)stage * stage_bytes;
@@ -525,8 +575,8 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
     uint32_t sit = 0;
     for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         AB_UNIT_DECODE
-      const long long m0 = (tile / tiles_n) * BLOCK_M;
-      const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
+      const long long m0 = tile_m * BLOCK_M;
+      const long long n0 = tile_n * p.block_n + half * half_n;
 #ifdef AB_EPILOGUE
       if (KIND == 1 || kb_end - kb_begin <= p.seg_kblocks) {  // bf16 products are never segmented
         // one segment: the epilogue reads TMEM chunk by chunk, then frees the stage
@@ -694,8 +744,8 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
       uint32_t phase = 0;
       for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
         AB_UNIT_DECODE
-        const int m0 = (int)((tile / tiles_n) * CLUSTER_M) + (int)pair * TILE_M + (int)rank * BLOCK_M;
-        const int n0 = (int)((tile % tiles_n) * p.block_n) + (int)rank * (p.block_n / 2);
+        const int m0 = (int)(tile_m * CLUSTER_M) + (int)pair * TILE_M + (int)rank * BLOCK_M;
+        const int n0 = (int)(tile_n * p.block_n) + (int)rank * (p.block_n / 2);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sbase = smem + (size_t)stage * stage_bytes;
@@ -769,8 +819,8 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
     uint32_t sit = 0;
     for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
         AB_UNIT_DECODE
-      const long long m0 = (tile / tiles_n) * CLUSTER_M + (long long)pair * TILE_M + (long long)rank * BLOCK_M;
-      const long long n0 = (tile % tiles_n) * p.block_n + half * half_n;
+      const long long m0 = tile_m * CLUSTER_M + (long long)pair * TILE_M + (long long)rank * BLOCK_M;
+      const long long n0 = tile_n * p.block_n + half * half_n;
 #ifdef AB_EPILOGUE
       if (KIND == 1 || kb_end - kb_begin <= p.seg_kblocks) {  // bf16 products are never segmented
         const uint32_t as = sit % (uint32_t)p.acc_stages;

@@ -276,7 +276,17 @@ class GemmEpilogueFusion:
         if self._src is None:
             names = "+".join(st[0].get("name", "?") for st in self.steps)
             merged = merge_exprs(self.steps, len(self.operand_vars), self.out_values, name=names)
-            self._src = gemm_region_source(merged, len(self.operand_vars), self.colsum, self.fullsum)
+            prog = self.program
+            # the operand that is a whole matrix (not known to broadcast along rows): read ahead
+            pre_op = -1
+            for k, v in enumerate(self.operand_vars):
+                ss = prog.vars[v].static_shape
+                c = prog.vars[v].const
+                if c is None and not (ss is not None and len(ss) == 2 and ss[0] == 1):
+                    pre_op = k
+                    break
+            self._src = gemm_region_source(merged, len(self.operand_vars), self.colsum, self.fullsum,
+                                           cin=prog.nodes[self.g].op == "Gemm", pre_op=pre_op)
         return self._src
 
     def compile_all(self):

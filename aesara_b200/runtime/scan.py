@@ -19,6 +19,9 @@ from . import kernels as K
 from .device import DeviceArray
 
 
+WHILE_POLL = 8  # an `until` condition is read back every this many steps when steps may run ahead
+
+
 class ScanRunner:
     def __init__(self, node, parent):
         from .vm import ProgramExecutor
@@ -52,6 +55,7 @@ class ScanRunner:
         self.used_fast_path = False
         self.fast_path_kind = None   # "lstm" (ahead-of-time cell) or "jit" (generated cell)
         self.direct_writes = 0
+        self.while_polls = 0
 
     def run(self, args):
         info = self.info
@@ -119,6 +123,11 @@ class ScanRunner:
                 i = n_steps
                 pos = [(p + n_steps) % s for p, s in zip(pos, store_steps)]
                 self.used_fast_path = True
+        # run ahead of an `until` condition only when no ring overwrites rows that matter
+        speculate = bool(info["as_while"]) and n_sh == 0 and all(
+            store_steps[idx] >= n_steps - self.mintaps[idx] for idx in range(n_outs)) and all(
+            nl >= n_steps for nl in nit_len)
+        flags, polled = None, i
         while i < n_steps and cond:
             inner_in = [s.index((i,)) for s in seqs]
             for idx, taps in enumerate(self.tap_array):
@@ -156,11 +165,32 @@ class ScanRunner:
             for j in range(n_sh):
                 shared_vals[j] = inner_out[k]
                 k += 1
-            if info["as_while"]:
-                c = inner_out[k]
-                cond = not bool(c.item() if isinstance(c, DeviceArray) else np.asarray(c).item())
             pos = [(p + 1) % s for p, s in zip(pos, store_steps)]
             i += 1
+            if info["as_while"]:
+                # `until`: the reference reads the condition after every step (op.py:2041-2046),
+                # a device->host synchronisation per step here.  When no output ring wraps (every
+                # row of every step has its own slot) steps may run ahead: the conditions are
+                # collected on the device and read back every WHILE_POLL steps; rows written past
+                # the stopping step are cut off below exactly like the unused tail of the rings.
+                c = inner_out[k]
+                if not isinstance(c, DeviceArray):
+                    cond = not bool(np.asarray(c).item())
+                elif not speculate:
+                    cond = not bool(c.item())
+                else:
+                    if flags is None:
+                        flags = DeviceArray.empty((n_steps,), c.dtype)
+                    K.copy_into(flags.index((slice(i - 1, i),)), c.reshape_view((1,)) if c.ndim == 0 else c)
+                    if i - polled >= WHILE_POLL or i == n_steps:
+                        got = flags.index((slice(polled, i),)).to_numpy().astype(bool)
+                        self.while_polls += 1
+                        if got.any():
+                            stop = polled + int(np.argmax(got)) + 1
+                            pos = [(p - (i - stop)) % s for p, s in zip(pos, store_steps)]
+                            i = stop
+                            cond = False
+                        polled = i
 
         allb = bufs + nit_bufs
         for idx in range(self.n_mit_mot, n_outs + n_nit):

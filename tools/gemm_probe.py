@@ -30,12 +30,12 @@ shapes = {
 res = {}
 VARIANTS = {
     "2cta": {},
-    "2cta, MN-major tiles by one 3-D copy": {"AB_GEMM_MN3D": "1"},
     "cluster4": {"AB_GEMM_CLUSTER4": "1"},
     "2cta, 6 stages": {"AB_GEMM_STAGES": "6"},
-    "2cta, 4 stages": {"AB_GEMM_STAGES": "4"},
+    "2cta, rows-then-columns tile order": {"AB_GEMM_GROUP_M": "1"},
+    "2cta, groups of 16 tile rows": {"AB_GEMM_GROUP_M": "16"},
 }
-KNOBS = ("AB_GEMM_MN3D", "AB_GEMM_CLUSTER4", "AB_GEMM_STAGES")
+KNOBS = ("AB_GEMM_MN3D", "AB_GEMM_CLUSTER4", "AB_GEMM_STAGES", "AB_GEMM_GROUP_M")
 
 
 def cublas_ms():
