@@ -22,7 +22,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 struct Module {
   cudaLibrary_t lib = nullptr;
   // lazily resolved kernels (names fixed by the skeletons in csrc/*.cuh)
-  enum { EW_FLAT_VEC, EW_FLAT, EW_ROWS_VEC, EW_ROWS, EW_ND, RED_ROWS, RED_ROWS_P, RED_ROWS_F,
+  enum { EW_FLAT_VEC, EW_FLAT, EW_ROWS_VEC, EW_ROWS, EW_ND, EW_TILE, RED_ROWS, RED_ROWS_P, RED_ROWS_F,
          RED_COLS, RED_COLS_P, RED_COLS_F, N_KERNELS };
   cudaKernel_t k[N_KERNELS] = {};
   bool tried[N_KERNELS] = {};

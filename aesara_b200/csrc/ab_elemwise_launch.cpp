@@ -9,6 +9,8 @@
 //      merge neighbours that are jointly contiguous for every operand;
 //   2. one merged dim with strides in {0,1}            -> ab_ew_flat[_vec]
 //      two merged dims with inner strides in {0,1}     -> ab_ew_rows[_vec]
+//      [batch,] rows x cols, every operand contiguous
+//      along rows or along columns (transposed views)  -> ab_ew_tile
 //      otherwise                                       -> ab_ew_nd.
 #include <algorithm>
 #include <cstdlib>
@@ -28,6 +30,7 @@ struct EwParamsHost {
                                          (size_t)nops_ * 8 * AB_MAX_DIMS, 0), nops(nops_) {}
   long long& n() { return *reinterpret_cast<long long*>(&buf[0]); }
   int& ndim() { return *reinterpret_cast<int*>(&buf[8]); }
+  int& pad() { return *reinterpret_cast<int*>(&buf[12]); }
   long long* shape() { return reinterpret_cast<long long*>(&buf[16]); }
   void** ptr() { return reinterpret_cast<void**>(&buf[16 + 8 * AB_MAX_DIMS]); }
   long long* stride(int k) {
@@ -170,10 +173,33 @@ extern "C" int ab_elemwise_launch(ab_module* mod, int n_in, int n_out, int ndim,
     grid.y = (unsigned)gy;
     which = v ? Module::EW_ROWS_VEC : Module::EW_ROWS;
   } else {
-    long long blocks = (total + threads - 1) / threads;
-    blocks = std::max<long long>(1, std::min<long long>(blocks, (long long)sms * 32));
-    grid.x = (unsigned)blocks;
-    which = Module::EW_ND;
+    // [batch,] rows x cols with every operand contiguous along the rows OR the columns (a
+    // matrix and a DimShuffle{1,0} view in one expression): the tiled kernel turns the
+    // row-contiguous inputs through shared memory
+    bool tiled = (nd == 2 || nd == 3) && n_in <= 16 && getenv("AB_EW_NO_TILE") == nullptr &&
+                 shp[nd - 1] >= 16 && shp[nd - 2] >= 16;
+    unsigned colmajor = 0;
+    for (int k = 0; k < nops && tiled; ++k) {
+      const int64_t sr = st[k][nd - 2], sc = st[k][nd - 1];
+      if (itemsizes[k] > 8) tiled = false;
+      else if (sc == 0 || sc == 1) continue;                       // read in output order
+      else if (k < n_in && (sr == 1 || sr == 0)) colmajor |= 1u << k;  // turned in shared memory
+      else tiled = false;
+    }
+    int max_item = 1;
+    for (int k = 0; k < n_in; ++k) max_item = std::max(max_item, (int)itemsizes[k]);
+    if (tiled && (long long)std::max(n_in, 1) * 32 * 33 * max_item > 48 * 1024) tiled = false;
+    if (tiled && colmajor) {
+      const long long tiles = (nd == 3 ? shp[0] : 1) * ((shp[nd - 2] + 31) / 32) * ((shp[nd - 1] + 31) / 32);
+      grid.x = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)sms * 32));
+      P.pad() = (int)colmajor;
+      which = Module::EW_TILE;
+    } else {
+      long long blocks = (total + threads - 1) / threads;
+      blocks = std::max<long long>(1, std::min<long long>(blocks, (long long)sms * 32));
+      grid.x = (unsigned)blocks;
+      which = Module::EW_ND;
+    }
   }
 
   cudaKernel_t kern;

@@ -34,7 +34,7 @@ int fail(int code, const char* fmt, ...) {
 std::atomic<uint64_t> g_launches{0};
 
 static const char* kKernelNames[Module::N_KERNELS] = {
-    "ab_ew_flat_vec", "ab_ew_flat", "ab_ew_rows_vec", "ab_ew_rows", "ab_ew_nd",
+    "ab_ew_flat_vec", "ab_ew_flat", "ab_ew_rows_vec", "ab_ew_rows", "ab_ew_nd", "ab_ew_tile",
     "ab_red_rows",    "ab_red_rows_p", "ab_red_rows_f", "ab_red_cols", "ab_red_cols_p",
     "ab_red_cols_f"};
 

@@ -580,6 +580,51 @@ def test_lstm_generated_cell_equals_the_ahead_of_time_cell(rt):
         np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("shape", [(1000, 777), (64, 4099), (33, 17), (5, 300, 130)])
+def test_elemwise_transposed_operands_take_the_tiled_kernel(rt, shape):
+    """An expression over a matrix and DimShuffle{1,0} views of others (`a.T * b + c.T > 0`):
+    the tiled kernel (csrc/ab_elemwise.cuh ab_ew_tile: row-contiguous inputs turned through
+    shared memory) gives the bits of the index-arithmetic kernel (AB_EW_NO_TILE), on float32,
+    float64, int and bool operands, ragged tile edges and a batched (3-D) case."""
+    import os
+
+    from aesara_b200.runtime import kernels as K
+    from aesara_b200.runtime.device import DeviceArray
+
+    rng = np.random.default_rng(sum(shape))
+    tshape = shape[:-2] + (shape[-1], shape[-2])
+    perm = list(range(len(shape) - 2)) + [len(shape) - 1, len(shape) - 2]
+    for dts in (("float32", "float32", "float32"), ("float64", "float32", "int32"), ("int16", "bool", "int64")):
+        a = (rng.standard_normal(tshape) * 3).astype(dts[0])
+        b = (rng.standard_normal(shape) * 3).astype(dts[1])
+        c = (rng.standard_normal(tshape) * 3).astype(dts[2])
+        out_dt = np.result_type(*dts).name if "bool" not in dts else "int64"
+        expr = {"inputs": list(dts), "out_dtypes": [out_dt, "bool"], "outputs": ["t2", "t3"], "name": "tiled_probe",
+                "stmts": [{"op": "cast", "args": ["i0"], "dtype": out_dt, "in_dtypes": [dts[0]]},
+                          {"op": "cast", "args": ["i1"], "dtype": out_dt, "in_dtypes": [dts[1]]},
+                          {"op": "add", "args": ["t0", "t1"], "dtype": out_dt, "in_dtypes": [out_dt, out_dt]},
+                          {"op": "gt", "args": ["i2", {"const": 0, "dtype": dts[2]}], "dtype": "bool", "in_dtypes": [dts[2], dts[2]]}]}
+        kern = K.ElemwiseKernel.get(expr)
+        ins = [DeviceArray.from_numpy(a).dimshuffle(perm), DeviceArray.from_numpy(b),
+               DeviceArray.from_numpy(c).dimshuffle(perm)]
+        res = []
+        for no_tile in (False, True):
+            if no_tile:
+                os.environ["AB_EW_NO_TILE"] = "1"
+            try:
+                outs = [DeviceArray.empty(shape, out_dt), DeviceArray.empty(shape, "bool")]
+                kern.launch(shape, ins, outs)
+                res.append([o.to_numpy() for o in outs])
+            finally:
+                os.environ.pop("AB_EW_NO_TILE", None)
+        at_, ct_ = np.transpose(a, perm), np.transpose(c, perm)
+        want0 = at_.astype(out_dt) + b.astype(out_dt)
+        np.testing.assert_array_equal(res[0][0], res[1][0])
+        np.testing.assert_array_equal(res[0][1], res[1][1])
+        np.testing.assert_array_equal(res[0][0], want0)
+        np.testing.assert_array_equal(res[0][1], ct_ > 0)
+
+
 def test_zz_launch_counts_are_recorded():
     """Writes the per-fixture launch counts next to the run (gpurun_out/) for the record."""
     import json
