@@ -533,8 +533,14 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     p.stages = std::max(2, std::min(p.stages, atoi(st_env)));
   p.acc_stages = 2;  // 2 x block_n <= 512 TMEM columns
   {
-    const char* gm_env = getenv("AB_GEMM_GROUP_M");  // probing knob; 1 = rows-then-columns order
-    p.group_m = gm_env ? std::max(1, atoi(gm_env)) : 8;
+    // Unit order inside a K range (AB_UNIT_DECODE).  Measured on the three cfg3 layouts
+    // (profiles/r02_gemm_probe_order_stages.json, variants interleaved in one process): a tall
+    // tile grid (65536 x 4096: 256 x 16 tiles) gains 8-18 % from groups of 8 tile rows, the
+    // square grid of the weight-gradient products (16 x 16 tiles, K = 65536) is 35 % FASTER in
+    // plain rows-then-columns order (all 16 column tiles of a row stream whole rows of B).
+    const char* gm_env = getenv("AB_GEMM_GROUP_M");  // probing knob
+    const long long tm = (M + 255) / 256, tn = (N + 255) / 256;
+    p.group_m = gm_env ? std::max(1, atoi(gm_env)) : (tm >= 4 * tn ? 8 : 1);
   }
   {
     // K segments (see "segments" above): 4 k-blocks = 128 K elements for the fp32-faithful
