@@ -203,9 +203,11 @@ ab_ew_rows(const __grid_constant__ AbEwParams p) {
 // ------------------------------------------------------------------ tile ------
 // shape = [R, C] (ndim 2) or [nb, R, C] (ndim 3).  Per operand: unit (or 0) stride along C
 // ("row-major": read in output order) or unit stride along R with any stride along C
-// ("column-major": staged through a 32 x 33 shared-memory tile).  Outputs are row-major.
-// p.pad_ carries a bit mask of the column-major inputs.  Block = 32 x 8 threads.
-#define AB_TILE 32
+// ("column-major": staged through a 64 x 65 shared-memory tile).  Outputs are row-major.
+// p.pad_ carries a bit mask of the column-major inputs; the launcher admits as many of them
+// as tiles fit into the 48 KB of static shared memory (ab_ew_tile_slots).  Block = 32 x 8
+// threads, 16 elements per thread: 16 independent loads per input in flight per thread.
+#define AB_TILE 64
 __host__ __device__ constexpr int ab_max_input_size() {
   int m = 1;
 #define AB_T_SZ(k, T) m = (int)sizeof(T) > m ? (int)sizeof(T) : m;
@@ -213,15 +215,15 @@ __host__ __device__ constexpr int ab_max_input_size() {
 #undef AB_T_SZ
   return m;
 }
+__host__ __device__ constexpr int ab_ew_tile_slots() {
+  return (48 * 1024) / (AB_TILE * (AB_TILE + 1) * ab_max_input_size());
+}
 extern "C" __global__ void __launch_bounds__(AB_THREADS)
 ab_ew_tile(const __grid_constant__ AbEwParams p) {
-  // one [32][33] tile per input, slots as wide as the widest input type; modules whose inputs
-  // would need more than the 48 KB of static shared memory never take this path (the launcher
-  // checks the same arithmetic)
   constexpr int kSlot = ab_max_input_size();
-  constexpr int kNeed = (AB_NIN > 0 ? AB_NIN : 1) * AB_TILE * (AB_TILE + 1) * kSlot;
-  __shared__ __align__(16) unsigned char tile_raw[kNeed <= 48 * 1024 ? kNeed : 16];
-#define AB_TSLOT(k, i, j) (tile_raw + ((((k) * AB_TILE + (i)) * (AB_TILE + 1) + (j)) * kSlot))
+  constexpr int kSlots = ab_ew_tile_slots() > 0 ? ab_ew_tile_slots() : 1;
+  __shared__ __align__(16) unsigned char tile_raw[kSlots * AB_TILE * (AB_TILE + 1) * kSlot];
+#define AB_TSLOT(s, i, j) (tile_raw + ((((s) * AB_TILE + (i)) * (AB_TILE + 1) + (j)) * kSlot))
   const int nd = p.ndim;
   const long long R = p.shape[nd - 2], C = p.shape[nd - 1];
   const long long nb = nd == 3 ? p.shape[0] : 1;
@@ -233,48 +235,54 @@ ab_ew_tile(const __grid_constant__ AbEwParams p) {
     const long long b = t / (tiles_r * tiles_c);
     const long long tr = (t / tiles_c) % tiles_r, tc = t % tiles_c;
     const long long r0 = tr * AB_TILE, c0 = tc * AB_TILE;
-    // 1. column-major inputs: coalesced along rows -> shared[c_local][r_local]
+    // 1. column-major inputs: coalesced along rows -> shared[slot][c_local][r_local]
 #define AB_T_STAGE(k, T)                                                              \
     if (mask & (1u << k)) {                                                           \
+      const int slot = __popc(mask & ((1u << k) - 1u));                               \
       const T* ip = reinterpret_cast<const T*>(p.ptr[k]) + (nd == 3 ? b * p.stride[k][0] : 0); \
       const long long sr = p.stride[k][nd - 2], sc = p.stride[k][nd - 1];             \
       _Pragma("unroll") for (int i = 0; i < AB_TILE; i += 8) {                        \
-        const long long r = r0 + tx, c = c0 + ty + i;                                 \
-        if (r < R && c < C)                                                           \
-          *reinterpret_cast<T*>(AB_TSLOT(k, ty + i, tx)) = ip[r * sr + c * sc];       \
+        _Pragma("unroll") for (int h = 0; h < AB_TILE; h += 32) {                     \
+          const long long r = r0 + tx + h, c = c0 + ty + i;                           \
+          if (r < R && c < C)                                                         \
+            *reinterpret_cast<T*>(AB_TSLOT(slot, ty + i, tx + h)) = ip[r * sr + c * sc]; \
+        }                                                                             \
       }                                                                               \
     }
     AB_INPUTS(AB_T_STAGE)
 #undef AB_T_STAGE
     __syncthreads();
     // 2. compute in output order (coalesced along columns)
-#pragma unroll
+#pragma unroll 4
     for (int i = 0; i < AB_TILE; i += 8) {
-      const long long r = r0 + ty + i, c = c0 + tx;
-      if (r < R && c < C) {
+#pragma unroll
+      for (int h = 0; h < AB_TILE; h += 32) {
+        const long long r = r0 + ty + i, c = c0 + tx + h;
+        if (r < R && c < C) {
 #define AB_T_LD(k, T)                                                                 \
-        T tin##k;                                                                     \
-        if (mask & (1u << k)) {                                                       \
-          tin##k = *reinterpret_cast<const T*>(AB_TSLOT(k, tx, ty + i));              \
-        } else {                                                                      \
-          const T* ip = reinterpret_cast<const T*>(p.ptr[k]) + (nd == 3 ? b * p.stride[k][0] : 0); \
-          tin##k = ip[r * p.stride[k][nd - 2] + c * p.stride[k][nd - 1]];             \
-        }
-        AB_INPUTS(AB_T_LD)
+          T tin##k;                                                                   \
+          if (mask & (1u << k)) {                                                     \
+            tin##k = *reinterpret_cast<const T*>(AB_TSLOT(__popc(mask & ((1u << k) - 1u)), tx + h, ty + i)); \
+          } else {                                                                    \
+            const T* ip = reinterpret_cast<const T*>(p.ptr[k]) + (nd == 3 ? b * p.stride[k][0] : 0); \
+            tin##k = ip[r * p.stride[k][nd - 2] + c * p.stride[k][nd - 1]];           \
+          }
+          AB_INPUTS(AB_T_LD)
 #undef AB_T_LD
 #define AB_T_OD(k, T) T tout##k;
-        AB_OUTPUTS(AB_T_OD)
+          AB_OUTPUTS(AB_T_OD)
 #undef AB_T_OD
 #define AB_IN_E(k) tin##k
 #define AB_OUT_E(k) tout##k
-        AB_CALL_BODY(AB_IN_E, AB_OUT_E);
+          AB_CALL_BODY(AB_IN_E, AB_OUT_E);
 #undef AB_IN_E
 #undef AB_OUT_E
 #define AB_T_ST(k, T)                                                                 \
-        (reinterpret_cast<T*>(p.ptr[AB_NIN + k]) + (nd == 3 ? b * p.stride[AB_NIN + k][0] : 0)) \
-            [r * p.stride[AB_NIN + k][nd - 2] + c * p.stride[AB_NIN + k][nd - 1]] = tout##k;
-        AB_OUTPUTS(AB_T_ST)
+          (reinterpret_cast<T*>(p.ptr[AB_NIN + k]) + (nd == 3 ? b * p.stride[AB_NIN + k][0] : 0)) \
+              [r * p.stride[AB_NIN + k][nd - 2] + c * p.stride[AB_NIN + k][nd - 1]] = tout##k;
+          AB_OUTPUTS(AB_T_ST)
 #undef AB_T_ST
+        }
       }
     }
     __syncthreads();

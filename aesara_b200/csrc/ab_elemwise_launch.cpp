@@ -186,11 +186,15 @@ extern "C" int ab_elemwise_launch(ab_module* mod, int n_in, int n_out, int ndim,
       else if (k < n_in && (sr == 1 || sr == 0)) colmajor |= 1u << k;  // turned in shared memory
       else tiled = false;
     }
-    int max_item = 1;
-    for (int k = 0; k < n_in; ++k) max_item = std::max(max_item, (int)itemsizes[k]);
-    if (tiled && (long long)std::max(n_in, 1) * 32 * 33 * max_item > 48 * 1024) tiled = false;
+    int max_item = 1, staged = 0;
+    for (int k = 0; k < n_in; ++k) {
+      max_item = std::max(max_item, (int)itemsizes[k]);
+      staged += (colmajor >> k) & 1u;
+    }
+    // 64 x 65 tiles of the widest input type in 48 KB of static shared memory (ab_ew_tile_slots)
+    if (tiled && staged > (48 * 1024) / (64 * 65 * max_item)) tiled = false;
     if (tiled && colmajor) {
-      const long long tiles = (nd == 3 ? shp[0] : 1) * ((shp[nd - 2] + 31) / 32) * ((shp[nd - 1] + 31) / 32);
+      const long long tiles = (nd == 3 ? shp[0] : 1) * ((shp[nd - 2] + 63) / 64) * ((shp[nd - 1] + 63) / 64);
       grid.x = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)sms * 32));
       P.pad() = (int)colmajor;
       which = Module::EW_TILE;

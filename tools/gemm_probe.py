@@ -60,12 +60,14 @@ best = {}
 for rnd in range(3):
     for name, (A, Bm, oshape) in shapes.items():
         C = DeviceArray.empty(oshape, "float32")
-        for variant, env in VARIANTS.items():
+        order = list(VARIANTS.items())
+        order = order[rnd % len(order):] + order[:rnd % len(order)]   # no variant is always first
+        for variant, env in order:
             for k in KNOBS:
                 os.environ.pop(k, None)
             os.environ.update(env)
             cache = K.PackCache()
-            for _ in range(2):
+            for _ in range(8):
                 K.gemm(C, 1.0, A, Bm, 0.0, precision=2, cache=cache)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
