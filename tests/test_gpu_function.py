@@ -292,3 +292,53 @@ def test_scan_variants_through_the_linker(env):
             (rng.standard_normal((H, H)) / np.sqrt(H)).astype("float32")]
     for k, (a, b) in enumerate(zip(f(*vals), g(*vals))):
         _close(a, b, True, f"rnn grad output {k}", rtol=3e-5)
+
+
+def test_host_chunks_pipeline_equals_whole_batch(env):
+    """``mode(host_chunks=K)``: NumPy arguments of a batch-map graph are uploaded and evaluated in
+    row blocks (shard.ChunkedHostExecutor) and the outputs combined as shardplan derives from the
+    graph (mean for the MLP loss and gradients, concat for a per-row output); a graph that is not
+    a batch map is evaluated whole."""
+    aesara, L, lib = env
+    import aesara.tensor as at
+    import torch
+
+    from aesara_b200 import graphs as G
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+
+    i, o = G.cfg3_mlp()
+    f = aesara.function(i, o, mode=L.mode(host_chunks=4))
+    i2, o2 = G.cfg3_mlp()
+    g = aesara.function(i2, o2, mode=L.mode())
+    vals = G.cfg3_inputs(16384 + 37, 256)          # ragged: the row blocks differ by one row
+    keep = [pinned(v) for v in vals]
+    got = f(*[k.numpy() for k in keep])
+    assert f.vm.executor.chunks_run == 4
+    assert [m[0] for m in f.maker.linker.shard_plan.outputs] == ["mean"] * 5
+    want = g(*vals)
+    for k, (a, b) in enumerate(zip(got, want)):
+        _close(a, b, True, f"chunked MLP output {k}", rtol=3e-5)
+    # per-row output: concat
+    x, y, z = at.fvectors("x", "y", "z")
+    h = aesara.function([x, y, z], [at.softplus(at.tanh(x) + y) * z, (x * y).sum()], mode=L.mode(host_chunks=3))
+    n = 50000
+    xs = G.cfg2_inputs(n)
+    out, tot = h(*xs)
+    assert h.vm.executor.chunks_run == 3 and out.shape == (n,)
+    ref = aesara.function([x, y, z], [at.softplus(at.tanh(x) + y) * z, (x * y).sum()], mode="FAST_RUN")(*xs)
+    _close(out, ref[0], False, "chunked elementwise output")
+    _close(tot, ref[1], True, "chunked sum output", rtol=2e-5)
+    # device-resident arguments are evaluated in one piece
+    from aesara_b200.runtime.device import DeviceArray
+
+    f.trust_input = True
+    f(*[DeviceArray.from_numpy(v) for v in vals])
+    assert f.vm.executor.chunks_run == 1
+    # not a batch map (a maximum over the batch axis): no chunking, same answer as the C-linker
+    m = aesara.function([x], x.max() + x.sum(), mode=L.mode(host_chunks=4))
+    assert not hasattr(m.vm.executor, "chunks_run")
+    _close(m(xs[0]), np.float32(xs[0].max() + xs[0].sum(dtype=np.float64)), True, "replicas-only graph")
