@@ -81,7 +81,10 @@ class B200VM:
         if self.time_thunks and hasattr(executor, "time_nodes"):
             executor.time_nodes = True
         self._replay = None
-        if linker.cuda_graph and not self.time_thunks and linker.shard is None:
+        if linker.cuda_graph and not self.time_thunks:
+            # with shard="rows" the captured evaluation includes the NCCL all-reduces and the
+            # side-stream fork/join of shard.ShardedExecutor (every rank captures and replays in
+            # lock step: one cudaGraphLaunch per rank per evaluation)
             from .runtime.graph import GraphReplay
 
             self._replay = GraphReplay(executor)

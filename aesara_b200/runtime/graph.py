@@ -27,7 +27,7 @@ from .vm import ProgramExecutor
 
 
 class GraphReplay:
-    def __init__(self, executor: ProgramExecutor, max_graphs: int = 8):
+    def __init__(self, executor, max_graphs: int = 8):
         if executor.host_outputs:
             raise ValueError("GraphReplay needs an executor with host_outputs=False")
         self.ex = executor

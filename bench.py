@@ -507,7 +507,7 @@ def measure(spec, precision, steps, warmup, rank=0, world=1, dist=None, use_grap
     # N > 1: the row sharding and the combination of the outputs are the linker's
     # (mode(shard="rows")): derived from the graph, one process per GPU, NCCL all-reduces
     f, ex, boundary = compile_b200(spec, precision, device_outputs=True,
-                                   cuda_graph=use_graph and world == 1,
+                                   cuda_graph=use_graph and (world == 1 or os.environ.get("AB_SHARD_GRAPH", "1") != "0"),
                                    shard="rows" if world > 1 else None)
     dev_in, keep = make_inputs_device(spec, seed=seed + rank)
 

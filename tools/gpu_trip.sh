@@ -45,10 +45,13 @@ case $sec in
     timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -p no:cacheprovider -x > gpurun_out/pytest_multi.log 2>&1; echo "multitest rc=$?"; tail -6 gpurun_out/pytest_multi.log | cut -c1-300;;
   scale_mlp)
     N=$(nvidia-smi -L | wc -l)
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_mlp_n$N.json 2> gpurun_out/bench_mlp_n$N.err; echo "scale_mlp N=$N rc=$?"; tail -3 gpurun_out/bench_mlp_n$N.err | cut -c1-300; python -c "import json;d=json.load(open('gpurun_out/bench_mlp_n$N.json'));print(d['n_gpus'], d['value'], d['ms_per_step'], d.get('parity_sharded'), d.get('exchange'))";;
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_mlp_n$N.json 2> gpurun_out/bench_mlp_n$N.err; echo "scale_mlp N=$N rc=$?"; tail -3 gpurun_out/bench_mlp_n$N.err | cut -c1-300; python -c "import json;d=json.loads([l for l in open('gpurun_out/bench_mlp_n$N.json') if l.startswith('{')][-1]);print(d['n_gpus'], d['value'], d['ms_per_step'], d['config']['executor'], d.get('parity_sharded'), d.get('exchange'))";;
+  scale_mlp_nograph)
+    N=$(nvidia-smi -L | wc -l)
+    AB_SHARD_GRAPH=0 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_mlp_nograph_n$N.json 2> gpurun_out/bench_mlp_nograph_n$N.err; echo "scale_mlp_nograph N=$N rc=$?"; python -c "import json;d=json.loads([l for l in open('gpurun_out/bench_mlp_nograph_n$N.json') if l.startswith('{')][-1]);print(d['n_gpus'], d['value'], d['ms_per_step'], d['config']['executor'])";;
   scale_logreg)
     N=$(nvidia-smi -L | wc -l)
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --workload logreg --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_logreg_n$N.json 2> gpurun_out/bench_logreg_n$N.err; echo "scale_logreg N=$N rc=$?"; tail -3 gpurun_out/bench_logreg_n$N.err | cut -c1-300; python -c "import json;d=json.load(open('gpurun_out/bench_logreg_n$N.json'));print(d['n_gpus'], d['value'], d['ms_per_step'], d.get('parity_sharded'), d.get('exchange'))";;
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --workload logreg --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_logreg_n$N.json 2> gpurun_out/bench_logreg_n$N.err; echo "scale_logreg N=$N rc=$?"; tail -3 gpurun_out/bench_logreg_n$N.err | cut -c1-300; python -c "import json;d=json.loads([l for l in open('gpurun_out/bench_logreg_n$N.json') if l.startswith('{')][-1]);print(d['n_gpus'], d['value'], d['ms_per_step'], d['config']['executor'], d.get('parity_sharded'), d.get('exchange'))";;
   ew_probe)
     timeout 300 python tools/ew_probe.py 2>&1 | tail -3;;
   reference)
