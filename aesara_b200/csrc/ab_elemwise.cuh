@@ -208,6 +208,9 @@ ab_ew_rows(const __grid_constant__ AbEwParams p) {
 // as tiles fit into the 48 KB of static shared memory (ab_ew_tile_slots).  Block = 32 x 8
 // threads, 16 elements per thread: 16 independent loads per input in flight per thread.
 #define AB_TILE 64
+#ifndef AB_TILE_BAND
+#define AB_TILE_BAND 1  // measured: bands of 2-32 tile rows are 10 % slower (profiles/r02_ew_transposed_tile64.json)
+#endif
 __host__ __device__ constexpr int ab_max_input_size() {
   int m = 1;
 #define AB_T_SZ(k, T) m = (int)sizeof(T) > m ? (int)sizeof(T) : m;
@@ -232,8 +235,15 @@ ab_ew_tile(const __grid_constant__ AbEwParams p) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const unsigned mask = (unsigned)p.pad_;
   for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    // tile order: bands of AB_TILE_BAND tile rows, rows fastest inside a band (1 = row-major
+    // tiles).  Wider bands make the tiles in flight cover AB_TILE_BAND * 256 contiguous bytes
+    // of the turned operands, and measured slower (knob AB_EW_TILE_BAND kept for the sweep).
     const long long b = t / (tiles_r * tiles_c);
-    const long long tr = (t / tiles_c) % tiles_r, tc = t % tiles_c;
+    const long long tb = t % (tiles_r * tiles_c);
+    const long long band = tb / (AB_TILE_BAND * tiles_c), in_band = tb % (AB_TILE_BAND * tiles_c);
+    const long long band_rows = (tiles_r - band * AB_TILE_BAND) < AB_TILE_BAND
+                                    ? (tiles_r - band * AB_TILE_BAND) : AB_TILE_BAND;
+    const long long tr = band * AB_TILE_BAND + in_band % band_rows, tc = in_band / band_rows;
     const long long r0 = tr * AB_TILE, c0 = tc * AB_TILE;
     // 1. column-major inputs: coalesced along rows -> shared[slot][c_local][r_local]
 #define AB_T_STAGE(k, T)                                                              \

@@ -60,16 +60,30 @@ struct GemmParams {
 
 // one operand tile -> shared memory.  K-major: a single box {128 B of K, tile rows};
 // MN-major: one box {128 B of MN, BLOCK_K rows} per chunk.
+// Loop-invariant description of one operand's tile loads.  The producer and the MMA issuer
+// copy what they need from GemmParams into locals BEFORE their loops: the kernel parameter
+// lives in constant memory, every mbarrier / TMA asm statement carries a "memory" clobber, and
+// a field read through `p` inside the loop is re-loaded (LDCU + dependent UISETP) after each
+// of them -- the single producer thread of the MN-major weight-gradient products spent ~540
+// of the 770 cycles per k-block on that (profiles/r02_region2_fp64_stalls.txt, dW launches).
+struct OperandLoad {
+  int mn_major, chunks, mn3d, chunk_bytes, mn_per_chunk;
+};
+__device__ __forceinline__ OperandLoad operand_load_a(const GemmParams& p) {
+  return OperandLoad{p.a_mn, p.a_chunks, p.a_mn3d, p.chunk_bytes, p.mn_per_chunk};
+}
+__device__ __forceinline__ OperandLoad operand_load_b(const GemmParams& p) {
+  return OperandLoad{p.b_mn, p.b_chunks, p.b_mn3d, p.chunk_bytes, p.mn_per_chunk};
+}
 __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
-                                          int kc, int mn0, int mn_major, int chunks,
-                                          const GemmParams& p, int mn3d = 0) {
-  if (!mn_major) {
+                                          int kc, int mn0, const OperandLoad& o) {
+  if (!o.mn_major) {
     tma_load_2d(dst, map, bar, kc, mn0);
-  } else if (mn3d) {
-    tma_load_3d(dst, map, bar, 0, kc, mn0 / p.mn_per_chunk);
+  } else if (o.mn3d) {
+    tma_load_3d(dst, map, bar, 0, kc, mn0 / o.mn_per_chunk);
   } else {
-    for (int c = 0; c < chunks; ++c)
-      tma_load_2d(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
+    for (int c = 0; c < o.chunks; ++c)
+      tma_load_2d(dst + c * o.chunk_bytes, map, bar, mn0 + c * o.mn_per_chunk, kc);
   }
 }
 
@@ -228,6 +242,30 @@ struct EpilogueOut {
   // of SASS, which every warp re-fetches from L2 for every tile (measured: the region with
   // two values and two reductions ran 1.5 ms slower than its five separate kernels).
   struct FusedScalars { float v[4]; bool is[4]; };
+  // Sums of the region are kept as unevaluated float pairs (hi + lo, error-free TwoSum) while
+  // they stay inside a thread or a warp, and become float64 where they leave it: the FP64
+  // pipe of this part retires a warp-wide DADD every ~20 cycles, and one DADD + one F2F.F64
+  // per element made the epilogue of the region with two reductions the critical path (ncu,
+  // profiles/r02_region2_fp64_stalls.txt: 47 % of the epilogue warps' samples on DADD,
+  // stall_math).  A pair carries ~48 bits: the float64 accumulator of the reference's
+  // CAReduce (tensor/elemwise.py:1371-1385) to well below the float32 rounding of the result.
+  struct FF { float hi, lo; };
+  static __device__ __forceinline__ void ff_add(FF& a, float x) {
+    const float t = __fadd_rn(a.hi, x);
+    const float bp = __fsub_rn(t, a.hi);
+    a.lo = __fadd_rn(a.lo, __fadd_rn(__fsub_rn(a.hi, __fsub_rn(t, bp)), __fsub_rn(x, bp)));
+    a.hi = t;
+  }
+  static __device__ __forceinline__ void ff_add(FF& a, const FF& b) {
+    const float lo = a.lo;
+    a.lo = 0.0f;
+    ff_add(a, b.hi);
+    a.lo = __fadd_rn(a.lo, __fadd_rn(lo, b.lo));
+  }
+  // non-finite sums: hi already is the inf / nan the float64 sum would be (lo is nan then)
+  static __device__ __forceinline__ double ff_double(const FF& a) {
+    return (a.hi - a.hi == 0.0f) ? (double)a.hi + (double)a.lo : (double)a.hi;
+  }
   __device__ __forceinline__ FusedScalars load_scalars() const {
     FusedScalars s;
 #pragma unroll
@@ -254,35 +292,51 @@ struct EpilogueOut {
       }
     }
   }
-  // x[32]: raw accumulator values of columns col0 .. col0+31 of `row`; on return (AB_EP_COLSUM
-  // builds) they have been replaced and reduced: the column sums of the warp's 32 rows are
-  // written to colsum_ws.  `fs` accumulates the AB_EP_FULLSUM value of this thread.
-  __device__ __forceinline__ void fused_chunk(float (&x)[32], long long row, long long col0, bool live,
-                                              int lane, const FusedScalars& sc, double& fs) const {
-    const long long r = live ? row : 0;
-    // Matrix-shaped reads of the whole chunk are issued up front: the loads of all four column
-    // groups are in flight together (one DRAM latency per chunk).  Loaded group by group right
-    // before their use, an epilogue that reads a [M, N] operand (the Gemm's z, or h in
-    // g * (1 - h^2)) is latency-bound: 16 dependent round trips per tile, tensor pipe 52-66 %
-    // active against 71-74 % without such a read (profiles/r02_bench_step_ncu.txt).
+  // Matrix-shaped reads of a 32-column chunk (the Gemm's z; one [M, N] operand such as h in
+  // g * (1 - h^2)) are issued as one batch, ONE CHUNK AHEAD of their use (store_fused*): the
+  // loads of all four column groups are in flight together and their DRAM latency passes
+  // under the evaluation of the previous chunk.  Loaded group by group right before their
+  // use, such an epilogue is latency-bound (16 dependent round trips per tile, tensor pipe
+  // 52-66 % active against 71-74 % without such a read, profiles/r02_bench_step_ncu.txt);
+  // loaded per chunk but consumed at once, it still waits one DRAM latency per chunk (19 % of
+  // the epilogue warps' samples, profiles/r02_region2_fp64_stalls.txt).
+  struct ChunkPre {
 #if AB_EP_CIN
-    float cin_pre[32];
+    float cin[32];
+#endif
+#if AB_EP_PRE_OP >= 0
+    float op[32];
+#endif
+  };
+  __device__ __forceinline__ void prefetch_chunk(ChunkPre& pre, long long row, long long col0, bool live,
+                                                 const FusedScalars& sc) const {
+    const long long r = live ? row : 0;
+    (void)r; (void)sc; (void)pre; (void)col0;
+#if AB_EP_CIN
     if (live && p.beta != 0.0f) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8)
-        if (col0 + j < p.N) ld8(p.Cin + r * p.cin_rs + col0 + j, *reinterpret_cast<float(*)[8]>(&cin_pre[j]), wide_in);
+        if (col0 + j < p.N) ld8(p.Cin + r * p.cin_rs + col0 + j, *reinterpret_cast<float(*)[8]>(&pre.cin[j]), wide_in);
     }
 #endif
 #if AB_EP_PRE_OP >= 0
-    float op_pre[32];
-    const bool pre_ok = live && !sc.is[AB_EP_PRE_OP] && p.ep_cs[AB_EP_PRE_OP] == 1;
-    if (pre_ok) {
+    if (live && !sc.is[AB_EP_PRE_OP] && p.ep_cs[AB_EP_PRE_OP] == 1) {
       const bool wide = ((reinterpret_cast<uintptr_t>(p.ep_ptr[AB_EP_PRE_OP]) & 31) == 0) && ((p.ep_rs[AB_EP_PRE_OP] & 7) == 0);
 #pragma unroll
       for (int j = 0; j < 32; j += 8)
         if (col0 + j < p.N)
-          ld8(p.ep_ptr[AB_EP_PRE_OP] + r * p.ep_rs[AB_EP_PRE_OP] + col0 + j, *reinterpret_cast<float(*)[8]>(&op_pre[j]), wide);
+          ld8(p.ep_ptr[AB_EP_PRE_OP] + r * p.ep_rs[AB_EP_PRE_OP] + col0 + j, *reinterpret_cast<float(*)[8]>(&pre.op[j]), wide);
     }
+#endif
+  }
+  // x[32]: raw accumulator values of columns col0 .. col0+31 of `row`; on return (AB_EP_COLSUM
+  // builds) they have been replaced and reduced: the column sums of the warp's 32 rows are
+  // written to colsum_ws.  `fs` accumulates the AB_EP_FULLSUM value of this thread.
+  __device__ __forceinline__ void fused_chunk(float (&x)[32], long long row, long long col0, bool live,
+                                              int lane, const FusedScalars& sc, FF& fs, const ChunkPre& pre) const {
+    const long long r = live ? row : 0;
+#if AB_EP_PRE_OP >= 0
+    const bool pre_ok = live && !sc.is[AB_EP_PRE_OP] && p.ep_cs[AB_EP_PRE_OP] == 1;
 #endif
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
@@ -294,7 +348,7 @@ struct EpilogueOut {
         if (p.beta != 0.0f) {
 #if AB_EP_CIN
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] += p.beta * cin_pre[j + t];
+          for (int t = 0; t < 8; ++t) v[t] += p.beta * pre.cin[j + t];
 #else
           float ci[8];
           ld8(p.Cin + r * p.cin_rs + col, ci, wide_in);
@@ -308,7 +362,7 @@ struct EpilogueOut {
 #if AB_EP_PRE_OP >= 0
           if (k == AB_EP_PRE_OP && pre_ok) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) e[k][t] = op_pre[j + t];
+            for (int t = 0; t < 8; ++t) e[k][t] = pre.op[j + t];
             continue;
           }
 #endif
@@ -334,7 +388,7 @@ struct EpilogueOut {
 #endif
 #if AB_EP_FULLSUM >= 0
 #pragma unroll
-        for (int t = 0; t < 8; ++t) fs += (double)o[AB_EP_FULLSUM][t];
+        for (int t = 0; t < 8; ++t) ff_add(fs, o[AB_EP_FULLSUM][t]);
 #endif
       } else {
 #if AB_EP_COLSUM >= 0
@@ -345,38 +399,45 @@ struct EpilogueOut {
     }
 #if AB_EP_COLSUM >= 0
     {
-      // 32 x 32 transpose-reduce over the warp's rows in float64 (the reference's CAReduce
-      // accumulates float32 sums in float64, tensor/elemwise.py:1371-1385): after the step
-      // with distance h every lane keeps the half of its columns selected by bit h of its lane
+      // 32 x 32 transpose-reduce over the warp's rows on float pairs (see FF above; the
+      // reference's CAReduce accumulates float32 sums in float64): after the step with
+      // distance h every lane keeps the half of its columns selected by bit h of its lane
       // index; lane l ends with the sum of column col0 + l
-      double d[16];
+      FF d[16];
       {
         const bool up = (lane & 16) != 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float keep = up ? x[16 + i] : x[i];
           const float send = up ? x[i] : x[16 + i];
-          d[i] = (double)keep + (double)__shfl_xor_sync(0xffffffffu, send, 16);
+          d[i].hi = keep;
+          d[i].lo = 0.0f;
+          ff_add(d[i], __shfl_xor_sync(0xffffffffu, send, 16));
         }
       }
 #define AB_COLSUM_STEP(H)                                                      \
       {                                                                        \
         const bool up = (lane & (H)) != 0;                                     \
         _Pragma("unroll") for (int i = 0; i < (H); ++i) {                      \
-          const double keep = up ? d[(H) + i] : d[i];                          \
-          const double send = up ? d[i] : d[(H) + i];                          \
-          d[i] = keep + __shfl_xor_sync(0xffffffffu, send, (H));               \
+          const FF keep = up ? d[(H) + i] : d[i];                              \
+          const FF send = up ? d[i] : d[(H) + i];                              \
+          FF got;                                                              \
+          got.hi = __shfl_xor_sync(0xffffffffu, send.hi, (H));                 \
+          got.lo = __shfl_xor_sync(0xffffffffu, send.lo, (H));                 \
+          d[i] = keep;                                                         \
+          ff_add(d[i], got);                                                   \
         }                                                                      \
       }
       AB_COLSUM_STEP(8) AB_COLSUM_STEP(4) AB_COLSUM_STEP(2) AB_COLSUM_STEP(1)
 #undef AB_COLSUM_STEP
       const long long rb = row >> 5;  // row - lane is a multiple of 32
-      if (rb * 32 < p.M && col0 + lane < p.N) p.colsum_ws[rb * p.N + col0 + lane] = d[0];
+      if (rb * 32 < p.M && col0 + lane < p.N) p.colsum_ws[rb * p.N + col0 + lane] = ff_double(d[0]);
     }
 #endif
   }
-  __device__ __forceinline__ void finish_fullsum(double fs, long long row, long long n0, int lane) const {
+  __device__ __forceinline__ void finish_fullsum(const FF& acc, long long row, long long n0, int lane) const {
 #if AB_EP_FULLSUM >= 0
+    double fs = ff_double(acc);
 #pragma unroll
     for (int h = 16; h >= 1; h >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, h);
     const long long rb = row >> 5;
@@ -388,11 +449,16 @@ struct EpilogueOut {
                                               int nchunks, int lane) const {
     const bool live = row < p.M;
     const FusedScalars sc = load_scalars();
-    double fs = 0.0;
+    FF fs = {0.0f, 0.0f};
+    // 128 accumulator registers are live here: the chunk's reads are issued and consumed in
+    // place (this mode spends 3x the tensor time per tile; its epilogue is not the bottleneck)
 #pragma unroll
     for (int c = 0; c < kAccRegs / 32; ++c) {
-      if (c < nchunks)
-        fused_chunk(*reinterpret_cast<float(*)[32]>(&acc[c * 32]), row, n0 + c * 32, live, lane, sc, fs);
+      if (c < nchunks) {
+        ChunkPre pre;
+        prefetch_chunk(pre, row, n0 + c * 32, live, sc);
+        fused_chunk(*reinterpret_cast<float(*)[32]>(&acc[c * 32]), row, n0 + c * 32, live, lane, sc, fs, pre);
+      }
     }
     finish_fullsum(fs, row, n0, lane);
   }
@@ -402,15 +468,19 @@ struct EpilogueOut {
                                                    int lane) const {
     const bool live = row < p.M;
     const FusedScalars sc = load_scalars();
-    double fs = 0.0;
+    FF fs = {0.0f, 0.0f};
+    ChunkPre cur, nxt;
+    prefetch_chunk(cur, row, n0, live, sc);
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
+      if (c + 1 < nchunks) prefetch_chunk(nxt, row, n0 + (c + 1) * 32, live, sc);
       uint32_t r[32];
       tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
       float x[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
-      fused_chunk(x, row, n0 + c * 32, live, lane, sc, fs);
+      fused_chunk(x, row, n0 + c * 32, live, lane, sc, fs, cur);
+      cur = nxt;  // the loads issued above have had the whole chunk to arrive
     }
     finish_fullsum(fs, row, n0, lane);
   }
@@ -495,24 +565,25 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b0)) : "memory");
       int stage = 0;
       uint32_t phase = 0;
+      const OperandLoad la = operand_load_a(p), lb = operand_load_b(p);
+      const int nparts = p.nparts, a_tile_bytes = p.a_tile_bytes, b_tile_bytes = p.b_tile_bytes;
+      const int stages = p.stages, k_per_kb = p.k_elems_per_row, block_n = p.block_n;
       for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         AB_UNIT_DECODE
         const int m0 = (int)(tile_m * BLOCK_M);
-        const int n0 = (int)(tile_n * p.block_n);
+        const int n0 = (int)(tile_n * block_n);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sbase = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          const int kc = kb * p.k_elems_per_row;
-          load_tile(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p, p.a_mn3d);
-          load_tile(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0, p.b_mn,
-                    p.b_chunks, p, p.b_mn3d);
-          if (p.nparts == 2) {
-            load_tile(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p, p.a_mn3d);
-            load_tile(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc, n0,
-                      p.b_mn, p.b_chunks, p, p.b_mn3d);
+          const int kc = kb * k_per_kb;
+          load_tile(sbase, &map_a0, &full_bar[stage], kc, m0, la);
+          load_tile(sbase + nparts * a_tile_bytes, &map_b0, &full_bar[stage], kc, n0, lb);
+          if (nparts == 2) {
+            load_tile(sbase + a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, la);
+            load_tile(sbase + 2 * a_tile_bytes + b_tile_bytes, &map_b1, &full_bar[stage], kc, n0, lb);
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -522,41 +593,46 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
       int stage = 0;
       uint32_t phase = 0;
       uint32_t sit = 0;  // accumulator segments issued by this CTA
+      // loop invariants in registers (see OperandLoad)
+      const int nparts = p.nparts, stages = p.stages, seg_kblocks = p.seg_kblocks;
+      const uint32_t acc_stages = (uint32_t)p.acc_stages, block_n = (uint32_t)p.block_n, idesc = p.idesc;
+      const uint32_t a_tile_bytes = (uint32_t)p.a_tile_bytes, b_tile_bytes = (uint32_t)p.b_tile_bytes;
+      const uint32_t a_kstep = (uint32_t)p.a_kstep, b_kstep = (uint32_t)p.b_kstep;
+      const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
+      const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
       for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         AB_UNIT_DECODE
-        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
-          const int kb1 = min(kb0 + p.seg_kblocks, kb_end);
-          const uint32_t as = sit % (uint32_t)p.acc_stages;
-          const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += seg_kblocks, ++sit) {
+          const int kb1 = min(kb0 + seg_kblocks, kb_end);
+          const uint32_t as = sit % acc_stages;
+          const uint32_t aphase = (sit / acc_stages) & 1u;
           // wait until the epilogue has drained this accumulator stage
           mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
           tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
+          const uint32_t d_tmem = tmem_base + as * block_n;
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
             const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t a_hi = sbase;
-            const uint32_t a_lo = sbase + p.a_tile_bytes;
-            const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
-            const uint32_t b_lo = b_hi + p.b_tile_bytes;
-            const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
-            const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
+            const uint32_t a_lo = sbase + a_tile_bytes;
+            const uint32_t b_hi = sbase + nparts * a_tile_bytes;
+            const uint32_t b_lo = b_hi + b_tile_bytes;
 #pragma unroll
             for (int k = 0; k < SW_BYTES / 32; ++k) {  // 32 bytes of K per instruction
-              const uint32_t ka = k * (uint32_t)p.a_kstep, kb_off = k * (uint32_t)p.b_kstep;
+              const uint32_t ka = k * a_kstep, kb_off = k * b_kstep;
               const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-              if (p.nparts == 2) {
+              if (nparts == 2) {
                 // small cross terms first, the dominant hi*hi term last
-                umma<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
-                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kb_off, b_lbo), p.idesc, 1u);
-                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, 1u);
+                umma<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), idesc, acc);
+                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kb_off, b_lbo), idesc, 1u);
+                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), idesc, 1u);
               } else {
-                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), p.idesc, acc);
+                umma<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kb_off, b_lbo), idesc, acc);
               }
             }
             tcgen05_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
           tcgen05_commit(&tmem_full_bar[as]);  // segment complete
         }
@@ -639,15 +715,14 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
 //     tmem_full barriers of both CTAs;
 //   * all 256 epilogue threads arrive on the leader's tmem_empty barrier.
 __device__ __forceinline__ void load_tile_2sm(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
-                                              int kc, int mn0, int mn_major, int chunks,
-                                              const GemmParams& p, int mn3d = 0) {
-  if (!mn_major) {
+                                              int kc, int mn0, const OperandLoad& o) {
+  if (!o.mn_major) {
     tma_load_2d_2sm(dst, map, bar, kc, mn0);
-  } else if (mn3d) {
-    tma_load_3d_2sm(dst, map, bar, 0, kc, mn0 / p.mn_per_chunk);
+  } else if (o.mn3d) {
+    tma_load_3d_2sm(dst, map, bar, 0, kc, mn0 / o.mn_per_chunk);
   } else {
-    for (int c = 0; c < chunks; ++c)
-      tma_load_2d_2sm(dst + c * p.chunk_bytes, map, bar, mn0 + c * p.mn_per_chunk, kc);
+    for (int c = 0; c < o.chunks; ++c)
+      tma_load_2d_2sm(dst + c * o.chunk_bytes, map, bar, mn0 + c * o.mn_per_chunk, kc);
   }
 }
 // GemmParams here: block_n = 256 (the pair's N tile), b_tile_bytes = 128 rows * 128 B
@@ -667,16 +742,17 @@ __device__ __forceinline__ void load_tile_2sm(uint8_t* dst, const CUtensorMap* m
 //   * tmem_full / tmem_empty stay inside a pair.
 template <int PAIRS>
 __device__ __forceinline__ void load_b_2sm(uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int kc,
-                                           int n0, uint32_t pair, uint16_t mask, const GemmParams& p) {
+                                           int n0, uint32_t pair, uint16_t mask, const OperandLoad& o,
+                                           int b_tile_bytes, int block_n) {
   if (PAIRS == 1) {
-    load_tile_2sm(dst, map, bar, kc, n0, p.b_mn, p.b_chunks, p, p.b_mn3d);
-  } else if (!p.b_mn) {
+    load_tile_2sm(dst, map, bar, kc, n0, o);
+  } else if (!o.mn_major) {
     // K-major: box {128 B of K, block_n / 4 rows}; this CTA's quarter lands behind the twin's
-    tma_load_2d_2sm_mc(dst + pair * (p.b_tile_bytes / 2), map, bar, kc, n0 + (int)pair * (p.block_n / 4), mask);
+    tma_load_2d_2sm_mc(dst + pair * (b_tile_bytes / 2), map, bar, kc, n0 + (int)pair * (block_n / 4), mask);
   } else {
-    const int cpq = p.b_chunks / 2;  // chunks per quarter
+    const int cpq = o.chunks / 2;  // chunks per quarter
     for (int c = (int)pair * cpq; c < ((int)pair + 1) * cpq; ++c)
-      tma_load_2d_2sm_mc(dst + c * p.chunk_bytes, map, bar, n0 + c * p.mn_per_chunk, kc, mask);
+      tma_load_2d_2sm_mc(dst + c * o.chunk_bytes, map, bar, n0 + c * o.mn_per_chunk, kc, mask);
   }
 }
 
@@ -742,25 +818,27 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const OperandLoad la = operand_load_a(p), lb = operand_load_b(p);
+      const int nparts = p.nparts, a_tile_bytes = p.a_tile_bytes, b_tile_bytes = p.b_tile_bytes;
+      const int stages = p.stages, k_per_kb = p.k_elems_per_row, block_n = p.block_n;
       for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
         AB_UNIT_DECODE
         const int m0 = (int)(tile_m * CLUSTER_M) + (int)pair * TILE_M + (int)rank * BLOCK_M;
-        const int n0 = (int)(tile_n * p.block_n) + (int)rank * (p.block_n / 2);
+        const int n0 = (int)(tile_n * block_n) + (int)rank * (block_n / 2);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sbase = smem + (size_t)stage * stage_bytes;
           if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
-          const int kc = kb * p.k_elems_per_row;
-          load_tile_2sm(sbase, &map_a0, &full_bar[stage], kc, m0, p.a_mn, p.a_chunks, p, p.a_mn3d);
-          load_b_2sm<PAIRS>(sbase + p.nparts * p.a_tile_bytes, &map_b0, &full_bar[stage], kc, n0, pair,
-                            twin_mask, p);
-          if (p.nparts == 2) {
-            load_tile_2sm(sbase + p.a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, p.a_mn,
-                          p.a_chunks, p, p.a_mn3d);
-            load_b_2sm<PAIRS>(sbase + 2 * p.a_tile_bytes + p.b_tile_bytes, &map_b1, &full_bar[stage], kc,
-                              n0, pair, twin_mask, p);
+          const int kc = kb * k_per_kb;
+          load_tile_2sm(sbase, &map_a0, &full_bar[stage], kc, m0, la);
+          load_b_2sm<PAIRS>(sbase + nparts * a_tile_bytes, &map_b0, &full_bar[stage], kc, n0, pair,
+                            twin_mask, lb, b_tile_bytes, block_n);
+          if (nparts == 2) {
+            load_tile_2sm(sbase + a_tile_bytes, &map_a1, &full_bar[stage], kc, m0, la);
+            load_b_2sm<PAIRS>(sbase + 2 * a_tile_bytes + b_tile_bytes, &map_b1, &full_bar[stage], kc,
+                              n0, pair, twin_mask, lb, b_tile_bytes, block_n);
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -770,39 +848,44 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
       int stage = 0;
       uint32_t phase = 0;
       uint32_t sit = 0;
+      // loop invariants in registers (see OperandLoad)
+      const int nparts = p.nparts, stages = p.stages, seg_kblocks = p.seg_kblocks;
+      const uint32_t acc_stages = (uint32_t)p.acc_stages, block_n = (uint32_t)p.block_n, idesc = p.idesc;
+      const uint32_t a_tile_bytes = (uint32_t)p.a_tile_bytes, b_tile_bytes = (uint32_t)p.b_tile_bytes;
+      const uint32_t a_kstep = (uint32_t)p.a_kstep, b_kstep = (uint32_t)p.b_kstep;
+      const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
+      const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
       for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
         AB_UNIT_DECODE
-        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += p.seg_kblocks, ++sit) {
-          const int kb1 = min(kb0 + p.seg_kblocks, kb_end);
-          const uint32_t as = sit % (uint32_t)p.acc_stages;
-          const uint32_t aphase = (sit / (uint32_t)p.acc_stages) & 1u;
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += seg_kblocks, ++sit) {
+          const int kb1 = min(kb0 + seg_kblocks, kb_end);
+          const uint32_t as = sit % acc_stages;
+          const uint32_t aphase = (sit / acc_stages) & 1u;
           mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
           tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + as * (uint32_t)p.block_n;
+          const uint32_t d_tmem = tmem_base + as * block_n;
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
             const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t a_hi = sbase;
-            const uint32_t a_lo = sbase + p.a_tile_bytes;
-            const uint32_t b_hi = sbase + p.nparts * p.a_tile_bytes;
-            const uint32_t b_lo = b_hi + p.b_tile_bytes;
-            const uint32_t a_lbo = p.a_mn ? (uint32_t)p.chunk_bytes : 16u;
-            const uint32_t b_lbo = p.b_mn ? (uint32_t)p.chunk_bytes : 16u;
+            const uint32_t a_lo = sbase + a_tile_bytes;
+            const uint32_t b_hi = sbase + nparts * a_tile_bytes;
+            const uint32_t b_lo = b_hi + b_tile_bytes;
 #pragma unroll
             for (int k = 0; k < SW_BYTES / 32; ++k) {
-              const uint32_t ka = k * (uint32_t)p.a_kstep, kbo = k * (uint32_t)p.b_kstep;
+              const uint32_t ka = k * a_kstep, kbo = k * b_kstep;
               const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-              if (p.nparts == 2) {
-                umma_2sm<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
-                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kbo, b_lbo), p.idesc, 1u);
-                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, 1u);
+              if (nparts == 2) {
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_lo + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), idesc, acc);
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_lo + kbo, b_lbo), idesc, 1u);
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), idesc, 1u);
               } else {
-                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), p.idesc, acc);
+                umma_2sm<KIND>(d_tmem, make_smem_desc(a_hi + ka, a_lbo), make_smem_desc(b_hi + kbo, b_lbo), idesc, acc);
               }
             }
             tcgen05_commit_2sm_mask(&empty_bar[stage], all_mask);  // frees the stage in every CTA it is written by
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
           tcgen05_commit_2sm_mask(&tmem_full_bar[as], pair_mask);  // both CTAs' epilogues may fold the segment
         }

@@ -26,9 +26,15 @@ expr = {"inputs": ["float32", "float32"], "out_dtypes": ["float32"], "outputs": 
 kern = K.ElemwiseKernel.get(expr)
 res = {}
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6482.4
-for name, env in (("ab_ew_tile", None), ("ab_ew_nd", "1")):
+VARIANTS = [("ab_ew_tile", None, None), ("ab_ew_nd", "1", None)] + [
+    (f"ab_ew_tile_band{g}", None, str(g)) for g in (1, 2, 4, 16, 32)]
+for name, env, band in VARIANTS:
     if env:
         os.environ["AB_EW_NO_TILE"] = env
+    if band:
+        os.environ["AB_EW_TILE_BAND"] = band
+        kern = K.ElemwiseKernel(expr)      # a fresh module with that tile order
+        os.environ.pop("AB_EW_TILE_BAND")
     ins = [a.dimshuffle([1, 0]), b]
     for _ in range(3):
         kern.launch((n, n), ins, [out])

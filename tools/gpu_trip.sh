@@ -53,7 +53,7 @@ case $sec in
     N=$(nvidia-smi -L | wc -l)
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --workload logreg --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_logreg_n$N.json 2> gpurun_out/bench_logreg_n$N.err; echo "scale_logreg N=$N rc=$?"; tail -3 gpurun_out/bench_logreg_n$N.err | cut -c1-300; python -c "import json;d=json.loads([l for l in open('gpurun_out/bench_logreg_n$N.json') if l.startswith('{')][-1]);print(d['n_gpus'], d['value'], d['ms_per_step'], d['config']['executor'], d.get('parity_sharded'), d.get('exchange'))";;
   ew_probe)
-    timeout 300 python tools/ew_probe.py 2>&1 | tail -3;;
+    timeout 300 python tools/ew_probe.py 2>&1 | tail -8;;
   reference)
     timeout 500 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"; tail -2 gpurun_out/bench_reference.err; cut -c1-1200 gpurun_out/bench_reference.json;;
   smoke)
