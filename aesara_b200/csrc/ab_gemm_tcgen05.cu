@@ -248,7 +248,7 @@ struct PackedOperand {
 // to the tensor cores.  `direct` = usable in place (precision 1 only: raw fp32, aligned).
 static void plan_operand(int precision, long long rows, long long k, long long s_r, long long s_k,
                          const void* ptr, bool* direct, int* mn_major, long long* pitch,
-                         size_t* plane_bytes) {
+                         size_t* plane_bytes, bool force_k = false) {
   const int es = precision == 2 ? 2 : 4;
   const bool aligned = (reinterpret_cast<uintptr_t>(ptr) % 16 == 0);
   if (s_k == 1 || k == 1) {
@@ -256,7 +256,7 @@ static void plan_operand(int precision, long long rows, long long k, long long s
     *direct = precision == 1 && aligned && (s_r % 4 == 0) && s_r >= k;
     *pitch = *direct ? s_r : (long long)align_up((size_t)k, 16 / es);
     *plane_bytes = *direct ? 0 : align_up((size_t)rows * (size_t)*pitch * es, 1024);
-  } else if (s_r == 1 && precision == 2 && getenv("AB_GEMM_NO_MN") == nullptr) {
+  } else if (s_r == 1 && precision == 2 && !force_k && getenv("AB_GEMM_NO_MN") == nullptr) {
     // MN-major is used for 16-bit operands only: a 32-bit (TF32) MN-major operand needs the
     // SWIZZLE_128B_BASE32B shared-memory layout (and the matching 32B-atom TMA swizzle);
     // TF32 operands that are not K-contiguous are gathered into a K-major plane below.
@@ -272,22 +272,25 @@ static void plan_operand(int precision, long long rows, long long k, long long s
   }
 }
 
-size_t gemm_pack_bytes(int precision, long long rows, long long k, long long s_r, long long s_k) {
+size_t gemm_pack_bytes(int precision, long long rows, long long k, long long s_r, long long s_k,
+                       bool force_k = false) {
   bool direct;
   int mn;
   long long pitch;
   size_t pb;
-  plan_operand(precision, rows, k, s_r, s_k, reinterpret_cast<const void*>(1), &direct, &mn, &pitch, &pb);
+  plan_operand(precision, rows, k, s_r, s_k, reinterpret_cast<const void*>(1), &direct, &mn, &pitch, &pb,
+               force_k);
   return (precision == 0 ? 2 : 1) * pb + 1024;
 }
 
 int gemm_pack(int precision, const float* src, long long rows, long long k, long long s_r,
-              long long s_k, void* dst, size_t dst_bytes, PackedOperand* out, cudaStream_t st) {
+              long long s_k, void* dst, size_t dst_bytes, PackedOperand* out, cudaStream_t st,
+              bool force_k = false) {
   bool direct;
   int mn;
   long long pitch;
   size_t pb;
-  plan_operand(precision, rows, k, s_r, s_k, src, &direct, &mn, &pitch, &pb);
+  plan_operand(precision, rows, k, s_r, s_k, src, &direct, &mn, &pitch, &pb, force_k);
   out->rows = rows; out->k = k; out->pitch = pitch; out->mn_major = mn; out->precision = precision;
   out->plane[0] = src; out->plane[1] = nullptr;
   if (direct) return AB_OK;
@@ -380,7 +383,7 @@ int g_cluster4_resident = 0;  // resident 4-CTA clusters reported by the driver 
 int cluster4_groups() { return g_cluster4_resident > 0 ? g_cluster4_resident : sm_count() / 4; }
 
 int plan_k_splits(int precision, long long M, long long N, long long K) {
-  static const char* env = getenv("AB_GEMM_SPLITK");  // 0/1 = off, n = force n ranges
+  const char* env = getenv("AB_GEMM_SPLITK");  // 0/1 = off, n = force n ranges
   const bool two = use_two_cta(M, N);
   const int pairs = cluster_pairs(M, N);
   const long long block_n = two ? 256 : (N >= 256 ? 256 : (N >= 128 ? 128 : 64));
@@ -452,6 +455,8 @@ struct EpilogueSpec {
   long long out_rs[3] = {};
   void* shadow[3] = {};
   long long shadow_pitch[3] = {};
+  void* shadow_t = nullptr;    // transposed bf16 plane of the module's AB_EP_TPLANE value, [N, pitch]
+  long long shadow_t_pitch = 0;
   double* colsum_ws = nullptr;
   double* fullsum_ws = nullptr;
 };
@@ -596,6 +601,11 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
       p.shadow[k] = ep->shadow[k]; p.shadow_pitch[k] = ep->shadow_pitch[k];
       p.out_ptr[k] = ep->out_ptr[k]; p.out_rs[k] = ep->out_rs[k];
     }
+    if (ep->shadow_t && ((reinterpret_cast<uintptr_t>(ep->shadow_t) & 15) || (ep->shadow_t_pitch & 7) ||
+                         ep->shadow_t_pitch < M))
+      return fail(AB_ERR_UNSUPPORTED, "transposed bf16 shadow plane rows are not 16-byte aligned / too short");
+    p.shadow_t = ep->shadow_t;
+    p.shadow_t_pitch = ep->shadow_t_pitch;
     p.colsum_ws = ep->colsum_ws;
     p.fullsum_ws = ep->fullsum_ws;
     p.fullsum_cols = 2 * ((N + p.block_n - 1) / p.block_n);
@@ -645,7 +655,10 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
       }
       if (pairs == 2) g_cluster4_resident = res;
     }
-    const long long clusters = std::min<long long>(tiles2, res);
+    long long clusters = std::min<long long>(tiles2, res);
+    // measurement knob: run on fewer SM pairs (does the per-CTA rate rise when fewer CTAs
+    // share L2 / the crossbar / the power budget?)
+    if (const char* cap = getenv("AB_GEMM_MAX_CLUSTERS")) clusters = std::max<long long>(1, std::min<long long>(clusters, atoll(cap)));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(ctas * clusters));
     cfg.blockDim = dim3(kThreads);
@@ -757,6 +770,32 @@ extern "C" int ab_gemm_pack(int precision, const void* src, int64_t rows, int64_
   return AB_OK;
 }
 
+// The same with the planes forced K-major ([rows, pitch], K contiguous) whatever the strides:
+// a view that is contiguous along its rows (the transpose of a row-major matrix) is turned
+// while it is packed.  For small matrices (weights) that are read with the contraction along
+// their rows: tcgen05.mma reads a K-major operand at full rate, an MN-major one costs 10-28 %
+// of the tensor pipe's cycles (profiles/r02_dw_layouts_ncu.txt).
+extern "C" int ab_gemm_pack_kmajor_bytes(int precision, int64_t rows, int64_t k, int64_t s_r,
+                                         int64_t s_k, size_t* bytes) {
+  if (!bytes) return ab::fail(AB_ERR_INVALID, "null out pointer");
+  *bytes = ab::gemm_pack_bytes(precision, rows, k, s_r, s_k, true);
+  return AB_OK;
+}
+
+extern "C" int ab_gemm_pack_kmajor(int precision, const void* src, int64_t rows, int64_t k,
+                                   int64_t s_r, int64_t s_k, void* dst, size_t dst_bytes,
+                                   ab_gemm_operand* out, void* stream) {
+  if (!out) return ab::fail(AB_ERR_INVALID, "null ab_gemm_operand");
+  ab::PackedOperand po{};
+  int rc = ab::gemm_pack(precision, static_cast<const float*>(src), rows, k, s_r, s_k, dst,
+                         dst_bytes, &po, ab::as_stream(stream), true);
+  if (rc) return rc;
+  out->plane0 = po.plane[0]; out->plane1 = po.plane[1];
+  out->rows = po.rows; out->k = po.k; out->pitch = po.pitch;
+  out->mn_major = po.mn_major; out->precision = po.precision;
+  return AB_OK;
+}
+
 extern "C" int ab_gemm_packed(int precision, int64_t m, int64_t n, int64_t k, double alpha,
                               const ab_gemm_operand* A, const ab_gemm_operand* B, double beta,
                               const void* Cin, int64_t cin_rs, int64_t cin_cs, void* C,
@@ -797,6 +836,8 @@ extern "C" int ab_gemm_packed_fused(int precision, int64_t m, int64_t n, int64_t
     spec.shadow[i] = ep->shadow_bf16[i];
     spec.shadow_pitch[i] = ep->shadow_pitch[i];
   }
+  spec.shadow_t = ep->shadow_t_bf16;
+  spec.shadow_t_pitch = ep->shadow_t_pitch;
   spec.colsum_ws = static_cast<double*>(ep->colsum_ws);
   spec.fullsum_ws = static_cast<double*>(ep->fullsum_ws);
   return ab::gemm_run(precision, m, n, k, (float)alpha, pa, pb, (float)beta, static_cast<float*>(C),

@@ -49,6 +49,13 @@ struct GemmParams {
   long long out_rs[3];
   void* shadow[3];
   long long shadow_pitch[3];
+  // shadow_t (optional, value AB_EP_TPLANE only): the TRANSPOSED bf16 copy, an [N, shadow_t_pitch]
+  // plane whose rows are the columns of the value -- the K-major operand of a product that
+  // contracts over the ROWS of the value (h.T @ dout, X.T @ dpre: both operands of a weight
+  // gradient).  Read as an MN-major operand instead, the natural plane costs the tensor pipe
+  // 10-28 % of its cycles (profiles/r02_dw_layouts_ncu.txt).
+  void* shadow_t;
+  long long shadow_t_pitch;
   // reductions of one value each, accumulated in float64 like the reference's CAReduce
   // (tensor/elemwise.py:1371-1385): colsum_ws[rb][col] = sum over the 32 rows of row block
   // rb of value AB_EP_COLSUM; fullsum_ws[rb][cb] = sum of value AB_EP_FULLSUM over row block
@@ -241,7 +248,7 @@ struct EpilogueOut {
   // columns of a thread (tanh, IEEE division, float64 sums per element) is several hundred KB
   // of SASS, which every warp re-fetches from L2 for every tile (measured: the region with
   // two values and two reductions ran 1.5 ms slower than its five separate kernels).
-  struct FusedScalars { float v[4]; bool is[4]; };
+  struct FusedScalars { float v[4]; bool is[4]; bool vec[4]; };
   // Sums of the region are kept as unevaluated float pairs (hi + lo, error-free TwoSum) while
   // they stay inside a thread or a warp, and become float64 where they leave it: the FP64
   // pipe of this part retires a warp-wide DADD every ~20 cycles, and one DADD + one F2F.F64
@@ -272,6 +279,7 @@ struct EpilogueOut {
     for (int k = 0; k < 4; ++k) {
       s.is[k] = k < AB_EP_NOPS && p.ep_rs[k] == 0 && p.ep_cs[k] == 0;  // a [1,1] operand
       s.v[k] = s.is[k] ? p.ep_ptr[k][0] : 0.0f;
+      s.vec[k] = k < AB_EP_NOPS && p.ep_rs[k] == 0 && p.ep_cs[k] == 1;  // a [1,N] row (a bias)
     }
     return s;
   }
@@ -300,6 +308,13 @@ struct EpilogueOut {
   // 52-66 % active against 71-74 % without such a read, profiles/r02_bench_step_ncu.txt);
   // loaded per chunk but consumed at once, it still waits one DRAM latency per chunk (19 % of
   // the epilogue warps' samples, profiles/r02_region2_fp64_stalls.txt).
+  //
+  // A [1, N] operand (a bias row) is the same for all 32 rows of a warp: lane l fetches the
+  // value of column col0 + l (one coalesced 128-byte read per chunk, a chunk ahead like the
+  // matrices) and the evaluation takes column j's value from lane j by shuffle.  Read through
+  // ld8 per column group instead, every one of the four groups of a chunk waits for an L2
+  // round trip (L1 is swept by the matrix reads): 13 % of the epilogue warps' samples in the
+  // region with Y and b2 (profiles/r02_region2_after_pairs.txt).
   struct ChunkPre {
 #if AB_EP_CIN
     float cin[32];
@@ -307,11 +322,15 @@ struct EpilogueOut {
 #if AB_EP_PRE_OP >= 0
     float op[32];
 #endif
+    float vec[AB_EP_NOPS > 0 ? AB_EP_NOPS : 1];
   };
   __device__ __forceinline__ void prefetch_chunk(ChunkPre& pre, long long row, long long col0, bool live,
-                                                 const FusedScalars& sc) const {
+                                                 const FusedScalars& sc, int lane) const {
     const long long r = live ? row : 0;
     (void)r; (void)sc; (void)pre; (void)col0;
+#pragma unroll
+    for (int k = 0; k < AB_EP_NOPS; ++k)
+      if (sc.vec[k]) pre.vec[k] = (col0 + lane < p.N) ? __ldg(p.ep_ptr[k] + col0 + lane) : 0.0f;
 #if AB_EP_CIN
     if (live && p.beta != 0.0f) {
 #pragma unroll
@@ -341,6 +360,15 @@ struct EpilogueOut {
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       const long long col = col0 + j;
+      // row operands: column j + t's value sits in lane j + t (all 32 lanes take part)
+      float ev[AB_EP_NOPS > 0 ? AB_EP_NOPS : 1][8];
+#pragma unroll
+      for (int k = 0; k < AB_EP_NOPS; ++k) {
+        if (sc.vec[k]) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) ev[k][t] = __shfl_sync(0xffffffffu, pre.vec[k], j + t);
+        }
+      }
       if (live && col < p.N) {  // N % 8 == 0: a group of 8 columns is inside or outside as a whole
         float v[8];
 #pragma unroll
@@ -366,7 +394,10 @@ struct EpilogueOut {
             continue;
           }
 #endif
-          if (sc.is[k]) {
+          if (sc.vec[k]) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) e[k][t] = ev[k][t];
+          } else if (sc.is[k]) {
 #pragma unroll
             for (int t = 0; t < 8; ++t) e[k][t] = sc.v[k];
           } else if (p.ep_cs[k] == 1) {
@@ -385,13 +416,16 @@ struct EpilogueOut {
 #if AB_EP_COLSUM >= 0
 #pragma unroll
         for (int t = 0; t < 8; ++t) x[j + t] = o[AB_EP_COLSUM][t];
+#elif AB_EP_TPLANE >= 0
+#pragma unroll
+        for (int t = 0; t < 8; ++t) x[j + t] = o[AB_EP_TPLANE][t];
 #endif
 #if AB_EP_FULLSUM >= 0
 #pragma unroll
         for (int t = 0; t < 8; ++t) ff_add(fs, o[AB_EP_FULLSUM][t]);
 #endif
       } else {
-#if AB_EP_COLSUM >= 0
+#if AB_EP_COLSUM >= 0 || AB_EP_TPLANE >= 0
 #pragma unroll
         for (int t = 0; t < 8; ++t) x[j + t] = 0.0f;
 #endif
@@ -434,6 +468,51 @@ struct EpilogueOut {
       if (rb * 32 < p.M && col0 + lane < p.N) p.colsum_ws[rb * p.N + col0 + lane] = ff_double(d[0]);
     }
 #endif
+#if AB_EP_TPLANE >= 0
+    // (AB_EP_COLSUM, when present, is the same value: x[] holds it)
+    if (p.shadow_t) {
+      // 32 x 32 transpose in registers: after the exchange with distance h, register i of lane l
+      // holds what register (i ^ h) of lane (l ^ h) held if bit h of i and l differ.  Five
+      // steps turn "lane = row, register = column" into "lane = column, register = row".
+#define AB_T_STEP(H)                                                            \
+      {                                                                         \
+        const bool up = (lane & (H)) != 0;                                      \
+        _Pragma("unroll") for (int i = 0; i < 32; ++i) {                        \
+          if ((i & (H)) == 0) {                                                 \
+            const float send = up ? x[i] : x[i | (H)];                          \
+            const float got = __shfl_xor_sync(0xffffffffu, send, (H));          \
+            if (up) x[i] = got; else x[i | (H)] = got;                          \
+          }                                                                     \
+        }                                                                       \
+      }
+      AB_T_STEP(16) AB_T_STEP(8) AB_T_STEP(4) AB_T_STEP(2) AB_T_STEP(1)
+#undef AB_T_STEP
+      // lane l: column col0 + l, x[i] = its value in row (row - lane) + i: 32 consecutive
+      // bf16 = 64 contiguous bytes of the transposed plane
+      const long long row0 = row - lane;
+      const long long c = col0 + lane;
+      if (c < p.N && row0 < p.M) {
+        uint16_t* dst = static_cast<uint16_t*>(p.shadow_t) + c * p.shadow_t_pitch + row0;
+        if (row0 + 32 <= p.M) {
+          uint32_t h[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t)
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[t]) : "f"(x[2 * t + 1]), "f"(x[2 * t]));
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            reinterpret_cast<uint4*>(dst)[t] = make_uint4(h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (row0 + i < p.M) {
+              uint16_t b;
+              asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(b) : "f"(x[i]));
+              dst[i] = b;
+            }
+        }
+      }
+    }
+#endif
   }
   __device__ __forceinline__ void finish_fullsum(const FF& acc, long long row, long long n0, int lane) const {
 #if AB_EP_FULLSUM >= 0
@@ -456,7 +535,7 @@ struct EpilogueOut {
     for (int c = 0; c < kAccRegs / 32; ++c) {
       if (c < nchunks) {
         ChunkPre pre;
-        prefetch_chunk(pre, row, n0 + c * 32, live, sc);
+        prefetch_chunk(pre, row, n0 + c * 32, live, sc, lane);
         fused_chunk(*reinterpret_cast<float(*)[32]>(&acc[c * 32]), row, n0 + c * 32, live, lane, sc, fs, pre);
       }
     }
@@ -469,18 +548,31 @@ struct EpilogueOut {
     const bool live = row < p.M;
     const FusedScalars sc = load_scalars();
     FF fs = {0.0f, 0.0f};
-    ChunkPre cur, nxt;
-    prefetch_chunk(cur, row, n0, live, sc);
+    // two buffers used alternately by a loop body that handles two chunks (a copy `cur = nxt`
+    // at the end of a one-chunk body was scheduled by the compiler right behind the loads it
+    // copies: it waited for them there, and the read-ahead hid nothing)
+    ChunkPre pa, pb;
+    prefetch_chunk(pa, row, n0, live, sc, lane);
 #pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
-      if (c + 1 < nchunks) prefetch_chunk(nxt, row, n0 + (c + 1) * 32, live, sc);
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
-      float x[32];
+    for (int c = 0; c < nchunks; c += 2) {
+      if (c + 1 < nchunks) prefetch_chunk(pb, row, n0 + (c + 1) * 32, live, sc, lane);
+      {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
+        float x[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
-      fused_chunk(x, row, n0 + c * 32, live, lane, sc, fs, cur);
-      cur = nxt;  // the loads issued above have had the whole chunk to arrive
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+        fused_chunk(x, row, n0 + c * 32, live, lane, sc, fs, pa);
+      }
+      if (c + 1 < nchunks) {
+        if (c + 2 < nchunks) prefetch_chunk(pa, row, n0 + (c + 2) * 32, live, sc, lane);
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_acc + (uint32_t)((c + 1) * 32), r);
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+        fused_chunk(x, row, n0 + (c + 1) * 32, live, lane, sc, fs, pb);
+      }
     }
     finish_fullsum(fs, row, n0, lane);
   }

@@ -47,18 +47,56 @@ class EpilogueRequest:
     def __init__(self, fusion, operands, out_plan, colsum, fullsum):
         self.fusion = fusion
         self.operands = operands          # DeviceArrays (2-D, broadcastable over [M, N])
-        self.out_plan = out_plan          # per value: (store float32, write the bf16 plane)
+        self.out_plan = out_plan          # per value: (store float32, write the bf16 plane, write the transposed plane)
         self.colsum = colsum              # the module accumulates column sums / a total
         self.fullsum = fullsum
         self.applied = False
         self.arrays = None                # per value: DeviceArray [M, N] (written iff stored)
         self.shadows = None               # per value: (torch buffer, pitch) or None
+        self.tshadows = None              # per value: (torch buffer, pitch) of the TRANSPOSED plane or None
         self.colsum_ws = None             # DeviceArray float64 [row_blocks, N]
         self.fullsum_ws = None            # DeviceArray float64 [row_blocks * cols]
 
 
 def _gemm_operands(node):
     return (node.inputs[2], node.inputs[3]) if node.op == "Gemm" else (node.inputs[0], node.inputs[1])
+
+
+def _plane_users(program, v):
+    """How tensor-core products read the row-major matrix ``v``: ``(natural, transposed)`` lists
+    of GEMM node indices.  *natural*: the contraction runs along the columns of ``v`` (``v`` as
+    the left operand, ``v.T`` as the right one) -- its bf16 plane is K-major as written.
+    *transposed*: the contraction runs along the ROWS of ``v`` (``v`` as the right operand,
+    ``v.T`` as the left one: both operands of a weight gradient ``X.T @ G``) -- K-major only
+    in the transposed plane."""
+    cons = getattr(program, "_ab_consumers", None)
+    if cons is None:
+        cons = {}
+        for i, n in enumerate(program.nodes):
+            for w in n.inputs:
+                cons.setdefault(w, []).append(i)
+        program._ab_consumers = cons
+    nodes = program.nodes
+    nat, tr = [], []
+    for c in cons.get(v, []):
+        cn = nodes[c]
+        if cn.op in GEMM_OPS:
+            xv, yv = _gemm_operands(cn)
+            if xv == v:
+                nat.append(c)
+            if yv == v:
+                tr.append(c)
+        elif cn.op == "DimShuffle" and list(cn.params.get("new_order", [])) == [1, 0]:
+            t = cn.outputs[0]
+            for c2 in cons.get(t, []):
+                n2 = nodes[c2]
+                if n2.op in GEMM_OPS:
+                    xv, yv = _gemm_operands(n2)
+                    if xv == t:
+                        tr.append(c2)
+                    if yv == t:
+                        nat.append(c2)
+    return nat, tr
 
 
 class GemmEpilogueFusion:
@@ -80,6 +118,12 @@ class GemmEpilogueFusion:
         self.colsum = next((k for _, kind, k in reds if kind == "col"), -1)
         self.fullsum = next((k for _, kind, k in reds if kind == "full"), -1)
         self.shadow_consumer = any(v is not None and self._gemm_consumers(v) for v in out_vars)
+        # the one value whose transposed bf16 plane the module can write (shares its registers
+        # with the column sums, so it has to be that value when the region has column sums)
+        cand = [k for k, v in enumerate(out_vars) if v is not None and _plane_users(program, v)[1]]
+        if os.environ.get("AB_EP_NO_TPLANE"):
+            cand = []
+        self.tplane = (self.colsum if self.colsum in cand else -1) if self.colsum >= 0 else (cand[0] if cand else -1)
         self.broken = False
         self.f32_skipped = 0                  # values kept as a bf16 plane only (last run)
         self._src = None
@@ -286,7 +330,8 @@ class GemmEpilogueFusion:
                     pre_op = k
                     break
             self._src = gemm_region_source(merged, len(self.operand_vars), self.colsum, self.fullsum,
-                                           cin=prog.nodes[self.g].op == "Gemm", pre_op=pre_op)
+                                           cin=prog.nodes[self.g].op == "Gemm", pre_op=pre_op,
+                                           tplane=self.tplane)
         return self._src
 
     def compile_all(self):
@@ -319,13 +364,18 @@ class GemmEpilogueFusion:
             if a.dtype != np.float32 or a.ndim != 2 or a.shape[0] not in (1, M) or a.shape[1] not in (1, N):
                 return False
         plan = []
-        for v in self.out_vars:
+        for k, v in enumerate(self.out_vars):
             if v is None:
-                plan.append((False, False))  # reduction source only
+                plan.append((False, False, False))  # reduction source only
                 continue
-            shadow = ex.precision == 2 and N % 8 == 0 and bool(self._gemm_consumers(v))
-            store = not (shadow and self._plane_only_ok(ex, env, v, (M, N)))
-            plan.append((store, shadow))
+            planes = ex.precision == 2 and N % 8 == 0
+            nat_users, t_users = _plane_users(prog, v)
+            tshadow = planes and k == self.tplane and bool(t_users)
+            # products that contract over the rows of v and find no transposed plane read the
+            # natural one as an MN-major operand
+            shadow = planes and (bool(nat_users) or (bool(t_users) and not tshadow))
+            store = not ((shadow or tshadow) and self._plane_only_ok(ex, env, v, (M, N)))
+            plan.append((store, shadow, tshadow))
         req = EpilogueRequest(self, ops, plan, self.colsum >= 0, self.fullsum >= 0)
         ex._gemm_epilogue = req
         try:
@@ -349,8 +399,11 @@ class GemmEpilogueFusion:
             env[v] = req.arrays[k]
             if req.shadows[k] is not None:
                 ex.pack_cache.adopt(req.arrays[k], *req.shadows[k])
+            if req.tshadows[k] is not None:
+                ex.pack_cache.adopt(req.arrays[k], *req.tshadows[k], transposed=True)
             if not plan[k][0]:
                 self.f32_skipped += 1
+                ex.pack_cache.never_stored(req.arrays[k])
         for c, kind, _k in self.reds:
             rn = nodes[c]
             ws = req.colsum_ws if kind == "col" else req.fullsum_ws

@@ -269,18 +269,47 @@ class PackCache:
             for k in dead:
                 del self._e[k]
 
-    def adopt(self, arr: DeviceArray, buf, pitch):
+    # a matrix that is read with the contraction along its ROWS and has at most this many
+    # elements (weights) gets a transposed, K-major plane from a transposing pack; larger ones
+    # are read as MN-major operands of their natural plane (the pack would cost more than the
+    # tensor-pipe cycles it saves)
+    TRANSPOSE_PACK_MAX = 64 * 1024 * 1024
+
+    def never_stored(self, arr: DeviceArray):
+        """``arr`` exists as bf16 plane(s) only (its float32 buffer was not written by the
+        epilogue that produced it): packing from it would read garbage -- fail loudly."""
+        self._unstored = getattr(self, "_unstored", {})
+        self._unstored[arr.ptr] = arr.owner
+
+    def adopt(self, arr: DeviceArray, buf, pitch, transposed=False):
         """Register a bf16 plane written by a fused GEMM epilogue as the pack of ``arr``
-        ([rows, k] float32, K-contiguous): the next product reads it without a pack pass."""
+        ([rows, k] float32, K-contiguous): the next product reads it without a pack pass.
+        ``transposed``: the plane holds ``arr.T`` ([k, pitch] rows): the K-major operand of
+        products that contract over the rows of ``arr``."""
         import weakref
 
         rows, k = arr.shape
-        key = (arr.ptr, rows, k, arr.strides[0], 0, 2)
+        key = (arr.ptr, rows, k, arr.strides[0], 0, 2) + (("T",) if transposed else ())
         try:
             ref = weakref.ref(arr.owner)
         except TypeError:
             ref = (lambda o: (lambda: o))(arr.owner)
         self._e[key] = (ref, buf.data_ptr(), None, pitch, buf)
+
+    @staticmethod
+    def _ref(owner):
+        import weakref
+
+        try:
+            return weakref.ref(owner)
+        except TypeError:
+            return (lambda o: (lambda: o))(owner)
+
+    def _check_stored(self, arr):
+        un = getattr(self, "_unstored", None)
+        if un and un.get(arr.ptr) is arr.owner:
+            raise RuntimeError("PackCache: asked to pack a matrix that was kept as a bf16 plane only "
+                               "(the fused epilogue did not store its float32 values)")
 
     def operand(self, arr: DeviceArray, rows, k, s_r, s_k, precision):
         import weakref
@@ -296,10 +325,29 @@ class PackCache:
         else:
             canon = (arr.ptr, rows, k, s_r, s_k)
         key = canon + (precision,)
+        mn_use = not (s_k == 1 or k == 1) and s_r == 1 and share
+        if mn_use:
+            # contraction along the rows of the natural matrix: a transposed plane (written by
+            # the epilogue that produced the matrix, or packed here for a small one) is K-major
+            tkey = key + ("T",)
+            ent = self._e.get(tkey)
+            if ent is None and key not in self._e and rows * k <= self.TRANSPOSE_PACK_MAX \
+                    and not os.environ.get("AB_GEMM_NO_TPACK"):
+                self._check_stored(arr)
+                nbytes = C.c_size_t()
+                _lib.check(lib.ab_gemm_pack_kmajor_bytes(precision, rows, k, s_r, s_k, C.byref(nbytes)))
+                buf = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=arr.owner.device)
+                op = _lib.GemmOperand()
+                _lib.check(lib.ab_gemm_pack_kmajor(precision, arr.ptr, rows, k, s_r, s_k, buf.data_ptr(),
+                                                   nbytes.value, C.byref(op), stream_handle()))
+                ent = self._e[tkey] = (self._ref(arr.owner), op.plane0, None, op.pitch, buf)
+            if ent is not None and ent[0]() is arr.owner:
+                return _lib.GemmOperand(ent[1], None, rows, k, ent[3], 0, precision)
         ent = self._e.get(key)
         if ent is not None and ent[0]() is arr.owner:
             _, p0, p1, pitch, _buf = ent
         else:
+            self._check_stored(arr)
             nbytes = C.c_size_t()
             _lib.check(lib.ab_gemm_pack_bytes(precision, rows, k, s_r, s_k, C.byref(nbytes)))
             buf = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=arr.owner.device)
@@ -340,8 +388,8 @@ def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision
                 ep.cs[i] = 0 if a.shape[1] == 1 else a.strides[1]
             plan = epilogue.out_plan
             ep.n_outputs = len(plan)
-            arrays, shadows = [], []
-            for i, (store, want_shadow) in enumerate(plan):
+            arrays, shadows, tshadows = [], [], []
+            for i, (store, want_shadow, want_t) in enumerate(plan):
                 # value 0 lives in C_; a value that is not stored still gets its (unwritten)
                 # float32 buffer: it is what identifies the bf16 plane in the pack cache
                 arr = C_ if i == 0 else DeviceArray.empty((m, n), "float32")
@@ -356,6 +404,14 @@ def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision
                     ep.shadow_pitch[i] = n
                     sh = (buf, n)
                 shadows.append(sh)
+                tsh = None
+                if want_t and arr.strides == (n, 1):
+                    pitch_t = (m + 7) // 8 * 8
+                    tbuf = torch.empty(n * pitch_t * 2, dtype=torch.uint8, device=A.owner.device)
+                    ep.shadow_t_bf16 = tbuf.data_ptr()
+                    ep.shadow_t_pitch = pitch_t
+                    tsh = (tbuf, pitch_t)
+                tshadows.append(tsh)
             if epilogue.colsum or epilogue.fullsum:
                 rows, cols = C.c_int64(), C.c_int64()
                 _lib.check(lib.ab_gemm_fused_layout(m, n, C.byref(rows), C.byref(cols)))
@@ -370,7 +426,7 @@ def gemm(C_: DeviceArray, alpha, A: DeviceArray, B: DeviceArray, beta, precision
                                                 float(beta), *cin_args, c_ptr, C_.strides[0],
                                                 C_.strides[1], C.byref(ep), stream_handle()))
             epilogue.applied = True
-            epilogue.arrays, epilogue.shadows = arrays, shadows
+            epilogue.arrays, epilogue.shadows, epilogue.tshadows = arrays, shadows, tshadows
             return
         need = C.c_size_t()
         _lib.check(lib.ab_gemm_packed_workspace_bytes(precision, m, n, k, C.byref(need)))

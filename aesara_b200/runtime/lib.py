@@ -126,6 +126,14 @@ SIGNATURES = {
         [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t,
          C.c_void_p, C.c_void_p],
     ),
+    "ab_gemm_pack_kmajor_bytes": (
+        C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]
+    ),
+    "ab_gemm_pack_kmajor": (
+        C.c_int,
+        [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t,
+         C.c_void_p, C.c_void_p],
+    ),
     "ab_gemm_packed": (
         C.c_int,
         [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_double,
@@ -207,6 +215,8 @@ class GemmEpilogue(C.Structure):
         ("shadow_pitch", C.c_int64 * 3),
         ("colsum_ws", C.c_void_p),
         ("fullsum_ws", C.c_void_p),
+        ("shadow_t_bf16", C.c_void_p),
+        ("shadow_t_pitch", C.c_int64),
     ]
 
 

@@ -166,6 +166,14 @@ int ab_gemm_pack_bytes(int precision, int64_t rows, int64_t k, int64_t s_r, int6
                        size_t* bytes);
 int ab_gemm_pack(int precision, const void* src, int64_t rows, int64_t k, int64_t s_r,
                  int64_t s_k, void* dst, size_t dst_bytes, ab_gemm_operand* out, void* stream);
+/* The same with the planes forced K-major whatever the strides (a row-contiguous view, i.e.
+ * the transpose of a row-major matrix, is turned while it is packed): for small matrices
+ * (weights) that a product reads with the contraction along their rows. */
+int ab_gemm_pack_kmajor_bytes(int precision, int64_t rows, int64_t k, int64_t s_r, int64_t s_k,
+                              size_t* bytes);
+int ab_gemm_pack_kmajor(int precision, const void* src, int64_t rows, int64_t k, int64_t s_r,
+                        int64_t s_k, void* dst, size_t dst_bytes, ab_gemm_operand* out,
+                        void* stream);
 /* C <- beta*Cin + alpha*A@B.  Cin == NULL means in place (Cin = C); a separate Cin is
  * the Gemm{no_inplace} case (blas.py:1065-1093) without the copy of z.  `workspace` is
  * optional scratch for split-K (ab_gemm_packed_workspace_bytes; 0 bytes = not wanted):
@@ -185,6 +193,10 @@ int ab_gemm_packed_workspace_bytes(int precision, int64_t m, int64_t n, int64_t 
  * value k >= 1 to out_f32[k] ([m, out_rs[k]] rows, unit column stride; NULL: not stored).
  * `shadow_bf16[k]` (optional) receives the bf16 copy of value k as a [m, shadow_pitch[k]]
  * plane: the packed operand of the next product (replaces ab_gemm_pack for that matrix).
+ * `shadow_t_bf16` (optional; modules generated with a transposed-plane value) receives the
+ * TRANSPOSED bf16 copy of that value, an [n, shadow_t_pitch] plane (pitch >= m, % 8 == 0): the
+ * K-major operand of a product that contracts over the rows of the value (X.T @ value,
+ * value.T @ Y -- the weight gradients of tensor/blas.py:1650 Dot22 in a backward pass).
  * Reductions the module was generated with (tensor/elemwise.py:1221 CAReduce{add}, float64
  * accumulators like the reference): column sums of one value as partials per 32-row block,
  * colsum_ws[row_blocks][n]; the sum of all elements of one value as partials
@@ -202,6 +214,8 @@ typedef struct {
   int64_t shadow_pitch[3];
   void* colsum_ws;
   void* fullsum_ws;
+  void* shadow_t_bf16;
+  int64_t shadow_t_pitch;
 } ab_gemm_epilogue;
 int ab_gemm_fused_layout(int64_t m, int64_t n, int64_t* row_blocks, int64_t* fullsum_cols);
 int ab_gemm_packed_fused(int precision, int64_t m, int64_t n, int64_t k, double alpha,

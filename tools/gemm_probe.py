@@ -27,15 +27,33 @@ shapes = {
     "dh   D[B,H] @ W.T         (A K-major, B K-major)": (dD, dW.dimshuffle([1, 0]), (B, H)),
     "dW   X.T[H,B] @ D[B,H]    (A MN-major, B MN-major, K=65536)": (dX.dimshuffle([1, 0]), dD, (H, H)),
 }
+if os.environ.get("PROBE_DW_LAYOUTS"):
+    # the same product with materialised transposes: which operand layout costs what
+    Xt = X.t().contiguous()
+    Dt = D.t().contiguous()
+    dXt, dDt = DeviceArray.from_torch(Xt), DeviceArray.from_torch(Dt)
+    shapes = {
+        "dW   X.T[H,B] @ D[B,H]    (A MN-major, B MN-major, K=65536)": (dX.dimshuffle([1, 0]), dD, (H, H)),
+        "dWkk Xt[H,B] @ Dt.T       (A K-major,  B K-major,  K=65536)": (dXt, dDt.dimshuffle([1, 0]), (H, H)),
+        "dWkm Xt[H,B] @ D[B,H]     (A K-major,  B MN-major, K=65536)": (dXt, dD, (H, H)),
+        "dWmk X.T     @ Dt.T       (A MN-major, B K-major,  K=65536)": (dX.dimshuffle([1, 0]), dDt.dimshuffle([1, 0]), (H, H)),
+    }
 res = {}
 VARIANTS = {
+    "2cta": {},
+    "2cta, no split-K": {"AB_GEMM_SPLITK": "1"},
+    "2cta, split-K 4": {"AB_GEMM_SPLITK": "4"},
+} if os.environ.get("PROBE_DW_LAYOUTS") else {
     "2cta": {},
     "cluster4": {"AB_GEMM_CLUSTER4": "1"},
     "2cta, 6 stages": {"AB_GEMM_STAGES": "6"},
     "2cta, rows-then-columns tile order": {"AB_GEMM_GROUP_M": "1"},
     "2cta, groups of 16 tile rows": {"AB_GEMM_GROUP_M": "16"},
 }
-KNOBS = ("AB_GEMM_MN3D", "AB_GEMM_CLUSTER4", "AB_GEMM_STAGES", "AB_GEMM_GROUP_M")
+if os.environ.get("PROBE_HALF_GRID"):
+    VARIANTS = {"2cta, 74 pairs": {}, "2cta, 37 pairs": {"AB_GEMM_MAX_CLUSTERS": "37"},
+                "2cta, 18 pairs": {"AB_GEMM_MAX_CLUSTERS": "18"}}
+KNOBS = ("AB_GEMM_MN3D", "AB_GEMM_CLUSTER4", "AB_GEMM_STAGES", "AB_GEMM_GROUP_M", "AB_GEMM_SPLITK", "AB_GEMM_MAX_CLUSTERS")
 
 
 def cublas_ms():

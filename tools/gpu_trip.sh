@@ -33,6 +33,14 @@ case $sec in
     timeout 600 python tools/e2e_probe.py > gpurun_out/e2e_probe.log 2>&1; grep -a "host_chunks\|GB/s" gpurun_out/e2e_probe.log | tail -8;;
   gemm_probe)
     timeout 600 python tools/gemm_probe.py 20 > gpurun_out/gemm_probe.log 2>&1; tail -16 gpurun_out/gemm_probe.log;;
+  gemm_probe_dw)
+    PROBE_DW_LAYOUTS=1 timeout 600 python tools/gemm_probe.py 20 > gpurun_out/gemm_probe_dw.log 2>&1; tail -14 gpurun_out/gemm_probe_dw.log; cp gpurun_out/gemm_probe.json gpurun_out/gemm_probe_dw.json;;
+  region2_ncu)
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ab_gemm_ep" -s 4 -c 1 -o gpurun_out/region2_prof -f python bench.py --steps 1 --warmup 1 --no-also --no-cpu --no-e2e --no-truth --graph 0 > gpurun_out/region2_ncu.log 2>&1; echo "region2_ncu rc=$?"; tail -2 gpurun_out/region2_ncu.log | cut -c1-200; ls -la gpurun_out/region2_prof.ncu-rep;;
+  gemm_probe_half)
+    PROBE_HALF_GRID=1 timeout 600 python tools/gemm_probe.py 10 > gpurun_out/gemm_probe_half.log 2>&1; tail -11 gpurun_out/gemm_probe_half.log; cp gpurun_out/gemm_probe.json gpurun_out/gemm_probe_half.json;;
+  dw_ncu)
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tcgen05_2cta" -c 6 -o gpurun_out/dw_layout_prof -f python tools/dw_layout_ncu.py > gpurun_out/dw_ncu.log 2>&1; echo "dw_ncu rc=$?"; tail -4 gpurun_out/dw_ncu.log | cut -c1-200; ls -la gpurun_out/dw_layout_prof.ncu-rep;;
   gemm_ncu)
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 6 -c 2 -o gpurun_out/gemm_prof -f python tools/gemm_probe.py 2 > gpurun_out/gemm_ncu.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/gemm_ncu.log | cut -c1-300; ls -la gpurun_out/gemm_prof.ncu-rep;;
   scantests)
