@@ -538,6 +538,17 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     p.stages = std::max(2, std::min(p.stages, atoi(st_env)));
   p.acc_stages = 2;  // 2 x block_n <= 512 TMEM columns
   {
+    // L2 priority of the operands (GemmParams::a_l2): a small operand that every tile row (or
+    // column) of the other one re-reads -- the weight matrix of a batched layer -- is kept in L2
+    static const bool no_hint = getenv("AB_GEMM_NO_L2_HINT") != nullptr;
+    const double a_bytes = (double)M * (double)K * es * parts, b_bytes = (double)N * (double)K * es * parts;
+    const double keep_max = 48.0 * 1024 * 1024;
+    if (!no_hint) {
+      if (b_bytes <= keep_max && a_bytes >= 4.0 * b_bytes) p.b_l2 = 2;
+      else if (a_bytes <= keep_max && b_bytes >= 4.0 * a_bytes) p.a_l2 = 2;
+    }
+  }
+  {
     // Unit order inside a K range (AB_UNIT_DECODE).  Measured on the three cfg3 layouts
     // (profiles/r02_gemm_probe_order_stages.json, variants interleaved in one process): a tall
     // tile grid (65536 x 4096: 256 x 16 tiles) gains 8-18 % from groups of 8 tile rows, the
@@ -672,6 +683,7 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (ep) {
+      cfg.blockDim = dim3(kThreadsFused);
       cudaKernel_t kern;
       const char* name = pairs == 2 ? (bf16 ? "ab_gemm_ep_4cta_f16" : "ab_gemm_ep_4cta_tf32")
                                     : (bf16 ? "ab_gemm_ep_2cta_f16" : "ab_gemm_ep_2cta_tf32");
@@ -697,7 +709,7 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     cudaKernel_t kern;
     if ((rc = fused_kernel(ep->module, bf16 ? "ab_gemm_ep_1cta_f16" : "ab_gemm_ep_1cta_tf32", &kern))) return rc;
     void* args[] = {&ma[0], &ma[1], &mb[0], &mb[1], &p};
-    AB_CUDA(cudaLaunchKernel((const void*)kern, grid, dim3(kThreads), args, smem, st));
+    AB_CUDA(cudaLaunchKernel((const void*)kern, grid, dim3(kThreadsFused), args, smem, st));
     g_launches++;
     return AB_OK;
   }

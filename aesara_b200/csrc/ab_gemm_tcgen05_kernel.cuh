@@ -6,6 +6,27 @@
 // applied to the accumulator registers before the only store.
 #pragma once
 
+// Thread layout.  Ahead-of-time kernels (plain alpha/beta epilogue, ~124 registers): warp 0 =
+// TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue.  Fused-epilogue builds: the
+// generated region (read-ahead buffers, 32 accumulator columns, transposes, pair sums) wants
+// more than the 168 registers a 320-thread block gets -- ptxas then spills and re-reads
+// SR_TID at every use of `lane` (profiles/r02_region2_single_body.txt: 7 % of the samples on
+// the instruction behind an S2R) -- so those run 384 threads as three warpgroups: warps 0..3
+// (producer, issuer, two idle) shrink to kRegsControl registers and the epilogue warps 4..11
+// grow to kRegsEpilogue (setmaxnreg; 128 * 72 + 256 * 216 = 64 512 <= 65 536).
+#ifdef AB_EPILOGUE
+constexpr int kGemmThreads = kThreadsFused;
+constexpr int kEpiWarp0 = 4;
+#define AB_SETMAXNREG_CONTROL() asm volatile("setmaxnreg.dec.sync.aligned.u32 72;")
+#define AB_SETMAXNREG_EPILOGUE() asm volatile("setmaxnreg.inc.sync.aligned.u32 216;")
+#else
+constexpr int kGemmThreads = kThreads;
+constexpr int kEpiWarp0 = 2;
+#define AB_SETMAXNREG_CONTROL()
+#define AB_SETMAXNREG_EPILOGUE()
+#endif
+constexpr int kEpiThreads = 256;  // 8 epilogue warps
+
 struct GemmParams {
   long long M, N, K;      // K in elements of the packed type
   float alpha, beta;
@@ -63,6 +84,12 @@ struct GemmParams {
   double* colsum_ws;
   double* fullsum_ws;
   long long fullsum_cols;
+  // L2 eviction priority of the operands' tiles (make_l2_policy): a weight matrix that every
+  // tile row re-reads is kept (evict_last) against the stream of the large operand and of the
+  // epilogue's reads and writes (those use .cs accesses).  Without it the 32 MB W of cfg3 was
+  // fetched from DRAM ~50 times per product (dram__bytes_read 2.3-5.1 GB per launch against
+  // 0.5-1.5 GB of operands, profiles/r02_bench_step_ncu_v2.txt).
+  int a_l2, b_l2;
 };
 
 // one operand tile -> shared memory.  K-major: a single box {128 B of K, tile rows};
@@ -75,22 +102,23 @@ struct GemmParams {
 // of the 770 cycles per k-block on that (profiles/r02_region2_fp64_stalls.txt, dW launches).
 struct OperandLoad {
   int mn_major, chunks, mn3d, chunk_bytes, mn_per_chunk;
+  uint64_t policy;
 };
 __device__ __forceinline__ OperandLoad operand_load_a(const GemmParams& p) {
-  return OperandLoad{p.a_mn, p.a_chunks, p.a_mn3d, p.chunk_bytes, p.mn_per_chunk};
+  return OperandLoad{p.a_mn, p.a_chunks, p.a_mn3d, p.chunk_bytes, p.mn_per_chunk, make_l2_policy(p.a_l2)};
 }
 __device__ __forceinline__ OperandLoad operand_load_b(const GemmParams& p) {
-  return OperandLoad{p.b_mn, p.b_chunks, p.b_mn3d, p.chunk_bytes, p.mn_per_chunk};
+  return OperandLoad{p.b_mn, p.b_chunks, p.b_mn3d, p.chunk_bytes, p.mn_per_chunk, make_l2_policy(p.b_l2)};
 }
 __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
                                           int kc, int mn0, const OperandLoad& o) {
   if (!o.mn_major) {
-    tma_load_2d(dst, map, bar, kc, mn0);
+    tma_load_2d_hint(dst, map, bar, kc, mn0, o.policy);
   } else if (o.mn3d) {
     tma_load_3d(dst, map, bar, 0, kc, mn0 / o.mn_per_chunk);
   } else {
     for (int c = 0; c < o.chunks; ++c)
-      tma_load_2d(dst + c * o.chunk_bytes, map, bar, mn0 + c * o.mn_per_chunk, kc);
+      tma_load_2d_hint(dst + c * o.chunk_bytes, map, bar, mn0 + c * o.mn_per_chunk, kc, o.policy);
   }
 }
 
@@ -134,31 +162,52 @@ __device__ __forceinline__ void fold_segment(float (&acc)[kAccRegs], uint32_t t_
 #else
 #define AB_HAS_V8 0
 #endif
+// STREAM: the access belongs to a fused epilogue region -- [M, N] operands read once and values
+// written once, far larger than L2: evict-first, so that they do not push the products' small
+// operand (a weight matrix, GemmParams::b_l2) out of L2.  The plain alpha/beta epilogue keeps
+// the default policy (a small result is usually the next node's operand).
+template <bool STREAM>
 __device__ __forceinline__ void ld8(const float* q, float (&o)[8], bool wide) {
 #if AB_HAS_V8
   if (wide) {
-    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
-                 : "l"(q));
+    if (STREAM)
+      asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+                   : "l"(q));
+    else
+      asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+                   : "l"(q));
   } else
 #endif
   {
-    const float4 a = *reinterpret_cast<const float4*>(q);
-    const float4 b = *reinterpret_cast<const float4*>(q + 4);
+    const float4 a = STREAM ? __ldcs(reinterpret_cast<const float4*>(q)) : *reinterpret_cast<const float4*>(q);
+    const float4 b = STREAM ? __ldcs(reinterpret_cast<const float4*>(q + 4)) : *reinterpret_cast<const float4*>(q + 4);
     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
   }
 }
+template <bool STREAM>
 __device__ __forceinline__ void st8(float* q, const float (&v)[8], bool wide) {
 #if AB_HAS_V8
   if (wide) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(q), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
+    if (STREAM)
+      asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(q), "f"(v[0]), "f"(v[1]),
+                   "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                   : "memory");
+    else
+      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(q), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                   "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                   : "memory");
   } else
 #endif
   {
-    *reinterpret_cast<float4*>(q) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(q + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    if (STREAM) {
+      __stcs(reinterpret_cast<float4*>(q), make_float4(v[0], v[1], v[2], v[3]));
+      __stcs(reinterpret_cast<float4*>(q + 4), make_float4(v[4], v[5], v[6], v[7]));
+    } else {
+      *reinterpret_cast<float4*>(q) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(q + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
   }
 }
 
@@ -215,11 +264,11 @@ struct EpilogueOut {
             for (int t = 0; t < 8; ++t) v[t] = p.alpha * acc[c * 32 + j + t];
             if (p.beta != 0.0f) {
               float o[8];
-              ld8(irow + col0 + j, o, wide_in);
+              ld8<false>(irow + col0 + j, o, wide_in);
 #pragma unroll
               for (int t = 0; t < 8; ++t) v[t] += p.beta * o[t];
             }
-            st8(crow + col0 + j, v, wide_out);
+            st8<false>(crow + col0 + j, v, wide_out);
           }
         } else {
 #pragma unroll
@@ -289,14 +338,14 @@ struct EpilogueOut {
       float* dst = k == 0 ? p.C : p.out_ptr[k];
       const long long rs = k == 0 ? p.c_rs : p.out_rs[k];
       if (dst)
-        st8(dst + row * rs + col, o[k], ((rs & 7) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 31) == 0));
+        st8<true>(dst + row * rs + col, o[k], ((rs & 7) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 31) == 0));
       if (p.shadow[k]) {
         uint32_t h[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t)
           asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[t]) : "f"(o[k][2 * t + 1]), "f"(o[k][2 * t]));
         uint16_t* sp = static_cast<uint16_t*>(p.shadow[k]) + row * p.shadow_pitch[k] + col;
-        *reinterpret_cast<uint4*>(sp) = make_uint4(h[0], h[1], h[2], h[3]);
+        __stcs(reinterpret_cast<uint4*>(sp), make_uint4(h[0], h[1], h[2], h[3]));
       }
     }
   }
@@ -315,6 +364,24 @@ struct EpilogueOut {
   // ld8 per column group instead, every one of the four groups of a chunk waits for an L2
   // round trip (L1 is swept by the matrix reads): 13 % of the epilogue warps' samples in the
   // region with Y and b2 (profiles/r02_region2_after_pairs.txt).
+  // AB_EP_ROWMASK: operands known at code-generation time to be [1, N] rows.  Those are read as
+  // 32 values per lane with eight 128-bit loads at a warp-uniform address (one wavefront each, L1
+  // hits after the first warp of the CTA), a chunk ahead, instead of one value per lane plus 32
+  // SHFL.IDX per chunk at the point of use: the shuffles were the top short-scoreboard / MIO
+  // stall of region 1 (profiles/r02_bench_step_ncu_v2.txt).  A row operand that is only
+  // recognised at run time keeps the one-register shuffle path.
+#ifndef AB_EP_ROWMASK
+#define AB_EP_ROWMASK 0
+#endif
+  static __device__ __forceinline__ constexpr int popc4(unsigned m) {  // NVRTC has no __builtin_popcount
+    return (int)((m & 1u) + ((m >> 1) & 1u) + ((m >> 2) & 1u) + ((m >> 3) & 1u));
+  }
+  static constexpr int kRowOps = ((AB_EP_ROWMASK) & 1) + (((AB_EP_ROWMASK) >> 1) & 1) +
+                                 (((AB_EP_ROWMASK) >> 2) & 1) + (((AB_EP_ROWMASK) >> 3) & 1);
+  static __device__ __forceinline__ constexpr bool is_row_op(int k) { return ((AB_EP_ROWMASK >> k) & 1) != 0; }
+  static __device__ __forceinline__ constexpr int row_slot(int k) {
+    return popc4((unsigned)AB_EP_ROWMASK & ((1u << k) - 1u));
+  }
   struct ChunkPre {
 #if AB_EP_CIN
     float cin[32];
@@ -323,19 +390,32 @@ struct EpilogueOut {
     float op[32];
 #endif
     float vec[AB_EP_NOPS > 0 ? AB_EP_NOPS : 1];
+    float rowv[kRowOps > 0 ? kRowOps : 1][32];
   };
   __device__ __forceinline__ void prefetch_chunk(ChunkPre& pre, long long row, long long col0, bool live,
                                                  const FusedScalars& sc, int lane) const {
     const long long r = live ? row : 0;
     (void)r; (void)sc; (void)pre; (void)col0;
 #pragma unroll
-    for (int k = 0; k < AB_EP_NOPS; ++k)
-      if (sc.vec[k]) pre.vec[k] = (col0 + lane < p.N) ? __ldg(p.ep_ptr[k] + col0 + lane) : 0.0f;
+    for (int k = 0; k < AB_EP_NOPS; ++k) {
+      if (is_row_op(k) && sc.vec[k]) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          // N % 8 == 0 and 16-byte aligned rows (the fused launch's contract)
+          const float4 q = (col0 + j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ep_ptr[k] + col0 + j))
+                                            : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          float* d = &pre.rowv[row_slot(k)][j];
+          d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+        }
+      } else if (sc.vec[k]) {
+        pre.vec[k] = (col0 + lane < p.N) ? __ldg(p.ep_ptr[k] + col0 + lane) : 0.0f;
+      }
+    }
 #if AB_EP_CIN
     if (live && p.beta != 0.0f) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8)
-        if (col0 + j < p.N) ld8(p.Cin + r * p.cin_rs + col0 + j, *reinterpret_cast<float(*)[8]>(&pre.cin[j]), wide_in);
+        if (col0 + j < p.N) ld8<true>(p.Cin + r * p.cin_rs + col0 + j, *reinterpret_cast<float(*)[8]>(&pre.cin[j]), wide_in);
     }
 #endif
 #if AB_EP_PRE_OP >= 0
@@ -344,16 +424,26 @@ struct EpilogueOut {
 #pragma unroll
       for (int j = 0; j < 32; j += 8)
         if (col0 + j < p.N)
-          ld8(p.ep_ptr[AB_EP_PRE_OP] + r * p.ep_rs[AB_EP_PRE_OP] + col0 + j, *reinterpret_cast<float(*)[8]>(&pre.op[j]), wide);
+          ld8<true>(p.ep_ptr[AB_EP_PRE_OP] + r * p.ep_rs[AB_EP_PRE_OP] + col0 + j, *reinterpret_cast<float(*)[8]>(&pre.op[j]), wide);
     }
 #endif
   }
-  // x[32]: raw accumulator values of columns col0 .. col0+31 of `row`; on return (AB_EP_COLSUM
-  // builds) they have been replaced and reduced: the column sums of the warp's 32 rows are
-  // written to colsum_ws.  `fs` accumulates the AB_EP_FULLSUM value of this thread.
-  __device__ __forceinline__ void fused_chunk(float (&x)[32], long long row, long long col0, bool live,
-                                              int lane, const FusedScalars& sc, FF& fs, const ChunkPre& pre) const {
+  // ---- one 32-column chunk of one accumulator row, in two parts -------------------------
+  // fused_eval:   x[32] (raw accumulator values of columns col0 .. col0+31 of `row`) -> the
+  //               region's values; consumes the read-ahead buffer `pre`, stores the outputs and
+  //               their natural bf16 planes, adds to the thread's total `fs`, and leaves the
+  //               value that is reduced / transposed in x[] (0 for rows and columns outside).
+  // fused_reduce: the cross-lane part: column sums of the warp's 32 rows and the transposed
+  //               bf16 plane.
+  // The caller issues the NEXT chunk's reads between the two: `pre` is dead after fused_eval,
+  // and the ~300 shuffle/select instructions of fused_reduce give those reads their latency.
+  // (Two alternating buffers and a loop body of two chunks did the same at twice the code:
+  // ~4900 SASS instructions per iteration, 35 % of the epilogue warps' samples waiting for
+  // instruction fetch -- stall_no_inst, profiles/r02_region2_tplane_icache.txt.)
+  __device__ __forceinline__ void fused_eval(float (&x)[32], long long row, long long col0, bool live,
+                                             int lane, const FusedScalars& sc, FF& fs, const ChunkPre& pre) const {
     const long long r = live ? row : 0;
+    (void)lane; (void)fs;
 #if AB_EP_PRE_OP >= 0
     const bool pre_ok = live && !sc.is[AB_EP_PRE_OP] && p.ep_cs[AB_EP_PRE_OP] == 1;
 #endif
@@ -364,7 +454,10 @@ struct EpilogueOut {
       float ev[AB_EP_NOPS > 0 ? AB_EP_NOPS : 1][8];
 #pragma unroll
       for (int k = 0; k < AB_EP_NOPS; ++k) {
-        if (sc.vec[k]) {
+        if (is_row_op(k) && sc.vec[k]) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) ev[k][t] = pre.rowv[row_slot(k)][j + t];
+        } else if (sc.vec[k]) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) ev[k][t] = __shfl_sync(0xffffffffu, pre.vec[k], j + t);
         }
@@ -379,7 +472,7 @@ struct EpilogueOut {
           for (int t = 0; t < 8; ++t) v[t] += p.beta * pre.cin[j + t];
 #else
           float ci[8];
-          ld8(p.Cin + r * p.cin_rs + col, ci, wide_in);
+          ld8<true>(p.Cin + r * p.cin_rs + col, ci, wide_in);
 #pragma unroll
           for (int t = 0; t < 8; ++t) v[t] += p.beta * ci[t];
 #endif
@@ -401,7 +494,7 @@ struct EpilogueOut {
 #pragma unroll
             for (int t = 0; t < 8; ++t) e[k][t] = sc.v[k];
           } else if (p.ep_cs[k] == 1) {
-            ld8(p.ep_ptr[k] + r * p.ep_rs[k] + col, e[k],
+            ld8<true>(p.ep_ptr[k] + r * p.ep_rs[k] + col, e[k],
                 ((reinterpret_cast<uintptr_t>(p.ep_ptr[k]) & 31) == 0) && ((p.ep_rs[k] & 7) == 0));
           } else {
             const float* q = p.ep_ptr[k] + r * p.ep_rs[k] + col * p.ep_cs[k];
@@ -421,8 +514,18 @@ struct EpilogueOut {
         for (int t = 0; t < 8; ++t) x[j + t] = o[AB_EP_TPLANE][t];
 #endif
 #if AB_EP_FULLSUM >= 0
+#if AB_EP_EXACT_SUMS
 #pragma unroll
         for (int t = 0; t < 8; ++t) ff_add(fs, o[AB_EP_FULLSUM][t]);
+#else
+        {
+          // reduced-precision products (tf32 / bf16 operands): 8 values summed as a float32
+          // tree, the groups as float pairs
+          const float* w = o[AB_EP_FULLSUM];
+          ff_add(fs, __fadd_rn(__fadd_rn(__fadd_rn(w[0], w[1]), __fadd_rn(w[2], w[3])),
+                               __fadd_rn(__fadd_rn(w[4], w[5]), __fadd_rn(w[6], w[7]))));
+        }
+#endif
 #endif
       } else {
 #if AB_EP_COLSUM >= 0 || AB_EP_TPLANE >= 0
@@ -431,12 +534,41 @@ struct EpilogueOut {
 #endif
       }
     }
+  }
+  __device__ __forceinline__ void fused_reduce(float (&x)[32], long long row, long long col0, int lane) const {
+    (void)x; (void)row; (void)col0; (void)lane;
+#if AB_EP_TPLANE >= 0
+    // Transposed bf16 plane, first half: rows are lanes, so two vertically adjacent values sit
+    // in lanes l and l ^ 1.  Even lanes keep the even columns, odd lanes the odd ones: after
+    // one exchange, P[i] of lane l is column 2 i + (l & 1) of the row pair (l & ~1, l | 1),
+    // packed (low half = even row).  The remaining four exchanges (below, after the column
+    // sums have consumed x[]) work on 16 packed registers instead of 32 floats.
+    uint32_t P[16];
+    const bool want_t = p.shadow_t != nullptr;
+    if (want_t) {
+      const bool odd = (lane & 1) != 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float mine = odd ? x[2 * i + 1] : x[2 * i];
+        const float send = odd ? x[2 * i] : x[2 * i + 1];
+        const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+        uint32_t h;  // low half <- second source operand
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(got), "f"(mine));
+        P[i] = __byte_perm(h, 0u, odd ? 0x1032u : 0x3210u);
+      }
+    }
+#endif
 #if AB_EP_COLSUM >= 0
     {
-      // 32 x 32 transpose-reduce over the warp's rows on float pairs (see FF above; the
-      // reference's CAReduce accumulates float32 sums in float64): after the step with
-      // distance h every lane keeps the half of its columns selected by bit h of its lane
-      // index; lane l ends with the sum of column col0 + l
+      // 32 x 32 transpose-reduce over the warp's rows: after the step with distance h every
+      // lane keeps the half of its columns selected by bit h of its lane index; lane l ends
+      // with the sum of column col0 + l.  The reference's CAReduce accumulates float32 sums in
+      // float64 (tensor/elemwise.py:1371-1385): under the fp32-faithful policy the 32 rows are
+      // added as float pairs (see FF above); under the tf32 / bf16 policies -- the addends
+      // carry 2^-11 / 2^-8 relative error themselves -- as a float32 tree.  Either way the
+      // partial sum leaves the warp as float64.
+      const long long rb = row >> 5;  // row - lane is a multiple of 32
+#if AB_EP_EXACT_SUMS
       FF d[16];
       {
         const bool up = (lane & 16) != 0;
@@ -464,51 +596,53 @@ struct EpilogueOut {
       }
       AB_COLSUM_STEP(8) AB_COLSUM_STEP(4) AB_COLSUM_STEP(2) AB_COLSUM_STEP(1)
 #undef AB_COLSUM_STEP
-      const long long rb = row >> 5;  // row - lane is a multiple of 32
       if (rb * 32 < p.M && col0 + lane < p.N) p.colsum_ws[rb * p.N + col0 + lane] = ff_double(d[0]);
+#else
+#define AB_COLSUM_STEP(H)                                                      \
+      {                                                                        \
+        const bool up = (lane & (H)) != 0;                                     \
+        _Pragma("unroll") for (int i = 0; i < (H); ++i) {                      \
+          const float keep = up ? x[(H) + i] : x[i];                           \
+          const float send = up ? x[i] : x[(H) + i];                           \
+          x[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, (H)));     \
+        }                                                                      \
+      }
+      AB_COLSUM_STEP(16) AB_COLSUM_STEP(8) AB_COLSUM_STEP(4) AB_COLSUM_STEP(2) AB_COLSUM_STEP(1)
+#undef AB_COLSUM_STEP
+      if (rb * 32 < p.M && col0 + lane < p.N) p.colsum_ws[rb * p.N + col0 + lane] = (double)x[0];
+#endif
     }
 #endif
 #if AB_EP_TPLANE >= 0
-    // (AB_EP_COLSUM, when present, is the same value: x[] holds it)
-    if (p.shadow_t) {
-      // 32 x 32 transpose in registers: after the exchange with distance h, register i of lane l
-      // holds what register (i ^ h) of lane (l ^ h) held if bit h of i and l differ.  Five
-      // steps turn "lane = row, register = column" into "lane = column, register = row".
-#define AB_T_STEP(H)                                                            \
+    if (want_t) {
+      // second half: register index bit b <-> lane bit b + 1 (b = 0..3).  Before: lane bits
+      // 1..4 = row pair k, register index i = column / 2.  After: lane l = column col0 + l,
+      // P[k] = rows (row0 + 2 k, row0 + 2 k + 1): 64 contiguous bytes of the transposed plane.
+#define AB_T_STEP(B)                                                            \
       {                                                                         \
-        const bool up = (lane & (H)) != 0;                                      \
-        _Pragma("unroll") for (int i = 0; i < 32; ++i) {                        \
-          if ((i & (H)) == 0) {                                                 \
-            const float send = up ? x[i] : x[i | (H)];                          \
-            const float got = __shfl_xor_sync(0xffffffffu, send, (H));          \
-            if (up) x[i] = got; else x[i | (H)] = got;                          \
+        const bool up = (lane & (2 << (B))) != 0;                               \
+        _Pragma("unroll") for (int i = 0; i < 16; ++i) {                        \
+          if ((i & (1 << (B))) == 0) {                                          \
+            const uint32_t send = up ? P[i] : P[i | (1 << (B))];                \
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 2 << (B));  \
+            if (up) P[i] = got; else P[i | (1 << (B))] = got;                   \
           }                                                                     \
         }                                                                       \
       }
-      AB_T_STEP(16) AB_T_STEP(8) AB_T_STEP(4) AB_T_STEP(2) AB_T_STEP(1)
+      AB_T_STEP(0) AB_T_STEP(1) AB_T_STEP(2) AB_T_STEP(3)
 #undef AB_T_STEP
-      // lane l: column col0 + l, x[i] = its value in row (row - lane) + i: 32 consecutive
-      // bf16 = 64 contiguous bytes of the transposed plane
       const long long row0 = row - lane;
       const long long c = col0 + lane;
       if (c < p.N && row0 < p.M) {
         uint16_t* dst = static_cast<uint16_t*>(p.shadow_t) + c * p.shadow_t_pitch + row0;
         if (row0 + 32 <= p.M) {
-          uint32_t h[16];
-#pragma unroll
-          for (int t = 0; t < 16; ++t)
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[t]) : "f"(x[2 * t + 1]), "f"(x[2 * t]));
 #pragma unroll
           for (int t = 0; t < 4; ++t)
-            reinterpret_cast<uint4*>(dst)[t] = make_uint4(h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+            __stcs(reinterpret_cast<uint4*>(dst) + t, make_uint4(P[4 * t], P[4 * t + 1], P[4 * t + 2], P[4 * t + 3]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (row0 + i < p.M) {
-              uint16_t b;
-              asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(b) : "f"(x[i]));
-              dst[i] = b;
-            }
+            if (row0 + i < p.M) dst[i] = (uint16_t)((i & 1) ? (P[i >> 1] >> 16) : (P[i >> 1] & 0xffffu));
         }
       }
     }
@@ -525,9 +659,8 @@ struct EpilogueOut {
   }
   // accumulator already folded into registers (several K segments: the fp32-faithful mode)
   __device__ __forceinline__ void store_fused(float (&acc)[kAccRegs], long long row, long long n0,
-                                              int nchunks, int lane) const {
+                                              int nchunks, int lane, const FusedScalars& sc) const {
     const bool live = row < p.M;
-    const FusedScalars sc = load_scalars();
     FF fs = {0.0f, 0.0f};
     // 128 accumulator registers are live here: the chunk's reads are issued and consumed in
     // place (this mode spends 3x the tensor time per tile; its epilogue is not the bottleneck)
@@ -536,43 +669,33 @@ struct EpilogueOut {
       if (c < nchunks) {
         ChunkPre pre;
         prefetch_chunk(pre, row, n0 + c * 32, live, sc, lane);
-        fused_chunk(*reinterpret_cast<float(*)[32]>(&acc[c * 32]), row, n0 + c * 32, live, lane, sc, fs, pre);
+        float (&x)[32] = *reinterpret_cast<float(*)[32]>(&acc[c * 32]);
+        fused_eval(x, row, n0 + c * 32, live, lane, sc, fs, pre);
+        fused_reduce(x, row, n0 + c * 32, lane);
       }
     }
     finish_fullsum(fs, row, n0, lane);
   }
   // the whole K range sits in one TMEM accumulator (bf16 / tf32 policies): 32 columns at a
-  // time straight from TMEM in a rolled loop -- 32 live accumulator registers instead of 128
+  // time straight from TMEM in a rolled loop -- 32 live accumulator registers instead of 128,
+  // and the body exists once
   __device__ __forceinline__ void store_fused_tmem(uint32_t t_acc, long long row, long long n0, int nchunks,
-                                                   int lane) const {
+                                                   int lane, const FusedScalars& sc) const {
     const bool live = row < p.M;
-    const FusedScalars sc = load_scalars();
     FF fs = {0.0f, 0.0f};
-    // two buffers used alternately by a loop body that handles two chunks (a copy `cur = nxt`
-    // at the end of a one-chunk body was scheduled by the compiler right behind the loads it
-    // copies: it waited for them there, and the read-ahead hid nothing)
-    ChunkPre pa, pb;
-    prefetch_chunk(pa, row, n0, live, sc, lane);
+    ChunkPre pre;
+    prefetch_chunk(pre, row, n0, live, sc, lane);
 #pragma unroll 1
-    for (int c = 0; c < nchunks; c += 2) {
-      if (c + 1 < nchunks) prefetch_chunk(pb, row, n0 + (c + 1) * 32, live, sc, lane);
-      {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
-        float x[32];
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * 32), r);
+      float x[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
-        fused_chunk(x, row, n0 + c * 32, live, lane, sc, fs, pa);
-      }
-      if (c + 1 < nchunks) {
-        if (c + 2 < nchunks) prefetch_chunk(pa, row, n0 + (c + 2) * 32, live, sc, lane);
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_acc + (uint32_t)((c + 1) * 32), r);
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
-        fused_chunk(x, row, n0 + (c + 1) * 32, live, lane, sc, fs, pb);
-      }
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+      const long long col0 = n0 + c * 32;
+      fused_eval(x, row, col0, live, lane, sc, fs, pre);
+      if (c + 1 < nchunks) prefetch_chunk(pre, row, col0 + 32, live, sc, lane);
+      fused_reduce(x, row, col0, lane);
     }
     finish_fullsum(fs, row, n0, lane);
   }
@@ -632,7 +755,7 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], kThreads - 64);  // every epilogue thread arrives
+      mbar_init(&tmem_empty_bar[s], kEpiThreads);  // every epilogue thread arrives
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -650,6 +773,8 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  if (warp < kEpiWarp0) {
+  AB_SETMAXNREG_CONTROL();
   if (warp == 0) {
     // ================= TMA producer =================
     if (elect_one()) {
@@ -730,15 +855,26 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
         }
       }
     }
+  }
   } else {
+    AB_SETMAXNREG_EPILOGUE();
     // ================= epilogue (warps 2..9) =================
     // Two warps share each TMEM lane quarter; each owns half of the tile's columns and
     // keeps them as FP32 register accumulators across the K segments.
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;    // which half of the columns
+    const int half = (warp - kEpiWarp0) >> 2;    // which half of the columns
     const int half_n = p.block_n >> 1;
     const int nchunks = half_n >> 5;     // 32-column chunks: 1, 2 or 4
     const EpilogueOut eo(p);
+#ifdef AB_EPILOGUE
+    // the region's [1, 1] operands: read once per kernel (a global load per tile otherwise);
+    // `lane` through a volatile asm: ptxas otherwise re-reads SR_TID (S2R, ~20 cycles on the
+    // short scoreboard) at each of its many uses in the cross-lane code instead of keeping it
+    const EpilogueOut::FusedScalars sc = eo.load_scalars();
+    uint32_t lane_reg;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_reg));
+    const int lane = (int)lane_reg;
+#endif
     float acc[kAccRegs];
     uint32_t sit = 0;
     for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
@@ -755,7 +891,7 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
         tcgen05_fence_after();
         const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
                                ((uint32_t)(q * 32) << 16);
-        eo.store_fused_tmem(t_acc, m0 + q * 32 + lane, n0, nchunks, lane);
+        eo.store_fused_tmem(t_acc, m0 + q * 32 + lane, n0, nchunks, lane, sc);
         tcgen05_fence_before();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as]))
                      : "memory");
@@ -776,7 +912,7 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
                      : "memory");
       }
 #ifdef AB_EPILOGUE
-      eo.store_fused(acc, m0 + q * 32 + lane, n0, nchunks, lane);  // fused launches are never split along K
+      eo.store_fused(acc, m0 + q * 32 + lane, n0, nchunks, lane, sc);  // fused launches are never split along K
 #else
       if (split == 0) eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
       else eo.store_partial(acc, m0 + q * 32 + lane, n0, nchunks, split);
@@ -809,12 +945,12 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
 __device__ __forceinline__ void load_tile_2sm(uint8_t* dst, const CUtensorMap* map, uint64_t* bar,
                                               int kc, int mn0, const OperandLoad& o) {
   if (!o.mn_major) {
-    tma_load_2d_2sm(dst, map, bar, kc, mn0);
+    tma_load_2d_2sm_hint(dst, map, bar, kc, mn0, o.policy);
   } else if (o.mn3d) {
     tma_load_3d_2sm(dst, map, bar, 0, kc, mn0 / o.mn_per_chunk);
   } else {
     for (int c = 0; c < o.chunks; ++c)
-      tma_load_2d_2sm(dst + c * o.chunk_bytes, map, bar, mn0 + c * o.mn_per_chunk, kc);
+      tma_load_2d_2sm_hint(dst + c * o.chunk_bytes, map, bar, mn0 + c * o.mn_per_chunk, kc, o.policy);
   }
 }
 // GemmParams here: block_n = 256 (the pair's N tile), b_tile_bytes = 128 rows * 128 B
@@ -887,7 +1023,7 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 2 * (kThreads - 64));  // the epilogue threads of both CTAs
+      mbar_init(&tmem_empty_bar[s], 2 * kEpiThreads);  // the epilogue threads of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -905,6 +1041,8 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  if (warp < kEpiWarp0) {
+  AB_SETMAXNREG_CONTROL();
   if (warp == 0) {
     // ================= TMA producer (one per CTA) =================
     if (elect_one()) {
@@ -983,13 +1121,24 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
         }
       }
     }
+  }
   } else {
+    AB_SETMAXNREG_EPILOGUE();
     // ================= epilogue (warps 2..9 of both CTAs) =================
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - kEpiWarp0) >> 2;
     const int half_n = p.block_n >> 1;
     const int nchunks = half_n >> 5;
     const EpilogueOut eo(p);
+#ifdef AB_EPILOGUE
+    // the region's [1, 1] operands: read once per kernel (a global load per tile otherwise);
+    // `lane` through a volatile asm: ptxas otherwise re-reads SR_TID (S2R, ~20 cycles on the
+    // short scoreboard) at each of its many uses in the cross-lane code instead of keeping it
+    const EpilogueOut::FusedScalars sc = eo.load_scalars();
+    uint32_t lane_reg;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_reg));
+    const int lane = (int)lane_reg;
+#endif
     float acc[kAccRegs];
     uint32_t sit = 0;
     for (long long unit = cluster_id; unit < num_units; unit += n_clusters) {
@@ -1005,7 +1154,7 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
         tcgen05_fence_after();
         const uint32_t t_acc = tmem_base + as * (uint32_t)p.block_n + (uint32_t)(half * half_n) +
                                ((uint32_t)(q * 32) << 16);
-        eo.store_fused_tmem(t_acc, m0 + q * 32 + lane, n0, nchunks, lane);
+        eo.store_fused_tmem(t_acc, m0 + q * 32 + lane, n0, nchunks, lane, sc);
         tcgen05_fence_before();
         asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(
                          smem_u32(&tmem_empty_bar[as]) & kPeerBitMask)
@@ -1027,7 +1176,7 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
                      : "memory");
       }
 #ifdef AB_EPILOGUE
-      eo.store_fused(acc, m0 + q * 32 + lane, n0, nchunks, lane);  // fused launches are never split along K
+      eo.store_fused(acc, m0 + q * 32 + lane, n0, nchunks, lane, sc);  // fused launches are never split along K
 #else
       if (split == 0) eo.store(acc, m0 + q * 32 + lane, n0, nchunks);
       else eo.store_partial(acc, m0 + q * 32 + lane, n0, nchunks, split);
@@ -1048,27 +1197,27 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
 
 #ifdef AB_EPILOGUE
 // NVRTC build: C-linkage entry points (the module is loaded by name from gemm_run)
-extern "C" __global__ void __launch_bounds__(kThreads, 1)
+extern "C" __global__ void __launch_bounds__(kGemmThreads, 1)
 ab_gemm_ep_1cta_tf32(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                      const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
                      const __grid_constant__ GemmParams p) { gemm_1cta_body<0>(a0, a1, b0, b1, p); }
-extern "C" __global__ void __launch_bounds__(kThreads, 1)
+extern "C" __global__ void __launch_bounds__(kGemmThreads, 1)
 ab_gemm_ep_1cta_f16(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                     const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
                     const __grid_constant__ GemmParams p) { gemm_1cta_body<1>(a0, a1, b0, b1, p); }
-extern "C" __global__ void __launch_bounds__(kThreads, 1)
+extern "C" __global__ void __launch_bounds__(kGemmThreads, 1)
 ab_gemm_ep_2cta_tf32(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                      const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
                      const __grid_constant__ GemmParams p) { gemm_2cta_body<0>(a0, a1, b0, b1, p); }
-extern "C" __global__ void __launch_bounds__(kThreads, 1)
+extern "C" __global__ void __launch_bounds__(kGemmThreads, 1)
 ab_gemm_ep_2cta_f16(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                     const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
                     const __grid_constant__ GemmParams p) { gemm_2cta_body<1>(a0, a1, b0, b1, p); }
-extern "C" __global__ void __launch_bounds__(kThreads, 1)
+extern "C" __global__ void __launch_bounds__(kGemmThreads, 1)
 ab_gemm_ep_4cta_tf32(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                      const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
                      const __grid_constant__ GemmParams p) { gemm_2cta_body<0, 2>(a0, a1, b0, b1, p); }
-extern "C" __global__ void __launch_bounds__(kThreads, 1)
+extern "C" __global__ void __launch_bounds__(kGemmThreads, 1)
 ab_gemm_ep_4cta_f16(const __grid_constant__ CUtensorMap a0, const __grid_constant__ CUtensorMap a1,
                     const __grid_constant__ CUtensorMap b0, const __grid_constant__ CUtensorMap b1,
                     const __grid_constant__ GemmParams p) { gemm_2cta_body<1, 2>(a0, a1, b0, b1, p); }

@@ -22,6 +22,9 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int SW_BYTES = 128;  // swizzle span = smem row pitch of every operand tile
 constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+// GEMM kernels with a fused epilogue region (NVRTC builds): three warpgroups -- {TMA warp, MMA
+// warp, two idle warps} hand most of their registers to the eight epilogue warps (setmaxnreg)
+constexpr int kThreadsFused = 384;
 constexpr int kMaxSmem = 200 * 1024;       // dynamic shared memory the Scan kernels ask for
 constexpr int kMaxSmemGemm = 226 * 1024;   // GEMM: 7 stages of 32 KB (227 KB is the per-block limit)
 
@@ -68,6 +71,23 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// L2 eviction priority of an operand's tiles: 0 = normal, 1 = evict_first (streamed once),
+// 2 = evict_last (the small operand every tile row re-reads, e.g. a weight matrix)
+__device__ __forceinline__ uint64_t make_l2_policy(int kind) {
+  uint64_t pol;
+  if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                 int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
@@ -162,6 +182,15 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_hint(void* smem_dst, const CUtensorMap* map,
+                                                     uint64_t* leader_bar, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1),
+      "l"(policy)
       : "memory");
 }
 // the same load delivered to every CTA of `mask` (same CTA-relative smem offset in each; the

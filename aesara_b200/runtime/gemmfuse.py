@@ -121,9 +121,11 @@ class GemmEpilogueFusion:
         # the one value whose transposed bf16 plane the module can write (shares its registers
         # with the column sums, so it has to be that value when the region has column sums)
         cand = [k for k, v in enumerate(out_vars) if v is not None and _plane_users(program, v)[1]]
-        if os.environ.get("AB_EP_NO_TPLANE"):
+        if os.environ.get("AB_EP_NO_TPLANE") or (self.fullsum >= 0 and os.environ.get("AB_EP_TPLANE_NO_FULLSUM")):
             cand = []
         self.tplane = (self.colsum if self.colsum in cand else -1) if self.colsum >= 0 else (cand[0] if cand else -1)
+        self.exact_sums = True                # set by the executor: float-pair sums (fp32-faithful policy)
+        self.planes = True                    # set by the executor: bf16 operand planes exist (bf16 policy)
         self.broken = False
         self.f32_skipped = 0                  # values kept as a bf16 plane only (last run)
         self._src = None
@@ -329,9 +331,16 @@ class GemmEpilogueFusion:
                 if c is None and not (ss is not None and len(ss) == 2 and ss[0] == 1):
                     pre_op = k
                     break
+            # operands that are statically [1, N] rows with N unknown or > 1 (biases)
+            row_mask = 0
+            for k, v in enumerate(self.operand_vars):
+                ss = prog.vars[v].static_shape
+                if ss is not None and len(ss) == 2 and ss[0] == 1 and ss[1] != 1:
+                    row_mask |= 1 << k
             self._src = gemm_region_source(merged, len(self.operand_vars), self.colsum, self.fullsum,
                                            cin=prog.nodes[self.g].op == "Gemm", pre_op=pre_op,
-                                           tplane=self.tplane)
+                                           tplane=self.tplane if self.planes else -1,
+                                           exact_sums=self.exact_sums, row_mask=row_mask)
         return self._src
 
     def compile_all(self):
@@ -368,7 +377,7 @@ class GemmEpilogueFusion:
             if v is None:
                 plan.append((False, False, False))  # reduction source only
                 continue
-            planes = ex.precision == 2 and N % 8 == 0
+            planes = self.planes and ex.precision == 2 and N % 8 == 0
             nat_users, t_users = _plane_users(prog, v)
             tshadow = planes and k == self.tplane and bool(t_users)
             # products that contract over the rows of v and find no transposed plane read the

@@ -258,9 +258,11 @@ class PackCache:
 
     def __init__(self):
         self._e = {}
+        self._unstored = {}
 
     def clear(self):
         self._e.clear()
+        self._unstored.clear()
 
     def invalidate(self, owner):
         """Drop the packs of a buffer that a destructive (in-place) node just rewrote."""
@@ -278,8 +280,9 @@ class PackCache:
     def never_stored(self, arr: DeviceArray):
         """``arr`` exists as bf16 plane(s) only (its float32 buffer was not written by the
         epilogue that produced it): packing from it would read garbage -- fail loudly."""
-        self._unstored = getattr(self, "_unstored", {})
-        self._unstored[arr.ptr] = arr.owner
+        # weak: a strong reference here would keep every evaluation's unwritten [M, N] float32
+        # buffer alive (the caching allocator then has to cudaMalloc fresh ones each step)
+        self._unstored[arr.ptr] = self._ref(arr.owner)
 
     def adopt(self, arr: DeviceArray, buf, pitch, transposed=False):
         """Register a bf16 plane written by a fused GEMM epilogue as the pack of ``arr``
@@ -306,8 +309,8 @@ class PackCache:
             return (lambda o: (lambda: o))(owner)
 
     def _check_stored(self, arr):
-        un = getattr(self, "_unstored", None)
-        if un and un.get(arr.ptr) is arr.owner:
+        ref = self._unstored.get(arr.ptr)
+        if ref is not None and ref() is arr.owner:
             raise RuntimeError("PackCache: asked to pack a matrix that was kept as a bf16 plane only "
                                "(the fused epilogue did not store its float32 values)")
 

@@ -259,13 +259,24 @@ def check(rc):
 # ---------------------------------------------------------------------------
 # JIT kernel cache: source hash -> cubin on disk -> loaded module handle
 # ---------------------------------------------------------------------------
+_cache_dir = {}
+
+
 def cache_dir():
-    d = os.environ.get("AESARA_B200_CACHE")
+    env = os.environ.get("AESARA_B200_CACHE")
+    if env not in _cache_dir:
+        _cache_dir[env] = _find_cache_dir(env)
+    return _cache_dir[env]
+
+
+def _find_cache_dir(d):
+    import threading
+
     if not d:
         d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_kcache")
     try:
         os.makedirs(d, exist_ok=True)
-        probe = os.path.join(d, ".w")
+        probe = os.path.join(d, f".w{os.getpid()}_{threading.get_ident()}")
         with open(probe, "w"):
             pass
         os.remove(probe)
@@ -291,7 +302,9 @@ def compile_cubin(src: str, name: str = "ab_module") -> bytes:
         data = C.string_at(out, size.value)
     finally:
         lib.ab_buffer_free(out)
-    tmp = path + f".tmp{os.getpid()}"
+    import threading
+
+    tmp = path + f".tmp{os.getpid()}_{threading.get_ident()}"
     with open(tmp, "wb") as f:
         f.write(data)
     os.replace(tmp, path)

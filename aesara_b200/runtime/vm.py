@@ -199,7 +199,11 @@ class ProgramExecutor:
 
         self._fusions = RowFusion.detect(program, self._destroys)
         taken = {i for f in self._fusions for i in f.members}
-        self._fusions += GemmEpilogueFusion.detect(program, self._destroys, taken)
+        gemm_regions = GemmEpilogueFusion.detect(program, self._destroys, taken)
+        for f in gemm_regions:
+            f.exact_sums = self.precision == 0
+            f.planes = self.precision == 2
+        self._fusions += gemm_regions
         from .redfuse import ReducePreFusion
 
         taken = {i for f in self._fusions for i in f.members}

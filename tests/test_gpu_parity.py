@@ -261,17 +261,23 @@ def lib_launches():
     return lib.load().ab_launch_count()
 
 
-def _fused_vs_plain(fused, plain, what):
+def _fused_vs_plain(fused, plain, what, exact_sums=True):
     """cfg3 outputs [loss, dW1, db1, dW2, db2]: the products see identical operands (the
     epilogue evaluates the same scalar expressions on the same fp32 values; a bf16 plane written
-    by the epilogue equals the separate pack), so the weight gradients are BIT-identical; loss
-    and bias gradients are float64 sums of identical float32 terms in a different (still
-    deterministic) order: equal to the last float32 bit or one ulp."""
+    by the epilogue equals the separate pack), so the weight gradients are BIT-identical.  Loss
+    and bias gradients, fp32-faithful policy: float64(-equivalent) sums of identical float32
+    terms in a different (still deterministic) order: equal to the last float32 bit or one ulp.
+    tf32 / bf16 policies (``exact_sums=False``): the epilogue adds 8 / 32 terms at a time as a
+    float32 tree before the float64 stage -- a few 2^-24 of the sum of magnitudes, checked
+    norm-wise at 2e-6 (the terms themselves carry 2^-8 from the bf16 operands)."""
     for k, (a, b) in enumerate(zip(fused, plain)):
         if np.ndim(a) == 2:
             np.testing.assert_array_equal(a, b, err_msg=f"{what} output {k}: fused vs node-by-node")
-        else:
+        elif exact_sums:
             np.testing.assert_allclose(a, b, rtol=3e-7, atol=0, err_msg=f"{what} output {k}: fused vs node-by-node")
+        else:
+            np.testing.assert_allclose(a, b, rtol=0, atol=2e-6 * float(np.max(np.abs(b))),
+                                       err_msg=f"{what} output {k}: fused vs node-by-node")
 
 
 @pytest.mark.parametrize("precision", [0, 2])
@@ -307,14 +313,14 @@ def test_mlp_gemm_epilogue_fusion_matches_node_by_node(rt, precision):
     before = lib_launches()
     plain = ex_plain(*ins)
     assert n_fused_launches < lib_launches() - before
-    _fused_vs_plain(fused, plain, f"precision {precision}")
+    _fused_vs_plain(fused, plain, f"precision {precision}", exact_sums=precision == 0)
     # the round-1 regions (one Elemwise per product) still give the same bits
     os.environ["AB_GEMM_FUSE_SINGLE"] = "1"
     try:
         single = rt(prog, precision=precision)(*ins)
     finally:
         del os.environ["AB_GEMM_FUSE_SINGLE"]
-    _fused_vs_plain(single, plain, f"precision {precision}, single-node regions")
+    _fused_vs_plain(single, plain, f"precision {precision}, single-node regions", exact_sums=precision == 0)
 
 
 @pytest.mark.parametrize("T,B,H", [(12, 256, 128), (5, 384, 192), (4, 200, 64)])
@@ -446,7 +452,7 @@ def test_mlp_full_size_fused_equals_node_by_node(rt):
         plain = run(rt(prog, precision=2, host_outputs=False), X, Y)
     finally:
         del os.environ["AB_NO_GEMM_FUSE"], os.environ["AB_NO_RED_FUSE"]
-    _fused_vs_plain(fused, plain, "full-size MLP")
+    _fused_vs_plain(fused, plain, "full-size MLP", exact_sums=False)
     perm = torch.randperm(B, device="cuda", generator=g)
     shuffled = run(ex, X[perm].contiguous(), Y[perm].contiguous())
     for k, (a, b) in enumerate(zip(shuffled, fused)):

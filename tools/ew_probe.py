@@ -50,5 +50,38 @@ for name, env, band in VARIANTS:
     res[name] = {"ms": ms, "gbs": gbs, "frac_of_measured_hbm": gbs / peak}
     print(f"a.T*b+1 {n}x{n} f32  {name:10s} {ms:7.3f} ms  {gbs:7.0f} GB/s  = {gbs/peak:.2f} of the measured copy bandwidth")
     os.environ.pop("AB_EW_NO_TILE", None)
+# yardsticks on the same box: a library transposing Elemwise (torch) and the plain copy, and a
+# shape that is not a power of two (column stride 32 800 B instead of 32 768 B)
+def _time(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+ta, tb = a.owner, b.owner
+to = torch.empty(n, n, device="cuda")
+ms = _time(lambda: torch.add(torch.mul(ta.t(), tb, out=to), 1.0, out=to))
+res["torch_mul_t_then_add (2 passes, 5 x 256 MiB)"] = {"ms": ms, "gbs": 5 * n * n * 4 / ms / 1e6}
+ms = _time(lambda: to.copy_(ta.t()))
+res["torch_copy_transposed (2 x 256 MiB)"] = {"ms": ms, "gbs": 2 * n * n * 4 / ms / 1e6, "frac_of_measured_hbm": 2 * n * n * 4 / ms / 1e6 / peak}
+ms = _time(lambda: to.copy_(ta))
+res["torch_copy (2 x 256 MiB)"] = {"ms": ms, "gbs": 2 * n * n * 4 / ms / 1e6, "frac_of_measured_hbm": 2 * n * n * 4 / ms / 1e6 / peak}
+m = 8200
+a2 = DeviceArray.from_torch(torch.randn(m, m, device="cuda"))
+b2 = DeviceArray.from_torch(torch.randn(m, m, device="cuda"))
+out2 = DeviceArray.empty((m, m), "float32")
+kern = K.ElemwiseKernel.get(expr)
+ins2 = [a2.dimshuffle([1, 0]), b2]
+ms = _time(lambda: kern.launch((m, m), ins2, [out2]))
+res["ab_ew_tile_8200"] = {"ms": ms, "gbs": 3 * m * m * 4 / ms / 1e6, "frac_of_measured_hbm": 3 * m * m * 4 / ms / 1e6 / peak}
+for k in list(res)[-4:]:
+    print(k, res[k])
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "ew_probe.json"), "w"), indent=1)

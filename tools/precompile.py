@@ -15,6 +15,11 @@ from tests._cases import case_names, load_case
 def main():
     t = time.time()
     exs = [ProgramExecutor(load_case(n)[0]) for n in case_names()]
+    # GEMM-epilogue regions are generated per precision policy (float-pair vs float32-tree sums)
+    for n in case_names():
+        prog = load_case(n)[0]
+        if any(nd.op in ("Dot22", "Gemm", "Dot22Scalar") for nd in prog.nodes):
+            exs += [ProgramExecutor(prog, precision=pr) for pr in (1, 2)]
     kerns = list(K.ElemwiseKernel._by_key.values()) + list(K.CAReduceKernel._by_key.values())
     for dt in ("float32", "float64", "int64", "int32", "int8", "bool"):
         kerns.append(K._identity_kernel(dt))
