@@ -483,6 +483,20 @@ int fused_kernel(Module* m, const char* name, cudaKernel_t* out) {
   return AB_OK;
 }
 
+// modules built with AB_EP_STAGED export a marker kernel: their epilogue warps use kStageBytes
+// of shared memory behind the operand ring
+bool fused_module_staged(Module* m) {
+  auto it = m->named.find("ab_gemm_ep_staged_marker");
+  if (it != m->named.end()) return it->second != nullptr;
+  cudaKernel_t kern = nullptr;
+  if (cudaLibraryGetKernel(&kern, m->lib, "ab_gemm_ep_staged_marker") != cudaSuccess) {
+    cudaGetLastError();
+    kern = nullptr;
+  }
+  m->named["ab_gemm_ep_staged_marker"] = kern;
+  return kern != nullptr;
+}
+
 int splitk_finish(const GemmParams& p, cudaStream_t st) {
   if (p.k_splits <= 1) return AB_OK;
   const long long work = (p.M * p.N + 3) / 4;
@@ -533,7 +547,8 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
   const int pairs = two_cta ? cluster_pairs(M, N) : 1;
   const int tile_m = two_cta ? 2 * BLOCK_M : BLOCK_M;
   const int stage_bytes = parts * (p.a_tile_bytes + p.b_tile_bytes);
-  p.stages = std::max(2, std::min(8, (kMaxSmemGemm - 1024) / stage_bytes));
+  const int stage_reserve = (ep && fused_module_staged(ep->module)) ? kStageBytes : 0;
+  p.stages = std::max(2, std::min(8, (kMaxSmemGemm - 1024 - stage_reserve) / stage_bytes));
   if (const char* st_env = getenv("AB_GEMM_STAGES"))  // probing knob (tools/gemm_probe.py)
     p.stages = std::max(2, std::min(p.stages, atoi(st_env)));
   p.acc_stages = 2;  // 2 x block_n <= 512 TMEM columns
@@ -642,7 +657,7 @@ int gemm_run(int precision, long long M, long long N, long long K, float alpha,
     if (rc) return rc;
   }
   if (parts == 1) { ma[1] = ma[0]; mb[1] = mb[0]; }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + stage_reserve;
   if (two_cta) {
     const int ctas = 2 * pairs;
     const long long cluster_m = (long long)tile_m * pairs;

@@ -211,10 +211,34 @@ __device__ __forceinline__ void st8(float* q, const float (&v)[8], bool wide) {
   }
 }
 
+#ifndef AB_EP_STAGED
+#define AB_EP_STAGED 0
+#endif
+constexpr int kStageBytesPerWarp = 32 * 32 * 4;                     // one 32 x 32 float32 chunk
+constexpr int kStageBytes = (kEpiThreads / 32) * kStageBytesPerWarp;  // behind the operand ring
+
+// explicit shared-space accesses of the staging buffer: through a generic pointer kept in a
+// struct ptxas emitted generic LD.E / ST.E (address-space lookup per access, on the long
+// scoreboard) in the larger regions
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 struct EpilogueOut {
   const GemmParams& p;
   bool vec_ok, wide_out, wide_in;
-  __device__ explicit EpilogueOut(const GemmParams& p_) : p(p_) {
+  uint32_t stage;  // AB_EP_STAGED builds: shared-space address of this warp's 4 KB (see fused_reduce)
+  __device__ explicit EpilogueOut(const GemmParams& p_, uint32_t stage_ = 0) : p(p_), stage(stage_) {
     vec_ok = (p.c_cs == 1) && ((p.c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
              (p.beta == 0.0f || ((p.cin_cs == 1) && ((p.cin_rs & 3) == 0) &&
                                  ((reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0)));
@@ -332,9 +356,12 @@ struct EpilogueOut {
     }
     return s;
   }
+  // SKIP: the value that leaves through the shared-memory staging buffer instead (-1: none)
+  template <int SKIP>
   __device__ __forceinline__ void put_outputs(const float (&o)[AB_EP_NOUT][8], long long row, long long col) const {
 #pragma unroll
     for (int k = 0; k < AB_EP_NOUT; ++k) {
+      if (k == SKIP) continue;
       float* dst = k == 0 ? p.C : p.out_ptr[k];
       const long long rs = k == 0 ? p.c_rs : p.out_rs[k];
       if (dst)
@@ -505,13 +532,19 @@ struct EpilogueOut {
         float o[AB_EP_NOUT][8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) { AB_EP_EVAL(v[t], e, t, o); }
-        put_outputs(o, r, col);
+#if AB_EP_STAGED
+        put_outputs<kStageValue>(o, r, col);
+        sts128(stage + 4u * st_off(lane, j >> 2), o[kStageValue][0], o[kStageValue][1], o[kStageValue][2], o[kStageValue][3]);
+        sts128(stage + 4u * st_off(lane, (j >> 2) + 1), o[kStageValue][4], o[kStageValue][5], o[kStageValue][6], o[kStageValue][7]);
+#else
+        put_outputs<-1>(o, r, col);
 #if AB_EP_COLSUM >= 0
 #pragma unroll
         for (int t = 0; t < 8; ++t) x[j + t] = o[AB_EP_COLSUM][t];
 #elif AB_EP_TPLANE >= 0
 #pragma unroll
         for (int t = 0; t < 8; ++t) x[j + t] = o[AB_EP_TPLANE][t];
+#endif
 #endif
 #if AB_EP_FULLSUM >= 0
 #if AB_EP_EXACT_SUMS
@@ -528,13 +561,126 @@ struct EpilogueOut {
 #endif
 #endif
       } else {
-#if AB_EP_COLSUM >= 0 || AB_EP_TPLANE >= 0
+#if AB_EP_STAGED
+        sts128(stage + 4u * st_off(lane, j >> 2), 0.0f, 0.0f, 0.0f, 0.0f);
+        sts128(stage + 4u * st_off(lane, (j >> 2) + 1), 0.0f, 0.0f, 0.0f, 0.0f);
+#elif AB_EP_COLSUM >= 0 || AB_EP_TPLANE >= 0
 #pragma unroll
         for (int t = 0; t < 8; ++t) x[j + t] = 0.0f;
 #endif
       }
     }
   }
+  // ---- AB_EP_STAGED: the value that is stored / reduced / transposed goes through 4 KB of
+  // shared memory per warp (a 32 x 32 float32 chunk, 16-byte groups XOR-swizzled with the row:
+  // the SWIZZLE_128B pattern, conflict-free for the row writes of fused_eval, for the row
+  // reads of pass 1 and for the column reads of pass 2):
+  //   pass 1  lanes 8 i .. 8 i + 7 read one row as 8 float4 and store it as ONE full 128-byte
+  //           line (float32 output) / 64 contiguous bytes (bf16 plane).  Stored from the
+  //           accumulator layout (lane = row) every STG touches 32 different lines, half a
+  //           sector each: the epilogue warps of regions 1 and 2 then wait on the store queue
+  //           (long-scoreboard stalls on the address registers of in-flight stores,
+  //           profiles/r02_bench_step_ncu_v2.txt);
+  //   pass 2  lane c reads column c (32 LDS, one per row): the transpose that took 48 shuffles
+  //           and ~130 selects, and the column sum becomes 31 adds without any shuffle.
+  // The buffer lives behind the operand ring, which gives up one of its 7 stages for it in the
+  // bf16 / tf32 kernels (the hi/lo kernels have the room anyway).
+  static constexpr int kStageValue = AB_EP_COLSUM >= 0 ? AB_EP_COLSUM : (AB_EP_TPLANE >= 0 ? AB_EP_TPLANE : 0);
+  static __device__ __forceinline__ uint32_t st_off(int r, int g) { return (uint32_t)(r * 32 + ((g ^ (r & 7)) << 2)); }
+#if AB_EP_STAGED
+  __device__ __forceinline__ void fused_reduce(float (&x)[32], long long row, long long col0, int lane) const {
+    (void)x;
+    __syncwarp();
+    const long long row0 = row - lane;
+    {
+      float* dst = kStageValue == 0 ? p.C : p.out_ptr[kStageValue];
+      const long long rs = kStageValue == 0 ? p.c_rs : p.out_rs[kStageValue];
+      uint16_t* sp = static_cast<uint16_t*>(p.shadow[kStageValue]);
+      if (dst != nullptr || sp != nullptr) {
+        const int g = lane & 7;
+        const long long col = col0 + 4 * g;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + (lane >> 3);
+          const float4 v = lds128(stage + 4u * st_off(r, g));
+          const long long grow = row0 + r;
+          if (grow < p.M && col < p.N) {
+            if (dst != nullptr) __stcs(reinterpret_cast<float4*>(dst + grow * rs + col), v);
+            if (sp != nullptr) {
+              uint32_t h0, h1;
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v.y), "f"(v.x));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v.w), "f"(v.z));
+              __stcs(reinterpret_cast<uint2*>(sp + grow * p.shadow_pitch[kStageValue] + col), make_uint2(h0, h1));
+            }
+          }
+        }
+      }
+    }
+#if AB_EP_COLSUM >= 0 || AB_EP_TPLANE >= 0
+    {
+#if AB_EP_TPLANE >= 0
+      const bool want_t = p.shadow_t != nullptr;
+#else
+      const bool want_t = false;
+#endif
+      if (AB_EP_COLSUM >= 0 || want_t) {
+        float v[32];
+        const int cg = lane >> 2, cw = lane & 3;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = lds32(stage + 4u * (r * 32 + ((cg ^ (r & 7)) << 2) + cw));
+        const long long c = col0 + lane;
+#if AB_EP_COLSUM >= 0
+        {
+          // lane = column: its sum over the warp's 32 rows (rows / columns outside were staged
+          // as zeros).  float pairs under the fp32-faithful policy, a float32 tree otherwise
+          const long long rb = row >> 5;
+#if AB_EP_EXACT_SUMS
+          FF s = {v[0], 0.0f};
+#pragma unroll
+          for (int r = 1; r < 32; ++r) ff_add(s, v[r]);
+          const double tot = ff_double(s);
+#else
+          float t16[16];
+#pragma unroll
+          for (int r = 0; r < 16; ++r) t16[r] = __fadd_rn(v[2 * r], v[2 * r + 1]);
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+            for (int r = 0; r < w; ++r) t16[r] = __fadd_rn(t16[2 * r], t16[2 * r + 1]);
+          }
+          const double tot = (double)t16[0];
+#endif
+          if (rb * 32 < p.M && c < p.N) p.colsum_ws[rb * p.N + c] = tot;
+        }
+#endif
+#if AB_EP_TPLANE >= 0
+        if (want_t && c < p.N && row0 < p.M) {
+          uint16_t* dst = static_cast<uint16_t*>(p.shadow_t) + c * p.shadow_t_pitch + row0;
+          if (row0 + 32 <= p.M) {
+            uint32_t h[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[t]) : "f"(v[2 * t + 1]), "f"(v[2 * t]));
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              __stcs(reinterpret_cast<uint4*>(dst) + t, make_uint4(h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (row0 + i < p.M) {
+                uint16_t b;
+                asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(b) : "f"(v[i]));
+                dst[i] = b;
+              }
+          }
+        }
+#endif
+      }
+    }
+#endif
+    __syncwarp();  // the buffer is free for the next chunk's values
+  }
+#else
   __device__ __forceinline__ void fused_reduce(float (&x)[32], long long row, long long col0, int lane) const {
     (void)x; (void)row; (void)col0; (void)lane;
 #if AB_EP_TPLANE >= 0
@@ -648,6 +794,7 @@ struct EpilogueOut {
     }
 #endif
   }
+#endif  // AB_EP_STAGED
   __device__ __forceinline__ void finish_fullsum(const FF& acc, long long row, long long n0, int lane) const {
 #if AB_EP_FULLSUM >= 0
     double fs = ff_double(acc);
@@ -865,7 +1012,12 @@ __device__ __forceinline__ void gemm_1cta_body(const CUtensorMap& map_a0, const 
     const int half = (warp - kEpiWarp0) >> 2;    // which half of the columns
     const int half_n = p.block_n >> 1;
     const int nchunks = half_n >> 5;     // 32-column chunks: 1, 2 or 4
+#if AB_EP_STAGED
+    const EpilogueOut eo(p, smem_u32(smem + (size_t)p.stages * stage_bytes) +
+                                (uint32_t)((warp - kEpiWarp0) * kStageBytesPerWarp));
+#else
     const EpilogueOut eo(p);
+#endif
 #ifdef AB_EPILOGUE
     // the region's [1, 1] operands: read once per kernel (a global load per tile otherwise);
     // `lane` through a volatile asm: ptxas otherwise re-reads SR_TID (S2R, ~20 cycles on the
@@ -1129,7 +1281,12 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
     const int half = (warp - kEpiWarp0) >> 2;
     const int half_n = p.block_n >> 1;
     const int nchunks = half_n >> 5;
+#if AB_EP_STAGED
+    const EpilogueOut eo(p, smem_u32(smem + (size_t)p.stages * stage_bytes) +
+                                (uint32_t)((warp - kEpiWarp0) * kStageBytesPerWarp));
+#else
     const EpilogueOut eo(p);
+#endif
 #ifdef AB_EPILOGUE
     // the region's [1, 1] operands: read once per kernel (a global load per tile otherwise);
     // `lane` through a volatile asm: ptxas otherwise re-reads SR_TID (S2R, ~20 cycles on the
@@ -1195,6 +1352,9 @@ __device__ __forceinline__ void gemm_2cta_body(const CUtensorMap& map_a0, const 
 }
 
 
+#if AB_EP_STAGED
+extern "C" __global__ void ab_gemm_ep_staged_marker() {}  // tells gemm_run to reserve kStageBytes
+#endif
 #ifdef AB_EPILOGUE
 // NVRTC build: C-linkage entry points (the module is loaded by name from gemm_run)
 extern "C" __global__ void __launch_bounds__(kGemmThreads, 1)

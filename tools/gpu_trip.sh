@@ -18,11 +18,13 @@ case $sec in
   bench)
     timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_default.err; cut -c1-2500 gpurun_out/bench_default.json;;
   bench_quick)
-    timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench_quick rc=$?"; tail -3 gpurun_out/bench_quick.err; cut -c1-1800 gpurun_out/bench_quick.json;;
+    timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench_quick rc=$?"; tail -3 gpurun_out/bench_quick.err; python -c "import json;d=json.load(open('gpurun_out/bench_quick.json'));print(d['ms_per_step'], d['ms_per_step_eager'], [g['ms'] for g in d['gemm_nodes']], d['roofline']['frac'], d['clocks'], d['parity']['max_err'])";;
   bench_notplane)
     AB_EP_NO_TPLANE=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_notplane.json 2> gpurun_out/bench_notplane.err; echo "bench_notplane rc=$?"; tail -3 gpurun_out/bench_notplane.err; python -c "import json;d=json.load(open('gpurun_out/bench_notplane.json'));print(d['ms_per_step'], d['ms_per_step_eager'], [g['ms'] for g in d['gemm_nodes']])";;
   bench_tplane_r13)
     AB_EP_TPLANE_NO_FULLSUM=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_tplane_r13.json 2> gpurun_out/bench_tplane_r13.err; echo "bench_tplane_r13 rc=$?"; tail -3 gpurun_out/bench_tplane_r13.err; python -c "import json;d=json.load(open('gpurun_out/bench_tplane_r13.json'));print(d['ms_per_step'], d['ms_per_step_eager'], [g['ms'] for g in d['gemm_nodes']])";;
+  bench_nostaging)
+    AB_EP_NO_STAGING=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_nostaging.json 2> gpurun_out/bench_nostaging.err; echo "bench_nostaging rc=$?"; tail -3 gpurun_out/bench_nostaging.err; python -c "import json;d=json.load(open('gpurun_out/bench_nostaging.json'));print(d['ms_per_step'], d['ms_per_step_eager'], [g['ms'] for g in d['gemm_nodes']])";;
   bench_noc4)
     AB_GEMM_NO_CLUSTER4=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_noc4.json 2> gpurun_out/bench_noc4.err; echo "bench_noc4 rc=$?"; tail -3 gpurun_out/bench_noc4.err; cut -c1-1800 gpurun_out/bench_noc4.json;;
   bench_single)
