@@ -217,23 +217,6 @@ __device__ __forceinline__ void st8(float* q, const float (&v)[8], bool wide) {
 constexpr int kStageBytesPerWarp = 32 * 32 * 4;                     // one 32 x 32 float32 chunk
 constexpr int kStageBytes = (kEpiThreads / 32) * kStageBytesPerWarp;  // behind the operand ring
 
-// explicit shared-space accesses of the staging buffer: through a generic pointer kept in a
-// struct ptxas emitted generic LD.E / ST.E (address-space lookup per access, on the long
-// scoreboard) in the larger regions
-__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float lds32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-  return v;
-}
-
 struct EpilogueOut {
   const GemmParams& p;
   bool vec_ok, wide_out, wide_in;
@@ -410,11 +393,25 @@ struct EpilogueOut {
     return popc4((unsigned)AB_EP_ROWMASK & ((1u << k) - 1u));
   }
   struct ChunkPre {
+    // [M, N] reads of the next chunk.  Register-only builds: this lane's row, 32 columns.
+    // AB_EP_STAGED builds: the COALESCED layout -- q[i] = row 4 i + lane / 8 of the warp's 32,
+    // columns 4 (lane % 8) .. + 3, so that every LDG.128 covers four full 128-byte lines
+    // (read row-per-lane, an instruction touches 32 lines, 16 bytes of each: the loads then
+    // queue in the LSU like the stores did, profiles/r02_bench_step_ncu_v3.txt) -- and turned
+    // into the row-per-lane layout through the staging buffer at the top of fused_eval.
 #if AB_EP_CIN
+#if AB_EP_STAGED
+    float4 cinq[8];
+#else
     float cin[32];
 #endif
+#endif
 #if AB_EP_PRE_OP >= 0
+#if AB_EP_STAGED
+    float4 opq[8];
+#else
     float op[32];
+#endif
 #endif
     float vec[AB_EP_NOPS > 0 ? AB_EP_NOPS : 1];
     float rowv[kRowOps > 0 ? kRowOps : 1][32];
@@ -438,6 +435,33 @@ struct EpilogueOut {
         pre.vec[k] = (col0 + lane < p.N) ? __ldg(p.ep_ptr[k] + col0 + lane) : 0.0f;
       }
     }
+#if AB_EP_STAGED
+    {
+      const long long row0 = row - lane, col = col0 + 4 * (lane & 7);
+      (void)row0; (void)col;
+#if AB_EP_CIN
+      if (p.beta != 0.0f) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long grow = row0 + 4 * i + (lane >> 3);
+          pre.cinq[i] = (grow < p.M && col < p.N) ? __ldcs(reinterpret_cast<const float4*>(p.Cin + grow * p.cin_rs + col))
+                                                  : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+      }
+#endif
+#if AB_EP_PRE_OP >= 0
+      if (!sc.is[AB_EP_PRE_OP] && p.ep_cs[AB_EP_PRE_OP] == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long grow = row0 + 4 * i + (lane >> 3);
+          pre.opq[i] = (grow < p.M && col < p.N)
+                           ? __ldcs(reinterpret_cast<const float4*>(p.ep_ptr[AB_EP_PRE_OP] + grow * p.ep_rs[AB_EP_PRE_OP] + col))
+                           : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+      }
+#endif
+    }
+#else
 #if AB_EP_CIN
     if (live && p.beta != 0.0f) {
 #pragma unroll
@@ -454,7 +478,22 @@ struct EpilogueOut {
           ld8<true>(p.ep_ptr[AB_EP_PRE_OP] + r * p.ep_rs[AB_EP_PRE_OP] + col0 + j, *reinterpret_cast<float(*)[8]>(&pre.op[j]), wide);
     }
 #endif
+#endif
   }
+#if AB_EP_STAGED
+  // coalesced layout (ChunkPre) -> this lane's row, through the staging buffer
+  __device__ __forceinline__ void restage(const float4 (&q)[8], float (&out)[32], int lane) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sts128(stage + 4u * st_off(4 * i + (lane >> 3), lane & 7), q[i].x, q[i].y, q[i].z, q[i].w);
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 v = lds128(stage + 4u * st_off(lane, g));
+      out[4 * g] = v.x; out[4 * g + 1] = v.y; out[4 * g + 2] = v.z; out[4 * g + 3] = v.w;
+    }
+    __syncwarp();
+  }
+#endif
   // ---- one 32-column chunk of one accumulator row, in two parts -------------------------
   // fused_eval:   x[32] (raw accumulator values of columns col0 .. col0+31 of `row`) -> the
   //               region's values; consumes the read-ahead buffer `pre`, stores the outputs and
@@ -473,6 +512,23 @@ struct EpilogueOut {
     (void)lane; (void)fs;
 #if AB_EP_PRE_OP >= 0
     const bool pre_ok = live && !sc.is[AB_EP_PRE_OP] && p.ep_cs[AB_EP_PRE_OP] == 1;
+#endif
+#if AB_EP_STAGED
+#if AB_EP_CIN
+    float cin_l[32];
+    if (p.beta != 0.0f) restage(pre.cinq, cin_l, lane);
+#endif
+#if AB_EP_PRE_OP >= 0
+    float op_l[32];
+    if (!sc.is[AB_EP_PRE_OP] && p.ep_cs[AB_EP_PRE_OP] == 1) restage(pre.opq, op_l, lane);
+#endif
+#else
+#if AB_EP_CIN
+    const float (&cin_l)[32] = pre.cin;
+#endif
+#if AB_EP_PRE_OP >= 0
+    const float (&op_l)[32] = pre.op;
+#endif
 #endif
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
@@ -496,7 +552,7 @@ struct EpilogueOut {
         if (p.beta != 0.0f) {
 #if AB_EP_CIN
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] += p.beta * pre.cin[j + t];
+          for (int t = 0; t < 8; ++t) v[t] += p.beta * cin_l[j + t];
 #else
           float ci[8];
           ld8<true>(p.Cin + r * p.cin_rs + col, ci, wide_in);
@@ -510,7 +566,7 @@ struct EpilogueOut {
 #if AB_EP_PRE_OP >= 0
           if (k == AB_EP_PRE_OP && pre_ok) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) e[k][t] = pre.op[j + t];
+            for (int t = 0; t < 8; ++t) e[k][t] = op_l[j + t];
             continue;
           }
 #endif

@@ -34,6 +34,28 @@
 
 constexpr int kCellThreads = 384;
 constexpr int kCellEpiThreads = 256;
+// Each epilogue warp owns 4 KB of shared memory behind the operand ring (a 32 x 32 float32
+// block, 16-byte groups XOR-swizzled with the row as in the GEMM epilogue regions): x_t is read
+// and the new states / operand planes are written in a COALESCED layout (eight lanes per
+// 128-byte line) and turned to / from the accumulator layout (lane = row) through it.  In the
+// accumulator layout every 128-bit access touches 32 different lines: of the 80 such accesses
+// per thread and LSTM tile (32 x_t, 16 previous state, 16 ring, 16 plane) 64 are coalesced now.
+constexpr int kCellStageBytesPerWarp = 32 * 32 * 4;
+constexpr int kCellStageBytes = (kCellEpiThreads / 32) * kCellStageBytesPerWarp;
+__device__ __forceinline__ uint32_t cell_st_off(int r, int g) { return (uint32_t)(r * 32 + ((g ^ (r & 7)) << 2)) * 4u; }
+// coalesced layout (v[4 i .. 4 i + 3] = row 4 i + lane / 8, columns 4 (lane % 8) ..) -> lane = row
+__device__ __forceinline__ void cell_to_rows(float (&v)[32], uint32_t stg, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    sts128(stg + cell_st_off(4 * i + (lane >> 3), lane & 7), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 q = lds128(stg + cell_st_off(lane, g));
+    v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+  }
+  __syncwarp();
+}
 constexpr int CELL_UNITS = 64;                           // hidden units per tile
 constexpr int CELL_TILE_N = AB_CELL_GATES * CELL_UNITS;  // accumulator columns
 constexpr int CELL_KB = 32;                              // K elements (tf32) per 128-byte smem row
@@ -229,6 +251,7 @@ __device__ __forceinline__ void cell_scan_body(const CUtensorMap& map_h00, const
     uint32_t it = 0;
     const int q = warp & 3;
     const int s = (warp - 4) >> 2;
+    const uint32_t stg = smem_u32(smem + (size_t)p.stages * stage_bytes) + (uint32_t)((warp - 4) * kCellStageBytesPerWarp);
     for (long long t = 0; t < p.T; ++t) {
       const int set = (int)(t & 1);
       float* out_row[S];
@@ -253,19 +276,38 @@ __device__ __forceinline__ void cell_scan_body(const CUtensorMap& map_h00, const
         float acc[G][32];
         const long long uc = u0 + s * 32;
         const long long so = row * p.H + uc;
-        if (row < p.B) {
-          const float* xr = xt + row * p.x_rs + uc;
+        const long long row0 = row - lane;  // first row of this warp's 32
+        if (row0 < p.B) {
+          const float* xr0 = xt + row0 * p.x_rs + uc + 4 * (lane & 7);
 #pragma unroll
           for (int g = 0; g < G; ++g) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 xv = __ldcs(reinterpret_cast<const float4*>(xr + g * p.H + j));
-              acc[g][j] = xv.x; acc[g][j + 1] = xv.y; acc[g][j + 2] = xv.z; acc[g][j + 3] = xv.w;
+            for (int i = 0; i < 8; ++i) {
+              const long long r = 4 * i + (lane >> 3);
+              const float4 xv = (row0 + r < p.B) ? __ldcs(reinterpret_cast<const float4*>(xr0 + r * p.x_rs + g * p.H))
+                                                 : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+              acc[g][4 * i] = xv.x; acc[g][4 * i + 1] = xv.y; acc[g][4 * i + 2] = xv.z; acc[g][4 * i + 3] = xv.w;
             }
           }
-          // the previous states of this row/unit range are needed after the last segment
+          if (row < p.B) {
+            // the previous states of this row/unit range are needed after the last segment
 #pragma unroll
-          for (int k = 0; k < S; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(prev_row[k] + so));
+            for (int k = 0; k < S; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(prev_row[k] + so));
+            // x_t of this CTA's next tile: in L2 by the time its coalesced loads are issued
+            const long long nt = tile + n_groups;
+            if (nt < num_tiles) {
+              const float* xn = xt + ((nt / tiles_n) * TILE_M + (long long)rank * BLOCK_M + q * 32 + lane) * p.x_rs +
+                                (nt % tiles_n) * CELL_UNITS + s * 32;
+              if ((nt / tiles_n) * TILE_M + (long long)rank * BLOCK_M + q * 32 + lane < p.B) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + g * p.H));
+              }
+            }
+          }
+          // into the accumulator layout: the registers start out as this row's x_t gate
+          // pre-activations (the Gemm's "+ 1 * x_t", blas.py:984-1017)
+#pragma unroll
+          for (int g = 0; g < G; ++g) cell_to_rows(acc[g], stg, lane);
         } else {
 #pragma unroll
           for (int g = 0; g < G; ++g)
@@ -289,10 +331,12 @@ __device__ __forceinline__ void cell_scan_body(const CUtensorMap& map_h00, const
                          : "memory");
           }
         }
+        float extra[S > G ? S - G : 1][32];  // states beyond the gate count (their values cannot reuse acc)
+        (void)extra;
         if (row < p.B) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float pv[S][4], ov[S][4];
+            float pv[S][4];
 #pragma unroll
             for (int k = 0; k < S; ++k) {
               const float4 q4 = *reinterpret_cast<const float4*>(prev_row[k] + so + j);
@@ -306,27 +350,50 @@ __device__ __forceinline__ void cell_scan_body(const CUtensorMap& map_h00, const
 #pragma unroll
               for (int k = 0; k < S; ++k) pe[k] = pv[k][e];
               AB_CELL_EVAL(gv, pe, oe);  // the Elemwise nodes of the inner graph on pre = x_t + s_hs @ U
+              // the gate values of this unit are dead: the new states take their registers
 #pragma unroll
-              for (int k = 0; k < S; ++k) ov[k][e] = oe[k];
+              for (int k = 0; k < S; ++k) {
+                if (k < G) acc[k < G ? k : 0][j + e] = oe[k];
+                else extra[k >= G ? k - G : 0][j + e] = oe[k];
+              }
             }
+          }
+        }
+        if (row0 < p.B) {
+          // state by state through the shared block: rows out as full 128-byte lines; the state
+          // that feeds the next step's Gemm also as the hi/lo TF32 planes its TMA loads read
 #pragma unroll
-            for (int k = 0; k < S; ++k)
-              *reinterpret_cast<float4*>(out_row[k] + so + j) = make_float4(ov[k][0], ov[k][1], ov[k][2], ov[k][3]);
-            float hh[4], hl[4];
+          for (int k = 0; k < S; ++k) {
+            float (&val)[32] = k < G ? acc[k < G ? k : 0] : extra[k >= G ? k - G : 0];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float hn = ov[0][e];  // the new value of the state that feeds the next step's Gemm
+            for (int g = 0; g < 8; ++g)
+              sts128(stg + cell_st_off(lane, g), val[4 * g], val[4 * g + 1], val[4 * g + 2], val[4 * g + 3]);
+            __syncwarp();
+            const bool feeds = p.hs == k;
 #pragma unroll
-              for (int k = 1; k < S; ++k)
-                if (p.hs == k) hn = ov[k][e];
-              uint32_t hb, lb;
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(hn));
-              hh[e] = __uint_as_float(hb);
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(hn - hh[e]));
-              hl[e] = __uint_as_float(lb);
+            for (int i = 0; i < 8; ++i) {
+              const long long r = 4 * i + (lane >> 3);
+              const float4 v = lds128(stg + cell_st_off((int)r, lane & 7));
+              if (row0 + r < p.B) {
+                const long long off = (row0 + r) * p.H + uc + 4 * (lane & 7);
+                *reinterpret_cast<float4*>(out_row[k] + off) = v;
+                if (feeds) {
+                  const float hn[4] = {v.x, v.y, v.z, v.w};
+                  float hh[4], hl[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    uint32_t hb, lb;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(hn[e]));
+                    hh[e] = __uint_as_float(hb);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(hn[e] - hh[e]));
+                    hl[e] = __uint_as_float(lb);
+                  }
+                  *reinterpret_cast<float4*>(hp_hi + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+                  *reinterpret_cast<float4*>(hp_lo + off) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+                }
+              }
             }
-            *reinterpret_cast<float4*>(hp_hi + so + j) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<float4*>(hp_lo + so + j) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+            __syncwarp();
           }
         }
         // the new states of this tile are written: count the tile on its row block so that the

@@ -199,13 +199,13 @@ int cell_scan_launch(const void* kern1, const void* kern2, int gates, int states
     // step t+1 spins on the counters of step t): cooperative launch, grid <= the occupancy query
     p.b_tile_bytes = (tile_n / 2) * SW_BYTES;
     const int stage_bytes = 2 * (p.a_tile_bytes + p.b_tile_bytes);
-    p.stages = std::max(2, std::min(8, (kMaxSmem - 1024) / stage_bytes));
+    p.stages = std::max(2, std::min(8, (kMaxSmemGemm - 1024 - kCellStageBytes) / stage_bytes));
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_n >> 3) << 17) |
               ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
     if ((rc = make_map_f32(&mu[0], u_hi, H, (long long)gates * H, tile_n / 2))) return rc;
     if ((rc = make_map_f32(&mu[1], u_lo, H, (long long)gates * H, tile_n / 2))) return rc;
-    AB_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    AB_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemGemm));
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + kCellStageBytes;
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(kCellThreads);
     cfg.dynamicSmemBytes = smem;
@@ -236,13 +236,13 @@ int cell_scan_launch(const void* kern1, const void* kern2, int gates, int states
   }
   p.b_tile_bytes = tile_n * SW_BYTES;
   const int stage_bytes = 2 * (p.a_tile_bytes + p.b_tile_bytes);
-  p.stages = std::max(2, std::min(8, (kMaxSmem - 1024) / stage_bytes));
+  p.stages = std::max(2, std::min(8, (kMaxSmemGemm - 1024 - kCellStageBytes) / stage_bytes));
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_n >> 3) << 17) |
             ((uint32_t)(BLOCK_M >> 4) << 24);
   if ((rc = make_map_f32(&mu[0], u_hi, H, (long long)gates * H, tile_n))) return rc;
   if ((rc = make_map_f32(&mu[1], u_lo, H, (long long)gates * H, tile_n))) return rc;
-  AB_CUDA(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  AB_CUDA(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemGemm));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + kCellStageBytes;
   int per_sm = 0;
   AB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern1, kCellThreads, smem));
   if (per_sm < 1) return fail(AB_ERR_CUDA, "the Scan cell kernel does not fit on an SM");

@@ -141,6 +141,23 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// explicit shared-space accesses of the staging buffer: through a generic pointer kept in a
+// struct ptxas emitted generic LD.E / ST.E (address-space lookup per access, on the long
+// scoreboard) in the larger regions
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute UMMA::SmemDescriptor
 // field layout): start address >>4 in [0,14), LBO>>4 in [16,30), SBO>>4 in
 // [32,46), version=1 in [46,48), layout type SWIZZLE_128B=2 in [61,64).
