@@ -292,6 +292,10 @@ def compile_cubin(src: str, name: str = "ab_module") -> bytes:
     key = hashlib.sha256((lib.ab_version().decode() + src).encode()).hexdigest()[:40]
     path = os.path.join(cache_dir(), f"{name}_{key}.cubin")
     if os.path.exists(path):
+        try:
+            os.utime(path)  # mark as used: prune_cache() drops what no build touched
+        except OSError:
+            pass
         with open(path, "rb") as f:
             return f.read()
     out = C.c_void_p()
@@ -309,6 +313,23 @@ def compile_cubin(src: str, name: str = "ab_module") -> bytes:
         f.write(data)
     os.replace(tmp, path)
     return data
+
+
+def prune_cache(older_than: float) -> int:
+    """Delete cached cubins that were neither compiled nor used since ``older_than`` (a
+    time.time() value): every kernel revision leaves its cubins behind otherwise, and the
+    cache travels with the tree to the GPU box."""
+    n = 0
+    d = cache_dir()
+    for name in os.listdir(d):
+        path = os.path.join(d, name)
+        try:
+            if name.endswith(".cubin") and os.path.getmtime(path) < older_than:
+                os.remove(path)
+                n += 1
+        except OSError:
+            pass
+    return n
 
 
 _modules = {}

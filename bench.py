@@ -827,7 +827,7 @@ def main():
     # DRAM traffic of the dominant kernel, per launch, from the committed ncu --set full summary
     tsrc = None
     if spec["name"] == "mlp" and args.precision == "bf16":
-        tsrc = ("r01_gemm_fused_epilogue.txt", "ab_gemm_ep_2cta_f16")
+        tsrc = ("r02_bench_step_ncu_v4.txt", "ab_gemm_ep_2cta_f16")  # first launch of the capture: region 3
     elif spec["name"] == "logreg" and m["fused_regions_run"] > 0:
         tsrc = ("r01_rowfused_logreg.txt", "ab_rowfused")
     elif spec["name"] == "elemwise":

@@ -323,6 +323,33 @@ def test_mlp_gemm_epilogue_fusion_matches_node_by_node(rt, precision):
     _fused_vs_plain(single, plain, f"precision {precision}, single-node regions", exact_sums=precision == 0)
 
 
+@pytest.mark.parametrize("precision", [0, 2])
+@pytest.mark.parametrize("B", [1000, 777, 4099])
+def test_mlp_gemm_epilogue_fusion_ragged_batch(rt, precision, B):
+    """cfg3 graph with a batch that is not a multiple of the 32-row chunks / 128-row tiles of the
+    fused epilogue (last warp partly outside, last tile partly outside, odd K of the weight
+    gradients; B=4099 takes the 2-CTA kernel): staged row stores, column sums over partly
+    empty 32-row blocks and the transposed bf16 plane's ragged rows give the node-by-node
+    result."""
+    import os
+
+    prog, _, _ = load_case("cfg3_mlp")
+    rng = np.random.default_rng(B)
+    H = 256
+    ins = [rng.standard_normal((B, H)).astype("float32"), rng.standard_normal((B, H)).astype("float32"),
+           (rng.standard_normal((H, H)) / np.sqrt(H)).astype("float32"), (rng.standard_normal(H) * 0.1).astype("float32"),
+           (rng.standard_normal((H, H)) / np.sqrt(H)).astype("float32"), (rng.standard_normal(H) * 0.1).astype("float32")]
+    ex = rt(prog, precision=precision)
+    fused = ex(*ins)
+    assert ex.fused_regions_run == 3 and not any(f.broken for f in ex._fusions)
+    os.environ["AB_NO_GEMM_FUSE"] = os.environ["AB_NO_RED_FUSE"] = "1"
+    try:
+        plain = rt(prog, precision=precision)(*ins)
+    finally:
+        del os.environ["AB_NO_GEMM_FUSE"], os.environ["AB_NO_RED_FUSE"]
+    _fused_vs_plain(fused, plain, f"precision {precision}, B={B}", exact_sums=precision == 0)
+
+
 @pytest.mark.parametrize("T,B,H", [(12, 256, 128), (5, 384, 192), (4, 200, 64)])
 def test_lstm_medium_size_vs_oracle_and_graph_replay(rt, T, B, H):
     """cfg4 graph at medium sizes (a full 2-CTA tile, a ragged second 2-CTA tile, and a

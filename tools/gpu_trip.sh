@@ -53,6 +53,8 @@ case $sec in
     timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -q -p no:cacheprovider -k "lstm or scan or cfg4" > gpurun_out/pytest_scan.log 2>&1; echo "scantests rc=$?"; tail -6 gpurun_out/pytest_scan.log | cut -c1-300;;
   bench_lstm)
     timeout 600 python bench.py --workload lstm --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_lstm.json 2> gpurun_out/bench_lstm.err; echo "bench_lstm rc=$?"; tail -2 gpurun_out/bench_lstm.err; python -c "import json;d=json.load(open('gpurun_out/bench_lstm.json'));print(d['ms_per_step'], d['roofline'])";;
+  lstm_ncu)
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lstm_scan" -s 1 -c 1 -o gpurun_out/lstm_prof -f python bench.py --workload lstm --steps 1 --warmup 1 --no-also --no-cpu --no-e2e --no-truth --graph 0 > gpurun_out/lstm_ncu.log 2>&1; echo "lstm_ncu rc=$?"; tail -2 gpurun_out/lstm_ncu.log | cut -c1-200; ls -la gpurun_out/lstm_prof.ncu-rep;;
   bench_ncu)
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ab_gemm_ep|gemm_tcgen05" -s 8 -c 5 -o gpurun_out/bench_prof -f python bench.py --steps 1 --warmup 1 --no-also --no-cpu --no-e2e --no-truth --graph 0 > gpurun_out/bench_ncu.log 2>&1; echo "bench_ncu rc=$?"; tail -2 gpurun_out/bench_ncu.log | cut -c1-200; ls -la gpurun_out/bench_prof.ncu-rep;;
   multitest)
