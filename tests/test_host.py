@@ -256,6 +256,59 @@ def test_fused_kernel_sources_compile_for_sm100a():
             assert f.compile_all() == 1
 
 
+def test_gemm_epilogue_sources_follow_the_precision_policy(monkeypatch):
+    """The generated GEMM-epilogue module depends on the executor's product policy: float-pair
+    (float64-equivalent) sums and no transposed plane under the fp32-faithful default, float32
+    tree sums and the transposed bf16 plane of a value whose consumer contracts over its rows
+    under the bf16 policy; bias rows are recognised statically; the shared-memory staged
+    epilogue is the default and can be switched off.  The bf16-policy kernels of the cfg3
+    regions compile (NVRTC, no GPU) with at most a small stack frame (no spills in the chunk loop)."""
+    import re
+    import subprocess
+    import tempfile
+
+    from aesara_b200.runtime import lib
+    from aesara_b200.runtime.vm import ProgramExecutor
+    from tests._cases import load_case
+
+    prog, _, _ = load_case("cfg3_mlp")
+
+    def defines(src):
+        out = {}  # the generated block comes first; the kernel header repeats some as #ifndef defaults
+        for m in re.finditer(r"^#define (AB_EP_\w+) \(?(-?\d+)\)?$", src, re.M):
+            out.setdefault(m.group(1), m.group(2))
+        return out
+
+    for precision, exact, tplane in ((0, "1", "-1"), (1, "0", "-1"), (2, "0", "0")):
+        regions = sorted((f for f in ProgramExecutor(prog, precision=precision)._fusions), key=lambda f: f.g)
+        d = [defines(f.source()) for f in regions]
+        assert [x["AB_EP_EXACT_SUMS"] for x in d] == [exact] * 3
+        assert [x["AB_EP_TPLANE"] for x in d] == [tplane] * 3    # h, dout, dpre: each feeds a weight gradient
+        assert [x["AB_EP_STAGED"] for x in d] == ["1"] * 3
+        assert [x["AB_EP_ROWMASK"] for x in d] == ["1", "1", "0"]  # b1, b2 are [1, N] rows; region 3 reads h
+        assert [x["AB_EP_COLSUM"] for x in d] == ["-1", "0", "0"] and [x["AB_EP_FULLSUM"] for x in d] == ["-1", "1", "-1"]
+    monkeypatch.setenv("AB_EP_NO_STAGING", "1")
+    monkeypatch.setenv("AB_EP_NO_TPLANE", "1")
+    d = [defines(f.source()) for f in ProgramExecutor(prog, precision=2)._fusions]
+    assert {x["AB_EP_STAGED"] for x in d} == {"0"} and {x["AB_EP_TPLANE"] for x in d} == {"-1"}
+    monkeypatch.delenv("AB_EP_NO_STAGING")
+    monkeypatch.delenv("AB_EP_NO_TPLANE")
+    # no spills in the kernels the default bench launches (cuobjdump -res-usage of the cached cubin)
+    import shutil
+
+    if shutil.which("cuobjdump") is None:
+        return
+    for f in ProgramExecutor(prog, precision=2)._fusions:
+        cubin = lib.compile_cubin(f.source(), "gemm_ep")
+        with tempfile.NamedTemporaryFile(suffix=".cubin") as tf:
+            tf.write(cubin)
+            tf.flush()
+            out = subprocess.run(["cuobjdump", "-res-usage", tf.name], capture_output=True, text=True).stdout
+        m = re.search(r"Function ab_gemm_ep_2cta_f16:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+        assert m is not None, out[:400]
+        assert int(m.group(2)) <= 128, f"stack frame of the fused bf16 kernel: {m.group(0)}"  # was 184-264 with spills in the chunk loop
+
+
 def test_regions_can_be_switched_off(monkeypatch):
     from aesara_b200.runtime.vm import ProgramExecutor
     from tests._cases import load_case
