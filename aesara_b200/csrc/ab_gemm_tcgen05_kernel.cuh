@@ -604,8 +604,21 @@ struct EpilogueOut {
 #endif
 #if AB_EP_FULLSUM >= 0
 #if AB_EP_EXACT_SUMS
+        {
+          // four independent pairs per group of 8 (the single running pair was a chain of 8
+          // dependent TwoSums per group), folded into the thread's total once per group
+          FF q4[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) ff_add(fs, o[AB_EP_FULLSUM][t]);
+          for (int t = 0; t < 4; ++t) {
+            q4[t].hi = o[AB_EP_FULLSUM][t];
+            q4[t].lo = 0.0f;
+            ff_add(q4[t], o[AB_EP_FULLSUM][t + 4]);
+          }
+          ff_add(q4[0], q4[1]);
+          ff_add(q4[2], q4[3]);
+          ff_add(q4[0], q4[2]);
+          ff_add(fs, q4[0]);
+        }
 #else
         {
           // reduced-precision products (tf32 / bf16 operands): 8 values summed as a float32
@@ -691,10 +704,24 @@ struct EpilogueOut {
           // as zeros).  float pairs under the fp32-faithful policy, a float32 tree otherwise
           const long long rb = row >> 5;
 #if AB_EP_EXACT_SUMS
-          FF s = {v[0], 0.0f};
+          // a tree of float pairs (depth 5): one running pair would be a chain of 31 dependent
+          // TwoSums per lane
+          FF tp[16];
 #pragma unroll
-          for (int r = 1; r < 32; ++r) ff_add(s, v[r]);
-          const double tot = ff_double(s);
+          for (int r = 0; r < 16; ++r) {
+            tp[r].hi = v[2 * r];
+            tp[r].lo = 0.0f;
+            ff_add(tp[r], v[2 * r + 1]);
+          }
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+            for (int r = 0; r < w; ++r) {
+              tp[r] = tp[2 * r];
+              ff_add(tp[r], tp[2 * r + 1]);
+            }
+          }
+          const double tot = ff_double(tp[0]);
 #else
           float t16[16];
 #pragma unroll

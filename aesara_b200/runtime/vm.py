@@ -14,6 +14,8 @@ implementation raises ``NotImplementedError`` at construction time.
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -199,7 +201,16 @@ class ProgramExecutor:
 
         self._fusions = RowFusion.detect(program, self._destroys)
         taken = {i for f in self._fusions for i in f.members}
-        gemm_regions = GemmEpilogueFusion.detect(program, self._destroys, taken)
+        # GEMM-epilogue regions under the reduced-precision product policies only.  The
+        # fp32-faithful kernels (hi/lo operands, K segments folded into 128 accumulator
+        # registers per thread) have no registers left for a region's epilogue: measured on
+        # cfg3, 58.8 ms with regions against 49.3 ms node by node (the Elemwise / CAReduce
+        # kernels of the unfused graph run at the HBM roof and cost 2.5 ms of that;
+        # profiles/r02_bench_fp32_regions.json).  AB_GEMM_FUSE_FP32=1 keeps them (tests).
+        if self.precision == 0 and not os.environ.get("AB_GEMM_FUSE_FP32"):
+            gemm_regions = []
+        else:
+            gemm_regions = GemmEpilogueFusion.detect(program, self._destroys, taken)
         for f in gemm_regions:
             f.exact_sums = self.precision == 0
             f.planes = self.precision == 2

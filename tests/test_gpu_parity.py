@@ -281,7 +281,7 @@ def _fused_vs_plain(fused, plain, what, exact_sums=True):
 
 
 @pytest.mark.parametrize("precision", [0, 2])
-def test_mlp_gemm_epilogue_fusion_matches_node_by_node(rt, precision):
+def test_mlp_gemm_epilogue_fusion_matches_node_by_node(rt, precision, monkeypatch):
     """cfg3 graph, B=1024, H=512: the three Gemm/Dot22 -> Elemwise pairs run as fused
     tcgen05 kernels (runtime/gemmfuse.py) and give the node-by-node result (the epilogue
     evaluates the same scalar expression on the same fp32 values; the bf16 shadow plane it
@@ -289,6 +289,10 @@ def test_mlp_gemm_epilogue_fusion_matches_node_by_node(rt, precision):
     import os
 
     prog, _, _ = load_case("cfg3_mlp")
+    if precision == 0:
+        # off by default under the fp32-faithful policy (slower than node by node there)
+        assert not any(type(f).__name__ == "GemmEpilogueFusion" for f in rt(prog, precision=0)._fusions)
+        monkeypatch.setenv("AB_GEMM_FUSE_FP32", "1")
     rng = np.random.default_rng(21)
     B, H = 1024, 512
     ins = [rng.standard_normal((B, H)).astype("float32"), rng.standard_normal((B, H)).astype("float32"),
@@ -325,7 +329,7 @@ def test_mlp_gemm_epilogue_fusion_matches_node_by_node(rt, precision):
 
 @pytest.mark.parametrize("precision", [0, 2])
 @pytest.mark.parametrize("B", [1000, 777, 4099])
-def test_mlp_gemm_epilogue_fusion_ragged_batch(rt, precision, B):
+def test_mlp_gemm_epilogue_fusion_ragged_batch(rt, precision, B, monkeypatch):
     """cfg3 graph with a batch that is not a multiple of the 32-row chunks / 128-row tiles of the
     fused epilogue (last warp partly outside, last tile partly outside, odd K of the weight
     gradients; B=4099 takes the 2-CTA kernel): staged row stores, column sums over partly
@@ -334,6 +338,8 @@ def test_mlp_gemm_epilogue_fusion_ragged_batch(rt, precision, B):
     import os
 
     prog, _, _ = load_case("cfg3_mlp")
+    if precision == 0:
+        monkeypatch.setenv("AB_GEMM_FUSE_FP32", "1")
     rng = np.random.default_rng(B)
     H = 256
     ins = [rng.standard_normal((B, H)).astype("float32"), rng.standard_normal((B, H)).astype("float32"),

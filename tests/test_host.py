@@ -206,7 +206,10 @@ def test_fusion_regions_detected_on_the_committed_programs():
     assert all(not ex._free_after[i] for i in f.members if i != f.last)  # operands stay alive
 
     prog, _, _ = load_case("cfg3_mlp")
-    ex = ProgramExecutor(prog)
+    # fp32-faithful default: no GEMM-epilogue regions (the hi/lo kernels have no registers for
+    # them: slower than node by node), the loss's Sqr -> Sum still runs as one reduction
+    assert sorted(type(f).__name__ for f in ProgramExecutor(prog)._fusions) == ["ReducePreFusion"]
+    ex = ProgramExecutor(prog, precision=2)
     kinds = sorted(type(f).__name__ for f in ex._fusions)
     assert kinds == ["GemmEpilogueFusion"] * 3  # Sqr -> Sum now lives inside the second region
     regions = sorted((f for f in ex._fusions), key=lambda f: f.g)
@@ -230,7 +233,7 @@ def test_fusion_regions_detected_on_the_committed_programs():
     import os
     os.environ["AB_GEMM_FUSE_SINGLE"] = "1"
     try:
-        ex1 = ProgramExecutor(prog)
+        ex1 = ProgramExecutor(prog, precision=2)
     finally:
         del os.environ["AB_GEMM_FUSE_SINGLE"]
     kinds = sorted(type(f).__name__ for f in ex1._fusions)
@@ -250,7 +253,7 @@ def test_fused_kernel_sources_compile_for_sm100a():
 
     for name in ("cfg5_logreg", "cfg3_mlp", "careduce_big_1d"):
         prog, _, _ = load_case(name)
-        ex = ProgramExecutor(prog)
+        ex = ProgramExecutor(prog, precision=2 if name == "cfg3_mlp" else 0)
         assert ex._fusions
         for f in ex._fusions:
             assert f.compile_all() == 1
@@ -272,6 +275,7 @@ def test_gemm_epilogue_sources_follow_the_precision_policy(monkeypatch):
     from tests._cases import load_case
 
     prog, _, _ = load_case("cfg3_mlp")
+    monkeypatch.setenv("AB_GEMM_FUSE_FP32", "1")  # regions are off by default under the fp32-faithful policy
 
     def defines(src):
         out = {}  # the generated block comes first; the kernel header repeats some as #ifndef defaults

@@ -23,6 +23,11 @@ case $sec in
     AB_EP_NO_TPLANE=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_notplane.json 2> gpurun_out/bench_notplane.err; echo "bench_notplane rc=$?"; tail -3 gpurun_out/bench_notplane.err; python -c "import json;d=json.load(open('gpurun_out/bench_notplane.json'));print(d['ms_per_step'], d['ms_per_step_eager'], [g['ms'] for g in d['gemm_nodes']])";;
   bench_tplane_r13)
     AB_EP_TPLANE_NO_FULLSUM=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_tplane_r13.json 2> gpurun_out/bench_tplane_r13.err; echo "bench_tplane_r13 rc=$?"; tail -3 gpurun_out/bench_tplane_r13.err; python -c "import json;d=json.load(open('gpurun_out/bench_tplane_r13.json'));print(d['ms_per_step'], d['ms_per_step_eager'], [g['ms'] for g in d['gemm_nodes']])";;
+  bench_fp32)
+    for v in ${FP32_VARIANTS:-default}; do
+      case $v in default) envs="";; regions) envs="AB_GEMM_FUSE_FP32=1";; nostaging) envs="AB_GEMM_FUSE_FP32=1 AB_EP_NO_STAGING=1";; nofuse) envs="AB_NO_GEMM_FUSE=1";; esac
+      env $envs timeout 400 python bench.py --gpus 1 --steps 4 --warmup 3 --precision fp32 --no-also --no-cpu --no-e2e --no-truth > gpurun_out/bench_fp32_$v.json 2> gpurun_out/bench_fp32_$v.err; echo "bench_fp32 $v rc=$?"; python -c "import json;d=json.load(open('gpurun_out/bench_fp32_$v.json'));print(d['ms_per_step'], d['ms_per_step_eager'], [g['ms'] for g in d['gemm_nodes']], d['device_ms'])"
+    done;;
   bench_nostaging)
     AB_EP_NO_STAGING=1 timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-cpu --no-e2e > gpurun_out/bench_nostaging.json 2> gpurun_out/bench_nostaging.err; echo "bench_nostaging rc=$?"; tail -3 gpurun_out/bench_nostaging.err; python -c "import json;d=json.load(open('gpurun_out/bench_nostaging.json'));print(d['ms_per_step'], d['ms_per_step_eager'], [g['ms'] for g in d['gemm_nodes']])";;
   bench_noc4)

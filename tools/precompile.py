@@ -14,6 +14,18 @@ from tests._cases import case_names, load_case
 
 def main():
     t = time.time()
+    had = os.environ.get("AB_GEMM_FUSE_FP32")
+    os.environ["AB_GEMM_FUSE_FP32"] = "1"  # also the (opt-in) regions of the fp32-faithful kernels: tests launch them
+    try:
+        _compile_all(t)
+    finally:
+        if had is None:
+            del os.environ["AB_GEMM_FUSE_FP32"]
+        else:
+            os.environ["AB_GEMM_FUSE_FP32"] = had
+
+
+def _compile_all(t):
     exs = [ProgramExecutor(load_case(n)[0]) for n in case_names()]
     # GEMM-epilogue regions are generated per precision policy (float-pair vs float32-tree sums)
     for n in case_names():
