@@ -313,6 +313,30 @@ def test_gemm_epilogue_sources_follow_the_precision_policy(monkeypatch):
         assert int(m.group(2)) <= 128, f"stack frame of the fused bf16 kernel: {m.group(0)}"  # was 184-264 with spills in the chunk loop
 
 
+def test_staging_swizzle_is_conflict_free():
+    """The shared-memory chunk of the fused GEMM epilogue / Scan cell epilogue (st_off in
+    csrc/ab_gemm_tcgen05_kernel.cuh, cell_st_off in ab_scan_cell_kernel.cuh): 32 rows x 32 floats,
+    16-byte group g of row r stored at group g ^ (r & 7).  Restated here: every access pattern the
+    kernels use touches each of the 32 banks at most once per shared-memory wavefront (128-bit
+    accesses are served a quarter warp = 8 lanes at a time, 32-bit accesses a whole warp)."""
+    def word(r, g, w=0):  # 32-bit word index of element 4 g + w of row r
+        return r * 32 + ((g ^ (r & 7)) << 2) + w
+
+    def banks128(addrs):  # a quarter warp of 128-bit accesses: 8 lanes x 4 consecutive banks
+        return sorted(b for a in addrs for b in range(a % 32, a % 32 + 4))
+
+    for g in range(8):  # fused_eval / cell epilogue: lane = row writes (reads) its group g
+        for q in range(4):
+            assert banks128([word(r, g) for r in range(8 * q, 8 * q + 8)]) == list(range(32))
+    for i in range(8):  # pass 1 / restage: lanes 8 k .. 8 k + 7 handle row 4 i + k, lane % 8 = group
+        for k in range(4):
+            assert banks128([word(4 * i + k, g) for g in range(8)]) == list(range(32))
+    for r in range(32):  # pass 2: lane c reads column c of row r (one 32-bit word per lane)
+        assert sorted(word(r, c >> 2, c & 3) % 32 for c in range(32)) == list(range(32))
+    # and the map is a bijection on the 1024 words of the chunk
+    assert sorted(word(r, g, w) for r in range(32) for g in range(8) for w in range(4)) == list(range(1024))
+
+
 def test_regions_can_be_switched_off(monkeypatch):
     from aesara_b200.runtime.vm import ProgramExecutor
     from tests._cases import load_case
