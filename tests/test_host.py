@@ -337,6 +337,36 @@ def test_staging_swizzle_is_conflict_free():
     assert sorted(word(r, g, w) for r in range(32) for g in range(8) for w in range(4)) == list(range(1024))
 
 
+def test_kernel_cache_is_thread_safe_and_prunable(tmp_path, monkeypatch):
+    """runtime/lib.py: several threads compiling the same (and different) sources into one cache
+    directory end with one valid cubin per source (the probe / temporary files of concurrent
+    callers used to collide and send one of them to ~/.cache); ``prune_cache`` drops what no
+    build has touched since a given time and keeps what was used."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
+    from aesara_b200.runtime import lib
+
+    monkeypatch.setenv("AESARA_B200_CACHE", str(tmp_path))
+    srcs = [f'extern "C" __global__ void k{i}(float* p) {{ p[threadIdx.x] = {i}.0f; }}' for i in range(3)]
+    with ThreadPoolExecutor(6) as pool:
+        blobs = list(pool.map(lambda s: lib.compile_cubin(s, "t"), srcs * 4))
+    assert lib.cache_dir() == str(tmp_path)
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".cubin"))
+    assert len(files) == 3 and not [f for f in os.listdir(tmp_path) if ".tmp" in f or f.startswith(".w")]
+    assert all(b[:4] == b"\x7fELF" for b in blobs) and len({bytes(b) for b in blobs}) == 3
+    old = time.time() - 3600
+    for f in files[:2]:
+        os.utime(os.path.join(tmp_path, f), (old, old))
+    lib.compile_cubin(srcs[0], "t")  # a cache hit marks the file as used
+    cutoff = time.time() - 60
+    dropped = lib.prune_cache(cutoff)
+    left = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert dropped >= 1 and len(left) == 3 - dropped
+    for s in srcs:  # whatever was dropped is simply compiled again
+        assert lib.compile_cubin(s, "t")[:4] == b"\x7fELF"
+
+
 def test_regions_can_be_switched_off(monkeypatch):
     from aesara_b200.runtime.vm import ProgramExecutor
     from tests._cases import load_case
